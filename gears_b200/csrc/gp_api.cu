@@ -1,0 +1,791 @@
+// gp_api.cu — host side of libgears_physics_cuda.so: the C ABI declared in include/gears_physics_cuda.h.
+// Owns all device memory, enqueues the kernels of gp_kernels.cuh on one non-blocking stream per handle.
+// No CPU fallback: every entry point fails with GP_ERR_NO_DEVICE / GP_ERR_CUDA if the device path is unusable.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gears_physics_cuda.h"
+#include "gp_kernels.cuh"
+#include "gp_multi.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+using namespace gp;
+
+static std::string g_create_error;
+
+struct gp_world {
+    gp_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+
+    uint32_t n = 0, cap = 0;
+    uint64_t pair_cap = 0;
+    bool uploaded = false;
+
+    // body state (SoA of float4)
+    float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr};
+    float4 *A = nullptr, *Lo = nullptr, *Hi = nullptr;
+    int cur = 0;
+    float* ext = nullptr;
+    // broad phase
+    float4 *box = nullptr, *sbox = nullptr;
+    uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr};
+    uint32_t* hist = nullptr;
+    uint32_t* LB = nullptr;
+    uint32_t lb_cap = 0;
+    Gap* gaps = nullptr;
+    uint32_t gap_cap = 0;
+    GridParams grid{};
+    int key_bits = 1;
+    float thr = 0.f, cell = 0.f;
+    // chains + sweep
+    uint32_t *chain_cnt = nullptr, *offs = nullptr, *tile_sums = nullptr;
+    uint4* pairs = nullptr;
+    unsigned long long* adj = nullptr;
+    uint32_t* pending = nullptr;
+    uint32_t* frontier[2] = {nullptr, nullptr};
+    uint32_t* heavy = nullptr;
+    uint32_t heavy_cap = 0;
+    int sweep_grid = 0;
+    // control
+    Ctl *ctl = nullptr, *ctl_snap = nullptr;
+    Ctl* h_ctl = nullptr;  // pinned
+    uint32_t *d_small = nullptr;  // scratch: ext histogram (EXT_BUCKETS) + bounds (6)
+    // staging for host-layout arrays
+    unsigned char* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    gp_step_stats last{};
+    uint64_t steps_total = 0;
+    uint32_t last_np = 0;
+    std::string err;
+    uint64_t launches = 0;
+    gp_multi* multi = nullptr;
+};
+
+static gp_status fail(gp_world* w, gp_status s, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (w)
+        w->err = buf;
+    else
+        g_create_error = buf;
+    return s;
+}
+
+#define CK(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(w, GP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t count) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+static void free_all(gp_world* w) {
+    void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A,     w->Lo,        w->Hi,     w->ext,
+                    w->box,    w->sbox,  w->key[0],     w->key[1],     w->val[0], w->val[1],    w->hist,   w->LB,
+                    w->gaps,   w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
+                    w->frontier[0], w->frontier[1], w->heavy, w->ctl, w->ctl_snap, w->d_small, w->stage};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (w->h_ctl) cudaFreeHost(w->h_ctl);
+}
+
+extern "C" int32_t gp_abi_version(void) { return GP_ABI_VERSION; }
+
+extern "C" const char* gp_last_error(const gp_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void gp_damping_factors(float dt, float* out3) {
+    // platform libm expf == what Rust's f32::exp lowers to on linux-gnu (physics.rs:437)
+    out3[0] = expf(-1.6f * dt);
+    out3[1] = expf(-1.8f * dt);
+    out3[2] = expf(-3.5f * dt);
+}
+
+extern "C" void* gp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void gp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" uint64_t gp_kernel_launches(const gp_world* w) { return w ? w->launches : 0; }
+
+extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
+    if (!out) return fail(nullptr, GP_ERR_BAD_ARG, "gp_create: out is NULL");
+    *out = nullptr;
+    gp_config c{};
+    c.struct_size = sizeof(gp_config);
+    if (cfg) {
+        if (cfg->struct_size == 0 || cfg->struct_size > sizeof(gp_config))
+            return fail(nullptr, GP_ERR_BAD_ARG, "gp_create: bad gp_config.struct_size %u", cfg->struct_size);
+        memcpy(&c, cfg, cfg->struct_size);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, GP_ERR_NO_DEVICE, "gp_create: no CUDA device (this library has no CPU path)");
+    if (c.device < 0 || c.device >= ndev) return fail(nullptr, GP_ERR_BAD_ARG, "gp_create: device %d of %d", c.device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, GP_ERR_NO_DEVICE, "gp_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                    c.device, prop.major, prop.minor);
+    gp_world* w = new gp_world();
+    w->cfg = c;
+    w->device = c.device;
+    w->sm_count = prop.multiProcessorCount;
+    gp_status rs = GP_OK;
+    do {
+        if (cudaSetDevice(w->device) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
+        if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
+        if (dmalloc(&w->ctl, 1) || dmalloc(&w->ctl_snap, 1) || dmalloc(&w->d_small, EXT_BUCKETS + 8)) { rs = GP_ERR_CUDA; break; }
+        if (cudaMallocHost((void**)&w->h_ctl, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
+        if (cudaMemset(w->ctl, 0, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, 256, 0) != cudaSuccess || occ < 1) {
+            rs = GP_ERR_NO_DEVICE;  // no kernel image for this device
+            break;
+        }
+        w->sweep_grid = std::min(occ, 4) * w->sm_count;
+    } while (0);
+    if (rs != GP_OK) {
+        fail(nullptr, rs, "gp_create: CUDA setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        free_all(w);
+        delete w;
+        return rs;
+    }
+    *out = w;
+    return GP_OK;
+}
+
+extern "C" void gp_destroy(gp_world* w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->st) cudaStreamSynchronize(w->st);
+    if (w->multi) gp_multi_destroy(w->multi);
+    free_all(w);
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
+    if (w->st) cudaStreamDestroy(w->st);
+    delete w;
+}
+
+static gp_status ensure_stage(gp_world* w, size_t bytes) {
+    if (bytes <= w->stage_bytes) return GP_OK;
+    CK(dmalloc(&w->stage, bytes));
+    w->stage_bytes = bytes;
+    return GP_OK;
+}
+
+static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
+    CK(dmalloc(&w->P[0], cap));
+    CK(dmalloc(&w->P[1], cap));
+    CK(dmalloc(&w->V[0], cap));
+    CK(dmalloc(&w->V[1], cap));
+    CK(dmalloc(&w->A, cap));
+    CK(dmalloc(&w->Lo, cap));
+    CK(dmalloc(&w->Hi, cap));
+    CK(dmalloc(&w->ext, cap));
+    CK(dmalloc(&w->box, 2 * (size_t)cap));
+    CK(dmalloc(&w->sbox, 2 * (size_t)cap));
+    for (int i = 0; i < 2; ++i) {
+        CK(dmalloc(&w->key[i], cap));
+        CK(dmalloc(&w->val[i], cap));
+    }
+    CK(dmalloc(&w->hist, (size_t)RS_RADIX * (size_t)w->sm_count * 4));
+    CK(dmalloc(&w->chain_cnt, (size_t)cap + 1));
+    CK(dmalloc(&w->offs, (size_t)cap + 2));
+    CK(dmalloc(&w->tile_sums, (size_t)cdiv(cap, SC_TILE) + 1));
+    w->cap = cap;
+    return GP_OK;
+}
+
+static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
+    if (pair_cap > 0x7fff0000ull) pair_cap = 0x7fff0000ull;
+    CK(dmalloc(&w->pairs, pair_cap));
+    CK(dmalloc(&w->adj, 2 * pair_cap));
+    CK(dmalloc(&w->pending, pair_cap));
+    CK(dmalloc(&w->frontier[0], pair_cap));
+    CK(dmalloc(&w->frontier[1], pair_cap));
+    w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);
+    CK(dmalloc(&w->heavy, w->heavy_cap));
+    w->pair_cap = pair_cap;
+    return GP_OK;
+}
+
+// Choose the extent threshold / cell size and the grid from what was uploaded.
+static gp_status setup_grid(gp_world* w) {
+    const uint32_t n = w->n;
+    uint32_t* d_hist = w->d_small;
+    uint32_t* d_bounds = w->d_small + EXT_BUCKETS;
+    uint32_t h_small[EXT_BUCKETS + 8];
+    CK(cudaMemsetAsync(d_hist, 0, EXT_BUCKETS * sizeof(uint32_t), w->st));
+    if (n) {
+        k_ext_hist<<<std::min<uint32_t>(cdiv(n, 256), 1024), 256, 0, w->st>>>(n, w->ext, d_hist);
+        w->launches++;
+    }
+    CK(cudaMemcpyAsync(h_small, d_hist, EXT_BUCKETS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    const uint32_t max_big = w->cfg.max_big ? w->cfg.max_big : 64u;
+    // smallest bucket edge that leaves at most max_big bodies above it
+    uint64_t above = 0;
+    int b = EXT_BUCKETS - 1;
+    for (; b > 0; --b) {
+        if (above + h_small[b] > max_big) break;
+        above += h_small[b];
+    }
+    // b = highest bucket that must stay in the grid; its upper edge bounds every grid-class extent
+    float thr = ext_bucket_edge(b);
+    if (b == EXT_BUCKETS - 1) thr = INFINITY;
+    w->thr = thr;
+    // classify + bounds of grid-class centres
+    uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, w->st));
+    if (n) {
+        k_classify<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->ext, thr, w->P[w->cur], w->Lo, w->Hi, w->A, d_bounds);
+        w->launches++;
+    }
+    uint32_t hb[6];
+    CK(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        if (hb[k] == 0xffffffffu || hb[3 + k] == 0u) {
+            lo[k] = 0.f, hi[k] = 1.f;  // no grid-class body
+        } else {
+            lo[k] = ord2f(hb[k]), hi[k] = ord2f(hb[3 + k]);
+        }
+    }
+    const gp_config& c = w->cfg;
+    const bool user_bounds = !(c.grid_min[0] == 0 && c.grid_min[1] == 0 && c.grid_min[2] == 0 && c.grid_max[0] == 0 &&
+                               c.grid_max[1] == 0 && c.grid_max[2] == 0);
+    if (user_bounds)
+        for (int k = 0; k < 3; ++k) lo[k] = c.grid_min[k], hi[k] = c.grid_max[k];
+    const float base = isfinite(thr) ? thr : 1.0f;  // typical body extent
+    float m_max = c.margin_max > 0 ? c.margin_max : 0.25f * base;
+    float m_init = c.margin_init > 0 ? c.margin_init : 0.05f * base;
+    if (m_init > m_max) m_init = m_max;
+    float maxabs = 0.f;
+    for (int k = 0; k < 3; ++k) maxabs = fmaxf(maxabs, fmaxf(fabsf(lo[k]), fabsf(hi[k])));
+    // the 27-neighbourhood needs cell >= extent + 2 m_max; slack covers rounding of centre / cell index
+    float need = (base + 2.0f * m_max) * 1.002f + 8.0f * maxabs * 1.2e-7f;
+    float cell = c.cell_size > need ? c.cell_size : need;
+    // grow the cell until the table fits 2^28 cells
+    int dx, dy, dz;
+    for (;;) {
+        double ex[3];
+        for (int k = 0; k < 3; ++k) ex[k] = floor(((double)hi[k] - (double)lo[k]) / cell) + 1.0 + 4.0 + 2.0;
+        if (ex[0] * ex[1] * ex[2] <= 268435456.0 && ex[0] < 2e9 && ex[1] < 2e9 && ex[2] < 2e9) {
+            dx = (int)ex[0], dy = (int)ex[1], dz = (int)ex[2];
+            break;
+        }
+        cell *= 1.25f;
+    }
+    w->cell = cell;
+    w->grid.inv_cell = 1.0f / cell;
+    w->grid.ox = lo[0] - 2.0f * cell, w->grid.oy = lo[1] - 2.0f * cell, w->grid.oz = lo[2] - 2.0f * cell;
+    w->grid.dx = dx, w->grid.dy = dy, w->grid.dz = dz;
+    w->grid.ncells = (uint32_t)dx * (uint32_t)dy * (uint32_t)dz;
+    int bits = 1;
+    while ((1ull << bits) <= (uint64_t)w->grid.ncells) ++bits;
+    w->key_bits = bits;
+    if (w->grid.ncells + 2 > w->lb_cap) {
+        CK(dmalloc(&w->LB, (size_t)w->grid.ncells + 2));
+        w->lb_cap = w->grid.ncells + 2;
+        w->gap_cap = w->grid.ncells / GAP_DIRECT + 1024;
+        CK(dmalloc(&w->gaps, w->gap_cap));
+    }
+    // control block
+    Ctl hc{};
+    hc.margin = m_init;
+    hc.margin_min = m_init;
+    hc.margin_max = m_max;
+    CK(cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    w->steps_total = 0;
+    return GP_OK;
+}
+
+extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const float* rot4, const float* scale3,
+                               const float* vel3, const float* acc3, const float* box_min3, const float* box_max3,
+                               const float* mass, const float* restitution, const uint8_t* is_static,
+                               const uint32_t* entity, const uint32_t* rank) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (n && (!pos3 || !vel3 || !box_min3 || !box_max3 || !mass || !restitution || !is_static))
+        return fail(w, GP_ERR_BAD_ARG, "gp_upload: a required array is NULL");
+    if (n >= 0x7fffffffu) return fail(w, GP_ERR_BAD_ARG, "gp_upload: n too large");
+    CK(cudaSetDevice(w->device));
+    if (w->cfg.max_bodies && n > w->cfg.max_bodies)
+        return fail(w, GP_ERR_CAPACITY, "gp_upload: %u bodies > max_bodies %u", n, w->cfg.max_bodies);
+    const uint32_t want = std::max<uint32_t>(w->cfg.max_bodies, std::max<uint32_t>(n, 1u));
+    if (want > w->cap) {
+        gp_status s = alloc_bodies(w, want);
+        if (s != GP_OK) return s;
+    }
+    uint64_t want_pairs = w->cfg.max_pairs ? w->cfg.max_pairs : std::max<uint64_t>(16ull * w->cap, 1ull << 20);
+    if (want_pairs > w->pair_cap) {
+        gp_status s = alloc_pairs(w, want_pairs);
+        if (s != GP_OK) return s;
+    }
+    w->n = n;
+    w->cur = 0;
+    // stage host-layout arrays on the device, then pack
+    const size_t f = sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_pos = take(3 * f * n), o_rot = take(4 * f * n), o_scale = take(3 * f * n), o_vel = take(3 * f * n),
+                 o_acc = take(3 * f * n), o_bmin = take(3 * f * n), o_bmax = take(3 * f * n), o_mass = take(f * n),
+                 o_rest = take(f * n), o_stat = take(n), o_ent = take(4 * (size_t)n), o_rank = take(4 * (size_t)n);
+    gp_status s = ensure_stage(w, off + 256);
+    if (s != GP_OK) return s;
+    unsigned char* sg = w->stage;
+    auto h2d = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        if (!src || !bytes) return cudaSuccess;
+        return cudaMemcpyAsync(sg + o, src, bytes, cudaMemcpyHostToDevice, w->st);
+    };
+    CK(h2d(o_pos, pos3, 3 * f * n));
+    CK(h2d(o_rot, rot4, 4 * f * n));
+    CK(h2d(o_scale, scale3, 3 * f * n));
+    CK(h2d(o_vel, vel3, 3 * f * n));
+    CK(h2d(o_acc, acc3, 3 * f * n));
+    CK(h2d(o_bmin, box_min3, 3 * f * n));
+    CK(h2d(o_bmax, box_max3, 3 * f * n));
+    CK(h2d(o_mass, mass, f * n));
+    CK(h2d(o_rest, restitution, f * n));
+    CK(h2d(o_stat, is_static, n));
+    CK(h2d(o_ent, entity, 4 * (size_t)n));
+    CK(h2d(o_rank, rank, 4 * (size_t)n));
+    if (n) {
+        k_pack<<<cdiv(n, 256), 256, 0, w->st>>>(
+            n, nullptr, (const float*)(sg + o_pos), rot4 ? (const float*)(sg + o_rot) : nullptr,
+            scale3 ? (const float*)(sg + o_scale) : nullptr, (const float*)(sg + o_vel),
+            acc3 ? (const float*)(sg + o_acc) : nullptr, (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
+            (const float*)(sg + o_mass), (const float*)(sg + o_rest), (const uint8_t*)(sg + o_stat),
+            entity ? (const uint32_t*)(sg + o_ent) : nullptr, rank ? (const uint32_t*)(sg + o_rank) : nullptr, w->P[0],
+            w->V[0], w->A, w->Lo, w->Hi, w->ext, 0);
+        w->launches++;
+        CK(cudaGetLastError());
+    }
+    s = setup_grid(w);
+    if (s != GP_OK) return s;
+    w->uploaded = true;
+    w->last = gp_step_stats{};
+    w->last_np = 0;
+    return GP_OK;
+}
+
+static gp_status stage_state(gp_world* w, uint32_t k, const uint32_t* idx, const float* pos3, const float* vel3,
+                             const float* acc3) {
+    if (!w || !w->uploaded) return w ? fail(w, GP_ERR_STATE, "no bodies uploaded") : GP_ERR_BAD_ARG;
+    CK(cudaSetDevice(w->device));
+    if (k == 0) return GP_OK;
+    const size_t b3 = 3 * sizeof(float) * (size_t)k;
+    const size_t a3 = (b3 + 255) & ~(size_t)255;
+    gp_status s = ensure_stage(w, 3 * a3 + (((size_t)k * 4 + 255) & ~(size_t)255) + 256);
+    if (s != GP_OK) return s;
+    unsigned char* sg = w->stage;
+    if (pos3) CK(cudaMemcpyAsync(sg, pos3, b3, cudaMemcpyHostToDevice, w->st));
+    if (vel3) CK(cudaMemcpyAsync(sg + a3, vel3, b3, cudaMemcpyHostToDevice, w->st));
+    if (acc3) CK(cudaMemcpyAsync(sg + 2 * a3, acc3, b3, cudaMemcpyHostToDevice, w->st));
+    if (idx) CK(cudaMemcpyAsync(sg + 3 * a3, idx, (size_t)k * 4, cudaMemcpyHostToDevice, w->st));
+    k_set_state<<<cdiv(k, 256), 256, 0, w->st>>>(k, idx ? (const uint32_t*)(sg + 3 * a3) : nullptr,
+                                                 pos3 ? (const float*)sg : nullptr,
+                                                 vel3 ? (const float*)(sg + a3) : nullptr,
+                                                 acc3 ? (const float*)(sg + 2 * a3) : nullptr, w->P[w->cur],
+                                                 w->V[w->cur], w->A);
+    w->launches++;
+    CK(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" gp_status gp_set_state(gp_world* w, const float* pos3, const float* vel3, const float* acc3) {
+    if (!w) return GP_ERR_BAD_ARG;
+    return stage_state(w, w->n, nullptr, pos3, vel3, acc3);
+}
+
+extern "C" gp_status gp_update_dirty(gp_world* w, uint32_t k, const uint32_t* idx, const float* pos3,
+                                     const float* vel3, const float* acc3) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (k && !idx) return fail(w, GP_ERR_BAD_ARG, "gp_update_dirty: idx is NULL");
+    for (uint32_t i = 0; i < k; ++i)
+        if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_update_dirty: idx[%u]=%u out of range", i, idx[i]);
+    gp_status s = stage_state(w, k, idx, pos3, vel3, acc3);
+    if (s != GP_OK) return s;
+    CK(cudaStreamSynchronize(w->st));  // idx/pos host arrays may be pageable and short-lived
+    return GP_OK;
+}
+
+extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* idx, const float* box_min3,
+                                     const float* box_max3, const float* rot4, const float* scale3, const float* mass,
+                                     const float* restitution, const uint8_t* is_static) {
+    if (!w || !w->uploaded) return w ? fail(w, GP_ERR_STATE, "no bodies uploaded") : GP_ERR_BAD_ARG;
+    if (k == 0) return GP_OK;
+    if (!idx || !box_min3 || !box_max3 || !mass || !restitution || !is_static)
+        return fail(w, GP_ERR_BAD_ARG, "gp_update_shape: a required array is NULL");
+    for (uint32_t i = 0; i < k; ++i)
+        if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_update_shape: idx[%u]=%u out of range", i, idx[i]);
+    CK(cudaSetDevice(w->device));
+    const size_t f = sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_idx = take(4 * (size_t)k), o_rot = take(4 * f * k), o_scale = take(3 * f * k),
+                 o_bmin = take(3 * f * k), o_bmax = take(3 * f * k), o_mass = take(f * k), o_rest = take(f * k),
+                 o_stat = take(k);
+    gp_status s = ensure_stage(w, off + 256);
+    if (s != GP_OK) return s;
+    unsigned char* sg = w->stage;
+    CK(cudaMemcpyAsync(sg + o_idx, idx, 4 * (size_t)k, cudaMemcpyHostToDevice, w->st));
+    if (rot4) CK(cudaMemcpyAsync(sg + o_rot, rot4, 4 * f * k, cudaMemcpyHostToDevice, w->st));
+    if (scale3) CK(cudaMemcpyAsync(sg + o_scale, scale3, 3 * f * k, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(sg + o_bmin, box_min3, 3 * f * k, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(sg + o_bmax, box_max3, 3 * f * k, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(sg + o_mass, mass, f * k, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(sg + o_rest, restitution, f * k, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(sg + o_stat, is_static, k, cudaMemcpyHostToDevice, w->st));
+    k_pack<<<cdiv(k, 256), 256, 0, w->st>>>(k, (const uint32_t*)(sg + o_idx), nullptr,
+                                            rot4 ? (const float*)(sg + o_rot) : nullptr,
+                                            scale3 ? (const float*)(sg + o_scale) : nullptr, nullptr, nullptr,
+                                            (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
+                                            (const float*)(sg + o_mass), (const float*)(sg + o_rest),
+                                            (const uint8_t*)(sg + o_stat), nullptr, nullptr, w->P[w->cur], w->V[w->cur],
+                                            w->A, w->Lo, w->Hi, w->ext, 1);
+    w->launches++;
+    CK(cudaGetLastError());
+    // a body that outgrew the cell joins the big list; the grid itself is kept
+    k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->ext, w->thr, w->P[w->cur], w->Lo, w->Hi, w->A,
+                                                   w->d_small + EXT_BUCKETS);
+    w->launches++;
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+// Enqueue the kernels of one step.  Reads P/V[cur], leaves the result in P/V[cur^1].
+static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch) {
+    const uint32_t n = w->n;
+    cudaStream_t st = w->st;
+    float d[3];
+    if (damp3)
+        d[0] = damp3[0], d[1] = damp3[1], d[2] = damp3[2];
+    else
+        gp_damping_factors(dt, d);
+    const int c = w->cur, o = c ^ 1;
+    if (n) {
+        k_integrate<<<cdiv(n, 256), 256, 0, st>>>(n, w->P[c], w->V[c], w->A, w->Lo, w->Hi, w->P[o], w->V[o], w->box,
+                                                  w->key[0], w->chain_cnt, w->grid, dt, d[0], d[1], d[2]);
+        w->launches++;
+        const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], n, w->key_bits, true, w->hist,
+                                        w->sm_count, st, &w->launches);
+        k_gather_cells<<<cdiv(n, 256), 256, 0, st>>>(n, w->key[r], w->val[r], w->box, w->sbox, w->LB, w->grid.ncells,
+                                                     w->gaps, w->gap_cap, w->ctl);
+        k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
+        k_find_pairs<<<cdiv(n, 128), 128, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->grid, w->pairs, w->pending,
+                                                   w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+        w->launches += 3;
+        exclusive_scan_u32(w->chain_cnt, n, w->offs, w->tile_sums, st, &w->launches);
+        k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
+                                                       w->ctl);
+        k_sort_chains<<<cdiv(n, 256), 256, 0, st>>>(n, w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl);
+        k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl);
+        w->launches += 3;
+        float4 *Pn = w->P[o], *Vn = w->V[o];
+        const float4 *Lo = w->Lo, *Hi = w->Hi, *box = w->box;
+        uint4* pairs = w->pairs;
+        uint32_t pair_cap = (uint32_t)w->pair_cap;
+        const uint32_t* offs = w->offs;
+        uint32_t* chain_cnt = w->chain_cnt;
+        const unsigned long long* adj = w->adj;
+        uint32_t* pending = w->pending;
+        uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
+        Ctl* ctl = w->ctl;
+        int record = (w->cfg.flags & GP_FLAG_RECORD_PAIRS) ? 1 : 0;
+        void* args[] = {&Pn, &Vn, &Lo, &Hi, &box, &pairs, &pair_cap, &offs, &chain_cnt, &adj, &pending, &f0, &f1, &ctl, &record};
+        CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
+        w->launches++;
+    }
+    k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
+    w->launches++;
+    CK(cudaGetLastError());
+    return GP_OK;
+}
+
+static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
+    gp_step_stats& s = w->last;
+    s.n_bodies = w->n;
+    s.n_big = w->n - std::min(c.n_small, w->n);
+    s.n_candidates = c.n_pairs;
+    s.n_snapshot = c.n_snapshot;
+    s.n_contacts = c.n_contacts;
+    s.n_rounds = c.n_rounds;
+    s.n_retries = retries;
+    s.margin = c.margin;
+    uint32_t mb = c.max_disp_bits;
+    memcpy(&s.max_displacement, &mb, 4);
+    s.cell_size = w->cell;
+    s.grid_dim[0] = w->grid.dx, s.grid_dim[1] = w->grid.dy, s.grid_dim[2] = w->grid.dz;
+    s.n_heavy = c.n_heavy;
+    s.steps_total = w->steps_total;
+    s.steps_inexact = c.steps_inexact;
+    w->last_np = (uint32_t)std::min<uint64_t>(c.n_pairs, w->pair_cap);
+}
+
+static gp_status read_ctl(gp_world* w) {
+    CK(cudaMemcpyAsync(w->h_ctl, w->ctl_snap, sizeof(Ctl), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_stats* stats) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_step before gp_upload");
+    CK(cudaSetDevice(w->device));
+    if (w->multi) return gp_multi_step(w->multi, dt, damp3, stats);
+    gp_status result = GP_OK;
+    uint32_t retries = 0;
+    CK(cudaEventRecord(w->ev0, w->st));
+    for (;;) {
+        gp_status s = enqueue_step(w, dt, damp3, 0);
+        if (s != GP_OK) return s;
+        s = read_ctl(w);
+        if (s != GP_OK) return s;
+        const Ctl& c = *w->h_ctl;
+        const uint32_t f = c.step_flags;
+        const bool no_retry = (w->cfg.flags & GP_FLAG_NO_RETRY) != 0;
+        if (f & (SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW))
+            return fail(w, GP_ERR_CAPACITY, "internal work list overflow (flags 0x%x)", f);
+        if (f & SF_PAIR_OVERFLOW) {
+            if (no_retry || retries >= 8)
+                return fail(w, GP_ERR_PAIR_OVERFLOW, "%u candidate pairs > max_pairs %llu", c.n_pairs,
+                            (unsigned long long)w->pair_cap);
+            gp_status a = alloc_pairs(w, std::max<uint64_t>(2 * w->pair_cap, (uint64_t)c.n_pairs + c.n_pairs / 4));
+            if (a != GP_OK) return a;
+            ++retries;
+            result = GP_WARN_MARGIN_RETRIED;
+            continue;
+        }
+        if (f & SF_MARGIN) {
+            if ((f & SF_MARGIN_MAX) || no_retry || retries >= 16) {
+                fill_stats(w, c, retries);
+                if (stats) *stats = w->last;
+                return fail(w, GP_ERR_MARGIN,
+                            "an AABB moved %.6g during contact resolution, more than the broad-phase margin %.6g "
+                            "(margin_max %.6g): step not applied",
+                            w->last.max_displacement, c.margin, c.margin_max);
+            }
+            ++retries;  // k_finish_step already doubled the margin; re-run from the untouched input buffers
+            result = GP_WARN_MARGIN_RETRIED;
+            continue;
+        }
+        w->cur ^= 1;
+        w->steps_total++;
+        fill_stats(w, c, retries);
+        break;
+    }
+    CK(cudaEventRecord(w->ev1, w->st));
+    w->timed = true;
+    if (stats) *stats = w->last;
+    return result;
+}
+
+extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, uint32_t nsteps) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_step_async before gp_upload");
+    CK(cudaSetDevice(w->device));
+    if (w->multi) return gp_multi_step_async(w->multi, dt, damp3, nsteps);
+    CK(cudaEventRecord(w->ev0, w->st));
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        gp_status r = enqueue_step(w, dt, damp3, 1);
+        if (r != GP_OK) return r;
+        w->cur ^= 1;
+        w->steps_total++;
+    }
+    CK(cudaEventRecord(w->ev1, w->st));
+    w->timed = true;
+    return GP_OK;
+}
+
+extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
+    if (!w) return GP_ERR_BAD_ARG;
+    CK(cudaSetDevice(w->device));
+    if (w->multi) return gp_multi_sync(w->multi, stats);
+    if (!w->uploaded) {
+        CK(cudaStreamSynchronize(w->st));
+        return GP_OK;
+    }
+    gp_status s = read_ctl(w);
+    if (s != GP_OK) return s;
+    const Ctl& c = *w->h_ctl;
+    if (w->steps_total) fill_stats(w, c, 0);
+    if (stats) *stats = w->last;
+    if (c.sticky_flags) {
+        const uint32_t f = c.sticky_flags;
+        // clear the latch so the caller can continue after reacting
+        Ctl* dc = w->ctl;
+        CK(cudaMemsetAsync(&dc->sticky_flags, 0, sizeof(uint32_t), w->st));
+        CK(cudaStreamSynchronize(w->st));
+        if (f & SF_PAIR_OVERFLOW)
+            return fail(w, GP_ERR_PAIR_OVERFLOW, "%u async step(s) were inexact: candidate pairs exceeded max_pairs",
+                        c.steps_inexact);
+        if (f & SF_MARGIN)
+            return fail(w, GP_ERR_MARGIN, "%u async step(s) were inexact: an AABB moved further than the margin",
+                        c.steps_inexact);
+        return fail(w, GP_ERR_CAPACITY, "%u async step(s) hit an internal work list overflow (0x%x)", c.steps_inexact, f);
+    }
+    return GP_OK;
+}
+
+extern "C" gp_status gp_last_step_ms(gp_world* w, float* ms) {
+    if (!w || !ms) return GP_ERR_BAD_ARG;
+    if (!w->timed) return fail(w, GP_ERR_STATE, "no step timed yet");
+    CK(cudaSetDevice(w->device));
+    CK(cudaEventSynchronize(w->ev1));
+    CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
+    if (!w || !w->uploaded) return w ? fail(w, GP_ERR_STATE, "no bodies uploaded") : GP_ERR_BAD_ARG;
+    CK(cudaSetDevice(w->device));
+    const uint32_t n = w->n;
+    if (n == 0) return gp_sync(w, nullptr);
+    const size_t b3 = 3 * sizeof(float) * (size_t)n;
+    const size_t a3 = (b3 + 255) & ~(size_t)255;
+    gp_status s = ensure_stage(w, 2 * a3 + 256);
+    if (s != GP_OK) return s;
+    float* dp = (float*)w->stage;
+    float* dv = (float*)(w->stage + a3);
+    k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->P[w->cur], w->V[w->cur], pos3 ? dp : nullptr, vel3 ? dv : nullptr);
+    w->launches++;
+    if (pos3) CK(cudaMemcpyAsync(pos3, dp, b3, cudaMemcpyDeviceToHost, w->st));
+    if (vel3) CK(cudaMemcpyAsync(vel3, dv, b3, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return gp_sync(w, nullptr);
+}
+
+extern "C" gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint64_t cap, uint64_t* n_out) {
+    if (!w || !n_out) return GP_ERR_BAD_ARG;
+    if (!(w->cfg.flags & GP_FLAG_RECORD_PAIRS)) return fail(w, GP_ERR_STATE, "gp_pairs needs GP_FLAG_RECORD_PAIRS");
+    if (which != 0 && which != 1) return fail(w, GP_ERR_BAD_ARG, "gp_pairs: which must be 0 or 1");
+    CK(cudaSetDevice(w->device));
+    *n_out = 0;
+    const uint32_t np = w->last_np;
+    if (np == 0) return GP_OK;
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr, *cnt = nullptr, *hist = nullptr;
+    uint2* outp = nullptr;
+    gp_status rs = GP_OK;
+    do {
+        if (dmalloc(&k0, np) || dmalloc(&k1, np) || dmalloc(&v0, np) || dmalloc(&v1, np) || dmalloc(&cnt, 1) ||
+            dmalloc(&hist, (size_t)RS_RADIX * w->sm_count * 4) || dmalloc(&outp, np)) {
+            rs = fail(w, GP_ERR_CUDA, "gp_pairs: out of device memory");
+            break;
+        }
+        cudaMemsetAsync(cnt, 0, 4, w->st);
+        k_export_pairs<<<cdiv(np, 256), 256, 0, w->st>>>(w->pairs, np, which, k0, v0, cnt);
+        w->launches++;
+        uint32_t m = 0;
+        cudaMemcpyAsync(&m, cnt, 4, cudaMemcpyDeviceToHost, w->st);
+        if (cudaStreamSynchronize(w->st) != cudaSuccess) {
+            rs = fail(w, GP_ERR_CUDA, "gp_pairs: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        *n_out = m;
+        if (m == 0) break;
+        const int r = rs_sort<unsigned long long>(k0, v0, k1, v1, m, 63, false, hist, w->sm_count, w->st, &w->launches);
+        k_gather_pairs<<<cdiv(m, 256), 256, 0, w->st>>>(w->pairs, r ? v1 : v0, m, outp);
+        w->launches++;
+        const uint64_t ncopy = std::min<uint64_t>(m, cap);
+        if (pairs2 && ncopy) cudaMemcpyAsync(pairs2, outp, ncopy * sizeof(uint2), cudaMemcpyDeviceToHost, w->st);
+        if (cudaStreamSynchronize(w->st) != cudaSuccess) {
+            rs = fail(w, GP_ERR_CUDA, "gp_pairs: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+    } while (0);
+    cudaFree(k0), cudaFree(k1), cudaFree(v0), cudaFree(v1), cudaFree(cnt), cudaFree(hist), cudaFree(outp);
+    return rs;
+}
+
+// ---- test hooks ----
+template <typename KeyT>
+static gp_status test_sort(int32_t device, uint32_t n, uint32_t key_bits, KeyT* keys, uint32_t* vals) {
+    gp_world* w = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return GP_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    KeyT *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr, *hist = nullptr;
+    CK(dmalloc(&k0, n));
+    CK(dmalloc(&k1, n));
+    CK(dmalloc(&v0, n));
+    CK(dmalloc(&v1, n));
+    CK(dmalloc(&hist, (size_t)RS_RADIX * prop.multiProcessorCount * 4));
+    CK(cudaMemcpy(k0, keys, sizeof(KeyT) * (size_t)n, cudaMemcpyHostToDevice));
+    if (vals) CK(cudaMemcpy(v0, vals, 4 * (size_t)n, cudaMemcpyHostToDevice));
+    const int r = rs_sort<KeyT>(k0, v0, k1, v1, n, (int)key_bits, vals == nullptr, hist, prop.multiProcessorCount, 0, nullptr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(keys, r ? k1 : k0, sizeof(KeyT) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (vals) CK(cudaMemcpy(vals, r ? v1 : v0, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(k0), cudaFree(k1), cudaFree(v0), cudaFree(v1), cudaFree(hist);
+    return GP_OK;
+}
+
+extern "C" gp_status gp_test_radix_sort(int32_t device, uint32_t n, uint32_t key_bits, uint32_t* keys_inout,
+                                        uint32_t* vals_inout) {
+    return test_sort<uint32_t>(device, n, key_bits, keys_inout, vals_inout);
+}
+extern "C" gp_status gp_test_radix_sort64(int32_t device, uint32_t n, uint32_t key_bits, uint64_t* keys_inout,
+                                          uint32_t* vals_inout) {
+    return test_sort<unsigned long long>(device, n, key_bits, (unsigned long long*)keys_inout, vals_inout);
+}
+extern "C" gp_status gp_test_exclusive_scan(int32_t device, uint32_t n, uint32_t* data_inout, uint32_t* total) {
+    gp_world* w = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return GP_ERR_NO_DEVICE;
+    uint32_t *in = nullptr, *out = nullptr, *ts = nullptr;
+    CK(dmalloc(&in, n));
+    CK(dmalloc(&out, (size_t)n + 1));
+    CK(dmalloc(&ts, (size_t)cdiv(n, SC_TILE) + 1));
+    CK(cudaMemcpy(in, data_inout, 4 * (size_t)n, cudaMemcpyHostToDevice));
+    exclusive_scan_u32(in, n, out, ts, 0, nullptr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(data_inout, out, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (total) CK(cudaMemcpy(total, out + n, 4, cudaMemcpyDeviceToHost));
+    cudaFree(in), cudaFree(out), cudaFree(ts);
+    return GP_OK;
+}
+
+#include "gp_multi_impl.cuh"

@@ -1,0 +1,778 @@
+// gp_kernels.cuh — the physics step as sm_100a CUDA kernels.
+//
+// Reference behaviour reproduced (paths relative to /root/reference):
+//   K1  k_integrate       RigidBody::update_pos            crates/gears-ecs/src/components/physics.rs:405-462
+//                         + world AABB (get_rotated_aabb)  physics.rs:84-135 (via per-body min/max offsets)
+//   K3  k_gather_cells    (new) cell-range table + AABB tiles in cell order
+//   K4  k_find_pairs      CollisionBox::intersects         physics.rs:148-165  (margin-inflated superset + exact snapshot test)
+//   K5  k_fill_chains / k_sort_chains   (new) per-body contact chains in the reference's pair order
+//   K6  k_sweep           check_and_resolve_collision      physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
+//                         in the order of update_systems.rs:408-487
+//
+// Ordering argument: the reference visits pairs (i,j), i<j in iteration order,
+// lexicographically.  Only pairs that share a DYNAMIC body interact (static bodies are never written,
+// physics.rs:245-270).  For a body x the pairs involving x, in reference order, are exactly its
+// partners sorted by partner rank.  So executing a pair when it is at the head of both of its
+// dynamic endpoints' chains (Kahn peeling, one round per dependency level) reproduces the sequential
+// sweep bit for bit; pairs within a round touch disjoint dynamic bodies.
+//
+// All arithmetic: IEEE binary32, compiled with --fmad=false (Rust never contracts), IEEE div/sqrt.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+namespace gp {
+
+// ---- flags kept in A.w ----
+constexpr uint32_t F_STATIC = 1u;
+constexpr uint32_t F_BIG = 2u;     // extent above the grid cell: brute-force list
+constexpr uint32_t F_GHOST = 4u;   // multi-GPU halo copy: resolved here but owned elsewhere
+
+constexpr uint32_t TOPBIT = 0x80000000u;
+
+// physics.rs:7-20
+constexpr float POSITION_CORRECTION_FACTOR = 0.4f;
+constexpr float POSITION_CORRECTION_SLOP = 0.01f;
+constexpr float FRICTION_COEFFICIENT = 0.8f;
+constexpr float VELOCITY_THRESHOLD = 0.05f;
+constexpr float GRAVITY_ACCELERATION = 28.0f;
+constexpr float FALL_MULTIPLIER = 1.75f;
+constexpr float APEX_MULTIPLIER = 0.6f;
+
+struct GridParams {
+    float ox, oy, oz;   // origin of cell (1,1,1) (cell 0 and dim-1 are an always-empty apron)
+    float inv_cell;
+    int dx, dy, dz;     // dims including the apron
+    uint32_t ncells;    // dx*dy*dz; key ncells = big list
+};
+
+// Device-resident control block: everything the kernels of one step communicate through, so that a
+// step needs no host round trip.
+struct Ctl {
+    float margin;             // m used by the current step (K4 inflation, K6 verification)
+    float margin_min, margin_max;
+    uint32_t n_pairs;         // candidate pairs emitted by K4 (may exceed capacity: then overflow)
+    uint32_t n_snapshot;
+    uint32_t n_contacts;
+    uint32_t n_rounds;
+    uint32_t max_disp_bits;   // max per-axis AABB displacement during the sweep (float bits, >= 0)
+    uint32_t frontier_n[3];   // rotating: round r consumes [r%3], fills [(r+1)%3], clears [(r+2)%3]
+    uint32_t n_heavy;
+    uint32_t n_gaps;
+    uint32_t step_flags;      // SF_* of the current step
+    uint32_t n_small;         // bodies in the grid (sorted prefix); n - n_small = big list
+    uint32_t sticky_flags;    // OR of step_flags over async steps
+    uint32_t steps_inexact;
+    uint32_t steps_total;
+};
+constexpr uint32_t SF_PAIR_OVERFLOW = 1u;
+constexpr uint32_t SF_MARGIN = 2u;       // displacement exceeded the margin used
+constexpr uint32_t SF_MARGIN_MAX = 4u;   // ... and the margin was already margin_max
+constexpr uint32_t SF_GAP_OVERFLOW = 8u;
+constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+// cgmath 0.18 dot: (x*x' + y*y') + z*z'   — no FMA (--fmad=false)
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float len3(V3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return mk((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+}
+__device__ __forceinline__ V3 xyz(float4 v) { return mk(v.x, v.y, v.z); }
+
+__device__ __forceinline__ uint32_t cell_key(const GridParams& g, float cx, float cy, float cz) {
+    // __float2int_rd saturates and maps NaN to 0; the clamp keeps every body inside [1, dim-2]
+    int ix = __float2int_rd((cx - g.ox) * g.inv_cell) + 1;
+    int iy = __float2int_rd((cy - g.oy) * g.inv_cell) + 1;
+    int iz = __float2int_rd((cz - g.oz) * g.inv_cell) + 1;
+    ix = min(max(ix, 1), g.dx - 2);
+    iy = min(max(iy, 1), g.dy - 2);
+    iz = min(max(iz, 1), g.dz - 2);
+    return (uint32_t)ix + (uint32_t)g.dx * ((uint32_t)iy + (uint32_t)g.dy * (uint32_t)iz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Upload: derive per-body AABB offsets.  off_min/off_max = component-wise min/max over the 8
+// corners of rot*(corner*scale) (physics.rs:93-119 without the translation).  Because rounding is
+// monotone, min_i fl(r_i + p) == fl(min_i r_i + p): adding pos afterwards gives the reference's AABB.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void corner_offsets(V3 bmin, V3 bmax, float4 q /*v.xyz, s*/, V3 sc, V3& omin, V3& omax) {
+    const V3 qv = mk(q.x, q.y, q.z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        V3 c = mk((i & 1) ? bmax.x : bmin.x, (i & 2) ? bmax.y : bmin.y, (i & 4) ? bmax.z : bmin.z);
+        V3 s = mk(c.x * sc.x, c.y * sc.y, c.z * sc.z);
+        V3 t = cross3(qv, s) + (s * q.w);
+        V3 r = (cross3(qv, t) * 2.0f) + s;
+        if (i == 0) {
+            omin = r;
+            omax = r;
+        } else {
+            omin = mk(fminf(omin.x, r.x), fminf(omin.y, r.y), fminf(omin.z, r.z));
+            omax = mk(fmaxf(omax.x, r.x), fmaxf(omax.y, r.y), fmaxf(omax.z, r.z));
+        }
+    }
+}
+
+// Packs host-layout staging arrays into the device SoA.  idx == nullptr: body i = thread i.
+__global__ void k_pack(uint32_t k, const uint32_t* __restrict__ idx, const float* __restrict__ pos3,
+                       const float* __restrict__ rot4, const float* __restrict__ scale3, const float* __restrict__ vel3,
+                       const float* __restrict__ acc3, const float* __restrict__ bmin3, const float* __restrict__ bmax3,
+                       const float* __restrict__ mass, const float* __restrict__ rest, const uint8_t* __restrict__ stat,
+                       const uint32_t* __restrict__ entity, const uint32_t* __restrict__ rank, float4* P, float4* V,
+                       float4* A, float4* Lo, float4* Hi, float* ext, int shape_only) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint32_t i = idx ? idx[t] : t;
+    const V3 bmin = mk(bmin3[3 * t], bmin3[3 * t + 1], bmin3[3 * t + 2]);
+    const V3 bmax = mk(bmax3[3 * t], bmax3[3 * t + 1], bmax3[3 * t + 2]);
+    const float4 q = rot4 ? make_float4(rot4[4 * t], rot4[4 * t + 1], rot4[4 * t + 2], rot4[4 * t + 3])
+                          : make_float4(0.f, 0.f, 0.f, 1.f);
+    const V3 sc = scale3 ? mk(scale3[3 * t], scale3[3 * t + 1], scale3[3 * t + 2]) : mk(1.f, 1.f, 1.f);
+    V3 omin, omax;
+    corner_offsets(bmin, bmax, q, sc, omin, omax);
+    const uint32_t fl_static = stat[t] ? F_STATIC : 0u;
+    if (shape_only) {
+        float4 p = P[i], v = V[i], a = A[i], lo = Lo[i], hi = Hi[i];
+        p.w = mass[t];
+        v.w = rest[t];
+        a.w = __uint_as_float((__float_as_uint(a.w) & ~F_STATIC) | fl_static);
+        lo = make_float4(omin.x, omin.y, omin.z, lo.w);
+        hi = make_float4(omax.x, omax.y, omax.z, hi.w);
+        P[i] = p, V[i] = v, A[i] = a, Lo[i] = lo, Hi[i] = hi;
+    } else {
+        P[i] = make_float4(pos3[3 * t], pos3[3 * t + 1], pos3[3 * t + 2], mass[t]);
+        V[i] = make_float4(vel3[3 * t], vel3[3 * t + 1], vel3[3 * t + 2], rest[t]);
+        A[i] = make_float4(acc3 ? acc3[3 * t] : 0.f, acc3 ? acc3[3 * t + 1] : 0.f, acc3 ? acc3[3 * t + 2] : 0.f,
+                           __uint_as_float(fl_static));
+        Lo[i] = make_float4(omin.x, omin.y, omin.z, __uint_as_float(entity ? entity[t] : i));
+        Hi[i] = make_float4(omax.x, omax.y, omax.z, __uint_as_float(rank ? rank[t] : i));
+    }
+    if (ext) ext[i] = fmaxf(omax.x - omin.x, fmaxf(omax.y - omin.y, omax.z - omin.z));
+}
+
+// histogram of body extents in quarter-octave buckets (bucket b: ext <= 2^((b-64)/4)), plus bounds of centres
+constexpr int EXT_BUCKETS = 160;
+__device__ __forceinline__ int ext_bucket(float e) {
+    if (!(e > 0.f)) return 0;
+    if (isinf(e) || isnan(e)) return EXT_BUCKETS - 1;
+    int b = (int)ceilf(log2f(e) * 4.0f) + 64;
+    // make the bucket edge an upper bound despite log2f rounding
+    if (b >= 0 && b < EXT_BUCKETS && exp2f((float)(b - 64) * 0.25f) < e) ++b;
+    return min(max(b, 0), EXT_BUCKETS - 1);
+}
+__host__ __device__ inline float ext_bucket_edge(int b) { return exp2f((float)(b - 64) * 0.25f); }
+
+__global__ void k_ext_hist(uint32_t n, const float* __restrict__ ext, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[EXT_BUCKETS];
+    for (int i = threadIdx.x; i < EXT_BUCKETS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&sh[ext_bucket(ext[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < EXT_BUCKETS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// order-preserving float <-> uint for atomicMin/Max
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & TOPBIT) ? ~u : (u | TOPBIT);
+}
+__host__ __device__ inline float ord2f(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+#endif
+}
+
+// classify by extent threshold and reduce the bounds of grid-class body centres
+__global__ void k_classify(uint32_t n, const float* __restrict__ ext, float thr, const float4* __restrict__ P,
+                           const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* A,
+                           uint32_t* __restrict__ bounds /*6: min xyz, max xyz (ordered uints)*/) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    if (i < n) {
+        float4 a = A[i];
+        uint32_t f = __float_as_uint(a.w) & ~F_BIG;
+        const bool big = !(ext[i] <= thr);
+        if (big) f |= F_BIG;
+        a.w = __uint_as_float(f);
+        A[i] = a;
+        if (!big) {
+            const float4 p = P[i], l = Lo[i], h = Hi[i];
+            const float c[3] = {((l.x + p.x) + (h.x + p.x)) * 0.5f, ((l.y + p.y) + (h.y + p.y)) * 0.5f,
+                                ((l.z + p.z) + (h.z + p.z)) * 0.5f};
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (isfinite(c[k])) lo[k] = hi[k] = c[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (lo[k] < 3.0e38f) atomicMin(&bounds[k], f2ord(lo[k]));
+            if (hi[k] > -3.0e38f) atomicMax(&bounds[3 + k], f2ord(hi[k]));
+        }
+    }
+}
+
+// bulk refresh of mutable state from host-layout arrays (gp_set_state / gp_update_dirty)
+__global__ void k_set_state(uint32_t k, const uint32_t* __restrict__ idx, const float* __restrict__ pos3,
+                            const float* __restrict__ vel3, const float* __restrict__ acc3, float4* P, float4* V,
+                            float4* A) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint32_t i = idx ? idx[t] : t;
+    if (pos3) {
+        float4 p = P[i];
+        p.x = pos3[3 * t], p.y = pos3[3 * t + 1], p.z = pos3[3 * t + 2];
+        P[i] = p;
+    }
+    if (vel3) {
+        float4 v = V[i];
+        v.x = vel3[3 * t], v.y = vel3[3 * t + 1], v.z = vel3[3 * t + 2];
+        V[i] = v;
+    }
+    if (acc3) {
+        float4 a = A[i];
+        a.x = acc3[3 * t], a.y = acc3[3 * t + 1], a.z = acc3[3 * t + 2];
+        A[i] = a;
+    }
+}
+
+__global__ void k_unpack(uint32_t n, const float4* __restrict__ P, const float4* __restrict__ V, float* pos3,
+                         float* vel3) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pos3) {
+        const float4 p = P[i];
+        pos3[3 * i] = p.x, pos3[3 * i + 1] = p.y, pos3[3 * i + 2] = p.z;
+    }
+    if (vel3) {
+        const float4 v = V[i];
+        vel3[3 * i] = v.x, vel3[3 * i + 1] = v.y, vel3[3 * i + 2] = v.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: fused integrate + world AABB + cell key.  One thread per body, float4 (128-bit) coalesced
+// access on every array.  R 80 B (P,V,A,Lo,Hi) + W 32 (P',V') + W 32 (box) + W 4 (key) + W 4 (chain counter).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_integrate(uint32_t n, const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
+                const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* __restrict__ P1,
+                float4* __restrict__ V1, float4* __restrict__ box, uint32_t* __restrict__ key,
+                uint32_t* __restrict__ chain_cnt, GridParams g, float dt, float d16, float d18, float d35) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = P0[i], v = V0[i];
+    const float4 a = A[i], lo = Lo[i], hi = Hi[i];
+    const uint32_t flags = __float_as_uint(a.w);
+    if (!(flags & F_STATIC)) {
+        // physics.rs:405-462
+        const bool falling = v.y < 0.0f;
+        const bool near_apex = fabsf(v.y) < 2.0f && v.y > 0.0f;
+        const float gm = falling ? FALL_MULTIPLIER : (near_apex ? APEX_MULTIPLIER : 1.0f);
+        v.y = v.y - ((GRAVITY_ACCELERATION * gm) * dt);
+        const bool accelerating = len3(mk(a.x, a.y, a.z)) > 0.01f;
+        const float d = accelerating ? d16 : (falling ? d18 : d35);
+        if (falling) {
+            v.x = v.x * d;
+            v.z = v.z * d;
+        } else {
+            v.x = v.x * d;
+            v.y = v.y * d;
+            v.z = v.z * d;
+        }
+        v.x = v.x + a.x * dt;
+        v.z = v.z + a.z * dt;
+        if (len3(mk(v.x, v.y, v.z)) < 0.005f) {
+            v.x = 0.0f, v.y = 0.0f, v.z = 0.0f;
+        }
+        p.x = p.x + v.x * dt;
+        p.y = p.y + v.y * dt;
+        p.z = p.z + v.z * dt;
+    }
+    P1[i] = p;
+    V1[i] = v;
+    // world AABB = offsets + position
+    const float lx = lo.x + p.x, ly = lo.y + p.y, lz = lo.z + p.z;
+    const float hx = hi.x + p.x, hy = hi.y + p.y, hz = hi.z + p.z;
+    const uint32_t tag = i | ((flags & F_STATIC) ? TOPBIT : 0u);
+    box[2 * (size_t)i] = make_float4(lx, ly, lz, __uint_as_float(tag));
+    box[2 * (size_t)i + 1] = make_float4(hx, hy, hz, hi.w /* rank */);
+    key[i] = (flags & F_BIG) ? g.ncells : cell_key(g, (lx + hx) * 0.5f, (ly + hy) * 0.5f, (lz + hz) * 0.5f);
+    chain_cnt[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: gather AABBs into cell order and build the cell lower-bound table LB[c] = first sorted
+// position whose key >= c (c in [0, ncells+1]).  Thread i owns cells (key[i-1], key[i]].
+// Long empty runs go to a gap list that k_fill_gaps spreads over the whole grid.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t GAP_DIRECT = 32;
+constexpr uint32_t GAP_CHUNK = 1u << 16;
+struct Gap {
+    uint32_t c0, len, val;
+};
+
+__device__ __forceinline__ void fill_cells(uint32_t* LB, uint32_t c0, uint32_t len, uint32_t val, Gap* gaps,
+                                           uint32_t gap_cap, Ctl* ctl) {
+    if (len <= GAP_DIRECT) {
+        for (uint32_t c = 0; c < len; ++c) LB[c0 + c] = val;
+    } else {
+        for (uint32_t o = 0; o < len; o += GAP_CHUNK) {
+            const uint32_t slot = atomicAdd(&ctl->n_gaps, 1u);
+            if (slot < gap_cap)
+                gaps[slot] = Gap{c0 + o, min(GAP_CHUNK, len - o), val};
+            else
+                atomicOr(&ctl->step_flags, SF_GAP_OVERFLOW);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_gather_cells(uint32_t n, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sval,
+                   const float4* __restrict__ box, float4* __restrict__ sbox, uint32_t* __restrict__ LB,
+                   uint32_t ncells, Gap* gaps, uint32_t gap_cap, Ctl* ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = sval[i];
+    const float4 lo = box[2 * (size_t)v], hi = box[2 * (size_t)v + 1];
+    sbox[2 * (size_t)i] = lo;
+    sbox[2 * (size_t)i + 1] = hi;
+    const uint32_t k = skey[i];
+    const uint32_t first = (i == 0) ? 0u : skey[i - 1] + 1u;  // cells (prev, k]
+    if (k + 1u > first) fill_cells(LB, first, k + 1u - first, i, gaps, gap_cap, ctl);
+    if (i == n - 1) {
+        // cells above the last key up to ncells+1 (inclusive) -> n
+        if (ncells + 2u > k + 1u) fill_cells(LB, k + 1u, ncells + 2u - (k + 1u), n, gaps, gap_cap, ctl);
+        if (k < ncells) ctl->n_small = n;  // no big body: the fill above covered LB[ncells]
+    }
+    if (k == ncells && (i == 0 || skey[i - 1] != ncells)) ctl->n_small = i;
+}
+
+__global__ void __launch_bounds__(256) k_fill_gaps(const Gap* __restrict__ gaps, uint32_t gap_cap, const Ctl* ctl,
+                                                   uint32_t* __restrict__ LB) {
+    const uint32_t ng = min(ctl->n_gaps, gap_cap);
+    for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
+        const Gap g = gaps[gi];
+        for (uint32_t c = threadIdx.x; c < g.len; c += blockDim.x) LB[g.c0 + c] = g.val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: broad phase + exact snapshot test.  One thread per sorted body p; candidates are the bodies
+// at later sorted positions in the 13 forward neighbour cells + the rest of the own cell (5
+// contiguous row ranges through LB) + the big list.  Each unordered pair is found exactly once.
+// A pair is a CANDIDATE if the AABBs inflated by the margin m overlap (superset of every pair that
+// can intersect at its turn while no AABB moves further than m, verified in K6); it carries the
+// S_snapshot flag if the un-inflated AABBs intersect (physics.rs:159-164, strict).
+// Pairs are appended with warp-aggregated atomics (one atomicAdd per warp-wide ballot).
+// Pair record: x = a | static<<31, y = b | static<<31, z = rank_a | snapshot<<31, w = rank_b (| hit<<31 in K6).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_pair(uint4 rec, bool dyn_a, bool dyn_b, uint4* __restrict__ pairs,
+                                          uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt,
+                                          uint32_t pair_cap, Ctl* ctl) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&ctl->n_pairs, g.size());
+    base = g.shfl(base, 0);
+    const uint32_t slot = base + g.thread_rank();
+    if (slot < pair_cap) {
+        pairs[slot] = rec;
+        pending[slot] = 0;
+        if (dyn_a) atomicAdd(&chain_cnt[rec.x & ~TOPBIT], 1u);
+        if (dyn_b) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
+        if (rec.z & TOPBIT) atomicAdd(&ctl->n_snapshot, 1u);
+    } else {
+        atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+    }
+}
+
+__device__ __forceinline__ void test_candidate(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi,
+                                               float m2, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
+                                               uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    // inflated test: (a.lo - b.hi) < 2m on every axis and direction
+    const bool cand = (alo.x - bhi.x < m2) && (blo.x - ahi.x < m2) && (alo.y - bhi.y < m2) && (blo.y - ahi.y < m2) &&
+                      (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
+    if (!cand) return;
+    const uint32_t ta = __float_as_uint(alo.w), tb = __float_as_uint(blo.w);
+    if ((ta & tb) & TOPBIT) return;  // static-static: no-op in the reference (physics.rs:225)
+    const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
+    const uint32_t ra = __float_as_uint(ahi.w), rb = __float_as_uint(bhi.w);
+    uint4 rec;
+    if (ra < rb)
+        rec = make_uint4(ta, tb, ra | (snap ? TOPBIT : 0u), rb);
+    else
+        rec = make_uint4(tb, ta, rb | (snap ? TOPBIT : 0u), ra);
+    emit_pair(rec, !(rec.x & TOPBIT), !(rec.y & TOPBIT), pairs, pending, chain_cnt, pair_cap, ctl);
+}
+
+__global__ void __launch_bounds__(128)
+    k_find_pairs(uint32_t n, const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
+                 const uint32_t* __restrict__ LB, GridParams g, uint4* __restrict__ pairs,
+                 uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float m2 = 2.0f * ctl->margin;
+    const uint32_t n_small = LB[g.ncells];
+    const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+    if (p < n_small) {
+        const uint32_t k = skey[p];
+        const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
+        // forward half of the 27-neighbourhood as 5 contiguous ranges of sorted positions
+        uint32_t r0[5], r1[5];
+        r0[0] = p + 1, r1[0] = LB[k + 2];
+        r0[1] = LB[k + row - 1], r1[1] = LB[k + row + 2];
+        r0[2] = LB[k + slab - row - 1], r1[2] = LB[k + slab - row + 2];
+        r0[3] = LB[k + slab - 1], r1[3] = LB[k + slab + 2];
+        r0[4] = LB[k + slab + row - 1], r1[4] = LB[k + slab + row + 2];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            for (uint32_t q = r0[r]; q < r1[r]; ++q) {
+                const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
+                test_candidate(alo, ahi, blo, bhi, m2, pairs, pending, chain_cnt, pair_cap, ctl);
+            }
+        }
+    }
+    // big list: every grid body tests all big bodies; big bodies test the big bodies after them
+    for (uint32_t q = max(p + 1, n_small); q < n; ++q) {
+        const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
+        test_candidate(alo, ahi, blo, bhi, m2, pairs, pending, chain_cnt, pair_cap, ctl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: contact chains.  offs = exclusive scan of chain_cnt (host launches scan.cuh).  k_fill_chains
+// drops, for every pair and dynamic endpoint x, the entry (partner rank << 32 | pair id) into x's
+// segment; k_sort_chains orders each segment by partner rank = the reference's visiting order for x,
+// and counts, per pair, on how many chains it is not yet at the head (pending).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_fill_chains(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
+                  uint32_t* __restrict__ chain_cnt, unsigned long long* __restrict__ adj, const Ctl* ctl) {
+    const uint32_t np = min(ctl->n_pairs, pair_cap);
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < np; pid += gridDim.x * blockDim.x) {
+        const uint4 r = pairs[pid];
+        const uint32_t ra = r.z & ~TOPBIT, rb = r.w & ~TOPBIT;
+        if (!(r.x & TOPBIT)) {
+            const uint32_t a = r.x;
+            const uint32_t s = offs[a] + atomicSub(&chain_cnt[a], 1u) - 1u;
+            adj[s] = ((unsigned long long)rb << 32) | pid;
+        }
+        if (!(r.y & TOPBIT)) {
+            const uint32_t b = r.y;
+            const uint32_t s = offs[b] + atomicSub(&chain_cnt[b], 1u) - 1u;
+            adj[s] = ((unsigned long long)ra << 32) | pid;
+        }
+    }
+}
+
+constexpr uint32_t CHAIN_INLINE = 48;  // longer chains go to the block-wide sorter
+
+__global__ void __launch_bounds__(256)
+    k_sort_chains(uint32_t n, const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj,
+                  uint32_t* __restrict__ pending, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const uint32_t b = offs[x], e = offs[x + 1];
+    const uint32_t d = e - b;
+    if (d == 0) return;
+    if (d > CHAIN_INLINE) {
+        const uint32_t s = atomicAdd(&ctl->n_heavy, 1u);
+        if (s < heavy_cap)
+            heavy[s] = x;
+        else
+            atomicOr(&ctl->step_flags, SF_HEAVY_OVERFLOW);
+        return;
+    }
+    // insertion sort in place (segments are short and L1-resident)
+    for (uint32_t i = b + 1; i < e; ++i) {
+        const unsigned long long v = adj[i];
+        uint32_t j = i;
+        while (j > b && adj[j - 1] > v) {
+            adj[j] = adj[j - 1];
+            --j;
+        }
+        adj[j] = v;
+    }
+    for (uint32_t i = b + 1; i < e; ++i) atomicAdd(&pending[(uint32_t)adj[i]], 1u);
+}
+
+// one CTA per heavy body: bitonic sort of its segment in global memory (any length)
+__global__ void __launch_bounds__(256)
+    k_sort_heavy(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending,
+                 const uint32_t* __restrict__ heavy, uint32_t heavy_cap, const Ctl* ctl) {
+    const uint32_t nh = min(ctl->n_heavy, heavy_cap);
+    for (uint32_t hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+        const uint32_t x = heavy[hi];
+        const uint32_t b = offs[x], d = offs[x + 1] - b;
+        uint32_t m = 1;
+        while (m < d) m <<= 1;
+        for (uint32_t k = 2; k <= m; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                    const uint32_t l = i ^ j;
+                    if (l > i && l < d) {  // virtual padding (> every key) never moves down
+                        const unsigned long long vi = adj[b + i], vl = adj[b + l];
+                        const bool up = ((i & k) == 0);
+                        if ((vi > vl) == up) {
+                            adj[b + i] = vl;
+                            adj[b + l] = vi;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x + 1; i < d; i += blockDim.x) atomicAdd(&pending[(uint32_t)adj[b + i]], 1u);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: the ordered contact sweep as ONE persistent cooperative kernel: a CTA per SM slot, a grid-wide
+// barrier per dependency level.  A frontier holds the pairs that are at the head of both chains.
+// Per pair: exact intersects with CURRENT positions (physics.rs:482-489), resolve (physics.rs:176-299),
+// then pop both chains; a pair whose pending count drops to 0 joins the next frontier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
+
+struct BodyRW {
+    V3 pos, vel;
+    float mass, rest;
+    V3 omin, omax;
+    bool is_static;
+};
+
+// physics.rs:176-299; a = earlier in iteration order.  Returns true if positions were corrected.
+__device__ __forceinline__ bool resolve_pair(BodyRW& a, BodyRW& b, V3 amin, V3 amax, V3 bmin, V3 bmax) {
+    const float overlap_x = fminf(amax.x, bmax.x) - fmaxf(amin.x, bmin.x);
+    const float overlap_y = fminf(amax.y, bmax.y) - fmaxf(amin.y, bmin.y);
+    const float overlap_z = fminf(amax.z, bmax.z) - fmaxf(amin.z, bmin.z);
+    const V3 a_center = (amin + amax) * 0.5f;
+    const V3 b_center = (bmin + bmax) * 0.5f;
+    const V3 cd = b_center - a_center;
+    float min_overlap;
+    V3 n;
+    if (overlap_x <= overlap_y && overlap_x <= overlap_z) {
+        min_overlap = overlap_x;
+        n = mk(cd.x > 0.0f ? 1.0f : -1.0f, 0.0f, 0.0f);
+    } else if (overlap_y <= overlap_z) {
+        min_overlap = overlap_y;
+        n = mk(0.0f, cd.y > 0.0f ? 1.0f : -1.0f, 0.0f);
+    } else {
+        min_overlap = overlap_z;
+        n = mk(0.0f, 0.0f, cd.z > 0.0f ? 1.0f : -1.0f);
+    }
+    const float inv_a = a.is_static ? 0.0f : 1.0f / a.mass;
+    const float inv_b = b.is_static ? 0.0f : 1.0f / b.mass;
+    const float tim = inv_a + inv_b;
+    if (tim <= 0.0f) return false;
+    const V3 rv = b.vel - a.vel;
+    const float vn = dot3(rv, n);
+    if (vn > 0.0f) return false;
+    bool moved = false;
+    if (min_overlap > POSITION_CORRECTION_SLOP) {
+        const float cm = ((min_overlap - POSITION_CORRECTION_SLOP) * POSITION_CORRECTION_FACTOR) / tim;
+        const V3 corr = n * cm;
+        if (!a.is_static) a.pos = a.pos - corr * inv_a;
+        if (!b.is_static) b.pos = b.pos + corr * inv_b;
+        moved = true;
+    }
+    const float e = fabsf(vn) < VELOCITY_THRESHOLD ? 0.0f : (a.rest + b.rest) * 0.5f;
+    const float j = ((-(1.0f + e)) * vn) / tim;
+    const V3 imp = n * j;
+    if (!a.is_static) a.vel = a.vel - imp * inv_a;
+    if (!b.is_static) b.vel = b.vel + imp * inv_b;
+    const V3 tv = rv - n * vn;
+    const float ts = len3(tv);
+    if (ts > 0.001f) {
+        const V3 t = tv / ts;
+        const float f = fminf(FRICTION_COEFFICIENT * fabsf(j), ts * tim);
+        if (!a.is_static) a.vel = a.vel - (t * f) * inv_a;
+        if (!b.is_static) b.vel = b.vel + (t * f) * inv_b;
+    }
+    if (!a.is_static && len3(a.vel) < VELOCITY_THRESHOLD * 0.5f) a.vel = mk(0.f, 0.f, 0.f);
+    if (!b.is_static && len3(b.vel) < VELOCITY_THRESHOLD * 0.5f) b.vel = mk(0.f, 0.f, 0.f);
+    return moved;
+}
+
+__device__ __forceinline__ void frontier_push(uint32_t q, uint32_t* __restrict__ frontier, uint32_t* counter) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    frontier[base + g.thread_rank()] = q;
+}
+
+__device__ __forceinline__ float max_abs_disp(V3 lo_now, float4 lo_snap) {
+    return fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
+}
+
+__global__ void __launch_bounds__(256)
+    k_sweep(float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Lo, const float4* __restrict__ Hi,
+            const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
+            const uint32_t* __restrict__ offs, uint32_t* __restrict__ chain_cnt,
+            const unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending, uint32_t* __restrict__ frontier0,
+            uint32_t* __restrict__ frontier1, Ctl* ctl, int record_hits) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t np = min(ctl->n_pairs, pair_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    // round 0 frontier: pairs at the head of all their chains
+    for (uint32_t pid = gtid; pid < np; pid += gsz)
+        if (__ldcg(&pending[pid]) == 0) frontier_push(pid, frontier0, &ctl->frontier_n[0]);
+    grid.sync();
+    const float mverify = 0.98f * ctl->margin;
+    uint32_t rounds = 0, contacts = 0;
+    float maxd = 0.0f;
+    while (true) {
+        const uint32_t ci = rounds % 3u, co = (rounds + 1u) % 3u, cz = (rounds + 2u) % 3u;
+        const uint32_t nf = __ldcg(&ctl->frontier_n[ci]);
+        if (nf == 0) break;
+        // counter cz was consumed in the previous round (all reads are behind that round's barrier)
+        // and is next filled in the round after this one (behind this round's barrier)
+        if (gtid == 0) ctl->frontier_n[cz] = 0;
+        const uint32_t* fin = (rounds & 1u) ? frontier1 : frontier0;
+        uint32_t* fout = (rounds & 1u) ? frontier0 : frontier1;
+        for (uint32_t f = gtid; f < nf; f += gsz) {
+            const uint32_t pid = __ldcg(&fin[f]);
+            uint4 rec = pairs[pid];
+            const uint32_t ia = rec.x & ~TOPBIT, ib = rec.y & ~TOPBIT;
+            BodyRW a, b;
+            a.is_static = (rec.x & TOPBIT) != 0;
+            b.is_static = (rec.y & TOPBIT) != 0;
+            const float4 pa = ldcg4(&P[ia]), pb = ldcg4(&P[ib]);
+            const float4 loa = Lo[ia], hia = Hi[ia], lob = Lo[ib], hib = Hi[ib];
+            a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
+            b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
+            const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
+            const V3 bmin = b.omin + b.pos, bmax = b.omax + b.pos;
+            // physics.rs:159-164 on the CURRENT positions
+            const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y &&
+                             amin.z < bmax.z && amax.z > bmin.z;
+            if (hit) {
+                ++contacts;
+                const float4 va = ldcg4(&V[ia]), vb = ldcg4(&V[ib]);
+                a.vel = xyz(va), a.rest = va.w;
+                b.vel = xyz(vb), b.rest = vb.w;
+                const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
+                if (!a.is_static) {
+                    __stcg(&P[ia], make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass));
+                    __stcg(&V[ia], make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest));
+                }
+                if (!b.is_static) {
+                    __stcg(&P[ib], make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass));
+                    __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
+                }
+                if (moved) {
+                    // superset check: every AABB must stay within its K1 snapshot inflated by the margin
+                    if (!a.is_static) maxd = fmaxf(maxd, max_abs_disp(a.omin + a.pos, box[2 * (size_t)ia]));
+                    if (!b.is_static) maxd = fmaxf(maxd, max_abs_disp(b.omin + b.pos, box[2 * (size_t)ib]));
+                }
+                if (record_hits) pairs[pid].w = rec.w | TOPBIT;
+            }
+            // pop the chains; wake pairs that reached the head everywhere
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const bool st = s ? b.is_static : a.is_static;
+                if (st) continue;
+                const uint32_t x = s ? ib : ia;
+                const uint32_t h = __ldcg(&chain_cnt[x]) + 1u;
+                __stcg(&chain_cnt[x], h);
+                const uint32_t o0 = offs[x], o1 = offs[x + 1];
+                if (o0 + h < o1) {
+                    const uint32_t q = (uint32_t)adj[o0 + h];
+                    if (atomicSub(&pending[q], 1u) == 1u) frontier_push(q, fout, &ctl->frontier_n[co]);
+                }
+            }
+        }
+        ++rounds;
+        grid.sync();
+    }
+    // per-thread partials -> warp -> global
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        contacts += __shfl_xor_sync(0xffffffffu, contacts, o);
+        maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (contacts) atomicAdd(&ctl->n_contacts, contacts);
+        if (maxd > 0.0f) atomicMax(&ctl->max_disp_bits, __float_as_uint(maxd));
+        if (maxd > mverify) atomicOr(&ctl->step_flags, SF_MARGIN);
+    }
+    if (gtid == 0) ctl->n_rounds = rounds;
+}
+
+// End of step: latch failures, adapt the margin for the next step, reset per-step counters.
+__global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
+    Ctl c = *ctl;
+    const float maxd = __uint_as_float(c.max_disp_bits);
+    if ((c.step_flags & SF_MARGIN) && c.margin >= c.margin_max) c.step_flags |= SF_MARGIN_MAX;
+    if (latch) {  // async stepping: failures are latched, the host looks later
+        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW)) {
+            c.steps_inexact += 1;
+            c.sticky_flags |= c.step_flags;
+        }
+        c.steps_total += 1;
+    }
+    *snapshot_out = c;  // what the host reads (stats of THIS step)
+    // next margin: at least twice what was just needed, slow decay otherwise
+    float m = fmaxf(2.5f * maxd, 0.9f * c.margin);
+    if (c.step_flags & SF_MARGIN) m = fmaxf(m, 2.0f * c.margin);
+    c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
+    c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
+    c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.n_gaps = 0, c.step_flags = 0;
+    *ctl = c;
+}
+
+// ---- pair-set export (gp_pairs): compact flagged pairs into (key = rank_a<<32|rank_b, value = pair id) ----
+__global__ void k_export_pairs(const uint4* __restrict__ pairs, uint32_t np, int which,
+                               unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* counter) {
+    const uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= np) return;
+    const uint4 r = pairs[pid];
+    const bool in = which == 0 ? (r.z & TOPBIT) != 0 : (r.w & TOPBIT) != 0;
+    if (!in) return;
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    const uint32_t s = base + g.thread_rank();
+    keys[s] = ((unsigned long long)(r.z & ~TOPBIT) << 32) | (r.w & ~TOPBIT);
+    vals[s] = pid;
+}
+
+__global__ void k_gather_pairs(const uint4* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t m,
+                               uint2* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint4 r = pairs[order[i]];
+    out[i] = make_uint2(r.x & ~TOPBIT, r.y & ~TOPBIT);
+}
+
+}  // namespace gp

@@ -1,0 +1,94 @@
+// scan.cuh — device-wide exclusive scan of u32 counters (contact-chain offsets).
+// reduce-per-tile -> scan of tile sums (one CTA) -> scan-per-tile with carry.  R 8 B + W 4 B per element.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "radix_sort.cuh"
+
+namespace gp {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 16;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* total, uint32_t* smem33) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem33[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (SC_THREADS / 32) ? smem33[lane] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < (SC_THREADS / 32)) smem33[lane] = wi - w;
+        if (lane == 31) smem33[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t r = smem33[warp] + inc - v;
+    if (total) *total = smem33[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) sc_reduce(const uint32_t* __restrict__ in, uint32_t n,
+                                                        uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sm[33];
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        const uint64_t p = base + (uint64_t)i * SC_THREADS + threadIdx.x;
+        if (p < n) s += in[p];
+    }
+    uint32_t total;
+    block_exclusive_scan_256(s, &total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// out[i] = sum_{j<i} in[j]; the last tile also writes out[n] = grand total.
+__global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* __restrict__ in, uint32_t n,
+                                                      const uint32_t* __restrict__ tile_offsets,
+                                                      uint32_t* __restrict__ out) {
+    __shared__ uint32_t sm[33];
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    uint32_t v[SC_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        s += v[i];
+    }
+    uint32_t run = block_exclusive_scan_256(s, nullptr, sm) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+        if (base + i + 1 == n) out[n] = run;
+    }
+}
+
+// tile_sums: ceil(n/SC_TILE) u32 of scratch.  out has n+1 entries.  in may alias nothing in out.
+static inline void exclusive_scan_u32(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums,
+                                      cudaStream_t st, uint64_t* launches) {
+    if (n == 0) {
+        cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
+        return;
+    }
+    const uint32_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    sc_reduce<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums);
+    rs_scan<<<1, RS_SCAN_THREADS, 0, st>>>(tile_sums, tiles);
+    sc_scan<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums, out);
+    if (launches) *launches += 3;
+}
+
+}  // namespace gp

@@ -1,0 +1,160 @@
+"""PhysicsWorld — thin Python host mirror over the C ABI, used by tests and bench.py.
+
+It plays the role of the `gears-physics-cuda` Rust crate's safe wrapper (rust/gears-physics-cuda):
+own a gp_world handle, mirror the ECS component arrays into it, call the step, read results back.
+No physics is computed here and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class GpError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"gp_status {status}: {msg}")
+        self.status = status
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, cols=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None and a.size:
+        assert a.shape[-1] == cols
+    return a
+
+
+class PhysicsWorld:
+    def __init__(self, device: int = 0, max_bodies: int = 0, max_pairs: int = 0, margin_init: float = 0.0,
+                 margin_max: float = 0.0, cell_size: float = 0.0, max_big: int = 0, record_pairs: bool = False,
+                 no_retry: bool = False, grid_min=None, grid_max=None):
+        self._lib = capi.lib()
+        cfg = capi.GpConfig()
+        cfg.struct_size = C.sizeof(capi.GpConfig)
+        cfg.device = device
+        cfg.max_bodies = max_bodies
+        cfg.max_pairs = max_pairs
+        cfg.margin_init = margin_init
+        cfg.margin_max = margin_max
+        cfg.cell_size = cell_size
+        cfg.max_big = max_big
+        cfg.flags = (capi.GP_FLAG_RECORD_PAIRS if record_pairs else 0) | (capi.GP_FLAG_NO_RETRY if no_retry else 0)
+        if grid_min is not None:
+            cfg.grid_min[:] = [float(x) for x in grid_min]
+            cfg.grid_max[:] = [float(x) for x in grid_max]
+        h = C.c_void_p()
+        st = self._lib.gp_create(C.byref(cfg), C.byref(h))
+        if st != 0:
+            raise GpError(st, self._lib.gp_last_error(None).decode())
+        self._h = h
+        self.n = 0
+
+    # -- helpers --
+    def _check(self, st: int) -> int:
+        if st < 0:
+            raise GpError(st, self._lib.gp_last_error(self._h).decode())
+        return st
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- mirror --
+    def upload(self, scene: dict):
+        n = int(scene["pos"].shape[0])
+        keep = dict(
+            pos=_f32(scene["pos"], 3), rot=_f32(scene.get("rot"), 4), scale=_f32(scene.get("scale"), 3),
+            vel=_f32(scene["vel"], 3), acc=_f32(scene.get("acc"), 3), bmin=_f32(scene["box_min"], 3),
+            bmax=_f32(scene["box_max"], 3), mass=_f32(scene["mass"]), rest=_f32(scene["restitution"]),
+            stat=np.ascontiguousarray(scene["is_static"], dtype=np.uint8),
+            ent=None if scene.get("entity") is None else np.ascontiguousarray(scene["entity"], dtype=np.uint32),
+            rank=None if scene.get("rank") is None else np.ascontiguousarray(scene["rank"], dtype=np.uint32))
+        self._check(self._lib.gp_upload(self._h, n, _ptr(keep["pos"]), _ptr(keep["rot"]), _ptr(keep["scale"]),
+                                        _ptr(keep["vel"]), _ptr(keep["acc"]), _ptr(keep["bmin"]), _ptr(keep["bmax"]),
+                                        _ptr(keep["mass"]), _ptr(keep["rest"]), _ptr(keep["stat"]), _ptr(keep["ent"]),
+                                        _ptr(keep["rank"])))
+        self.n = n
+
+    def set_state(self, pos=None, vel=None, acc=None):
+        pos, vel, acc = _f32(pos, 3), _f32(vel, 3), _f32(acc, 3)
+        self._check(self._lib.gp_set_state(self._h, _ptr(pos), _ptr(vel), _ptr(acc)))
+        self._check(self._lib.gp_sync(self._h, None))
+
+    def update_dirty(self, idx, pos=None, vel=None, acc=None):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        pos, vel, acc = _f32(pos, 3), _f32(vel, 3), _f32(acc, 3)
+        self._check(self._lib.gp_update_dirty(self._h, len(idx), _ptr(idx), _ptr(pos), _ptr(vel), _ptr(acc)))
+
+    def update_shape(self, idx, box_min, box_max, mass, restitution, is_static, rot=None, scale=None):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        a = [_f32(box_min, 3), _f32(box_max, 3), _f32(rot, 4), _f32(scale, 3), _f32(mass), _f32(restitution),
+             np.ascontiguousarray(is_static, dtype=np.uint8)]
+        self._check(self._lib.gp_update_shape(self._h, len(idx), _ptr(idx), *[_ptr(x) for x in a]))
+
+    # -- step --
+    def step(self, dt: float, damp=None) -> dict:
+        st = capi.GpStepStats()
+        d = None if damp is None else _f32(damp)
+        rc = self._check(self._lib.gp_step(self._h, C.c_float(dt), _ptr(d), C.byref(st)))
+        out = st.as_dict()
+        out["status"] = rc
+        return out
+
+    def step_async(self, dt: float, nsteps: int = 1, damp=None):
+        d = None if damp is None else _f32(damp)
+        self._check(self._lib.gp_step_async(self._h, C.c_float(dt), _ptr(d), nsteps))
+
+    def sync(self) -> dict:
+        st = capi.GpStepStats()
+        self._check(self._lib.gp_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.gp_last_step_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.gp_kernel_launches(self._h))
+
+    # -- results --
+    def download(self, pos_out=None, vel_out=None):
+        pos = np.empty((self.n, 3), np.float32) if pos_out is None else pos_out
+        vel = np.empty((self.n, 3), np.float32) if vel_out is None else vel_out
+        self._check(self._lib.gp_download(self._h, _ptr(pos), _ptr(vel)))
+        return pos, vel
+
+    def pairs(self, which: int) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._lib.gp_pairs(self._h, which, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), np.uint32)
+        if n.value:
+            self._check(self._lib.gp_pairs(self._h, which, _ptr(out), n.value, C.byref(n)))
+        return out
+
+
+def damping_factors(dt: float) -> np.ndarray:
+    out = np.zeros(3, np.float32)
+    capi.lib().gp_damping_factors(C.c_float(dt), out.ctypes.data_as(capi.f32p))
+    return out

@@ -1,0 +1,170 @@
+/* gears_physics_cuda.h — C ABI of libgears_physics_cuda.so (the `gears-physics-cuda-sys` boundary).
+ *
+ * B200-native (sm_100a) replacement for passes 1 and 2 of Gears' `update_physics` system
+ *   reference crates/gears-app/src/systems/update_systems.rs:362-487
+ * and the component math it calls
+ *   reference crates/gears-ecs/src/components/physics.rs:84-299,405-462.
+ * The reference has no FFI of its own (every crate is #![forbid(unsafe_code)]); the functions below
+ * are what a `gears-physics-cuda-sys` crate binds (rust/gears-physics-cuda-sys).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all device memory is owned by the gp_world handle;
+ *  - every function returns a gp_status (0 = ok, <0 = error, >0 = warning); never aborts, never throws;
+ *  - a handle may be used from any thread but by one thread at a time (not re-entrant);
+ *  - host arrays are tightly packed: vec3 = 3 floats, quaternion = 4 floats in cgmath order
+ *    (v.x, v.y, v.z, s) as laid out by `Quaternion<f32>` (reference transforms.rs:17-22);
+ *  - body i of an upload is "body index i" in every later call and in every pair output;
+ *  - rank[i] is the position of body i in the reference's iteration order, i.e. the index of its
+ *    entity in the Vec returned by World::get_entities_with_component (reference
+ *    crates/gears-ecs/src/lib.rs:422-433).  Ranks must be distinct.  NULL means rank[i] = i.
+ *  - arithmetic is IEEE binary32 without FMA contraction, so results are bit-identical to the
+ *    reference's scalar Rust for any schedule that keeps the per-body order of pair updates.
+ */
+#ifndef GEARS_PHYSICS_CUDA_H
+#define GEARS_PHYSICS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+typedef struct gp_world gp_world;
+
+typedef enum gp_status {
+    GP_OK = 0,
+    /* warnings (> 0): the call completed */
+    GP_WARN_MARGIN_RETRIED = 1, /* a step was re-run with a larger broad-phase margin (result exact)   */
+    /* errors (< 0) */
+    GP_ERR_BAD_ARG = -1,
+    GP_ERR_CUDA = -2,        /* CUDA runtime error, see gp_last_error                                   */
+    GP_ERR_NO_DEVICE = -3,   /* no sm_100 device / library built without a usable kernel image         */
+    GP_ERR_CAPACITY = -4,    /* more bodies than max_bodies                                             */
+    GP_ERR_PAIR_OVERFLOW = -5, /* candidate pairs exceeded max_pairs (step not applied)                 */
+    GP_ERR_MARGIN = -6,      /* a body moved further than margin_max during contact resolution          */
+                             /* (step result not guaranteed exact; raise margin_max)                    */
+    GP_ERR_NCCL = -7,
+    GP_ERR_STATE = -8        /* call order violation (e.g. step before upload)                          */
+} gp_status;
+
+/* gp_config.flags */
+#define GP_FLAG_RECORD_PAIRS 0x1u /* keep S_snapshot / S_sweep flags so gp_pairs can be called       */
+#define GP_FLAG_NO_RETRY 0x2u     /* never re-run a step: report GP_ERR_MARGIN/PAIR_OVERFLOW instead  */
+
+typedef struct gp_config {
+    uint32_t struct_size; /* = sizeof(gp_config); lets the library version the struct                */
+    int32_t device;       /* CUDA device ordinal                                                      */
+    uint32_t max_bodies;  /* capacity; 0 = sized by the first gp_upload                               */
+    uint64_t max_pairs;   /* candidate-pair capacity; 0 = 16 * max_bodies (min 1 Mi)                   */
+    float margin_init;    /* initial broad-phase AABB inflation m; <=0 = auto (0.05 * body extent)    */
+    float margin_max;     /* upper bound for the adaptive m;      <=0 = auto (0.25 * body extent)     */
+    float cell_size;      /* uniform-grid cell edge; <=0 = auto (largest grid-class extent + 2 m_max) */
+    uint32_t max_big;     /* bodies larger than the cell go to a brute-force list of at most this     */
+                          /* many (0 = 64); the cell grows until the rest fit                         */
+    uint32_t flags;
+    float grid_min[3], grid_max[3]; /* optional world bounds for the grid; all 0 = from the upload     */
+} gp_config;
+
+typedef struct gp_step_stats {
+    uint32_t n_bodies;
+    uint32_t n_big;          /* bodies on the brute-force list                                        */
+    uint64_t n_candidates;   /* broad-phase pairs (margin-inflated AABBs overlap)                     */
+    uint64_t n_snapshot;     /* |S_snapshot|: exact overlaps on the post-integration state            */
+    uint64_t n_contacts;     /* |S_sweep|: pairs whose exact test was true at their turn              */
+    uint32_t n_rounds;       /* dependency levels executed by the contact sweep                       */
+    uint32_t n_retries;      /* times this step was re-run (margin / capacity)                        */
+    float margin;            /* m used for this step                                                  */
+    float max_displacement;  /* largest per-axis move of any AABB during the sweep                    */
+    float cell_size;
+    uint32_t grid_dim[3];
+    uint32_t n_heavy;        /* bodies whose contact chain needed the block-wide sort                 */
+    uint32_t n_migrated_out, n_migrated_in, n_halo_out, n_halo_in; /* multi-GPU only               */
+    uint64_t steps_total;    /* steps since upload                                                    */
+    uint64_t steps_inexact;  /* async steps (gp_step_async) that hit GP_ERR_MARGIN/PAIR_OVERFLOW      */
+} gp_step_stats;
+
+/* ---- lifetime ---- */
+int32_t gp_abi_version(void);
+gp_status gp_create(const gp_config* cfg, gp_world** out);
+void gp_destroy(gp_world* w);
+/* NUL-terminated description of the last error on this handle (or of the last gp_create failure if w is NULL) */
+const char* gp_last_error(const gp_world* w);
+
+/* ---- component mirror: host SoA -> device (replaces the per-entity acquire_query/get/write of
+ *      update_systems.rs:381-400 and :414-475) ---- */
+gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const float* rot4 /*nullable: identity*/,
+                    const float* scale3 /*nullable: (1,1,1) = no Scale component*/, const float* vel3,
+                    const float* acc3 /*nullable: 0*/, const float* box_min3, const float* box_max3,
+                    const float* mass, const float* restitution, const uint8_t* is_static,
+                    const uint32_t* entity /*nullable: i*/, const uint32_t* rank /*nullable: i*/);
+
+/* Refresh the mutable state of ALL bodies from the host (external writers: user systems and
+ * MovementController write velocity/acceleration/position between steps).
+ * Any pointer may be NULL = keep the device value. */
+gp_status gp_set_state(gp_world* w, const float* pos3, const float* vel3, const float* acc3);
+
+/* Same for k listed bodies (dirty set). */
+gp_status gp_update_dirty(gp_world* w, uint32_t k, const uint32_t* idx, const float* pos3, const float* vel3,
+                          const float* acc3);
+
+/* Shape / material change of k listed bodies (rotation, scale, box, mass, restitution, static flag).
+ * All arrays required except rot4/scale3 (NULL = identity / none). */
+gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* idx, const float* box_min3,
+                          const float* box_max3, const float* rot4, const float* scale3, const float* mass,
+                          const float* restitution, const uint8_t* is_static);
+
+/* ---- the step: pass 1 (update_pos for every body) + pass 2 (ordered pair sweep) ---- */
+/* damp3 = { expf(-1.6*dt), expf(-1.8*dt), expf(-3.5*dt) } from the host libm (what Rust's f32::exp
+ * calls); NULL = computed here with expf.  Synchronous: returns after the step completed, re-running
+ * it transparently when the adaptive margin or the pair capacity was exceeded (unless GP_FLAG_NO_RETRY).
+ * stats may be NULL. */
+gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_stats* stats);
+
+/* Enqueue `nsteps` steps without any host synchronisation.  Failures latch: the first failing step's
+ * status is returned by the next gp_sync/gp_step/gp_download and counted in stats.steps_inexact. */
+gp_status gp_step_async(gp_world* w, float dt, const float* damp3, uint32_t nsteps);
+gp_status gp_sync(gp_world* w, gp_step_stats* stats /*nullable: stats of the last step*/);
+
+/* ---- results: device -> host (replaces the write-back through the RwLock guards) ---- */
+gp_status gp_download(gp_world* w, float* pos3 /*nullable*/, float* vel3 /*nullable*/);
+
+/* Pair sets of the LAST step (needs GP_FLAG_RECORD_PAIRS), in the reference's iteration order
+ * (ascending (rank_a, rank_b), rank_a < rank_b).  which: 0 = S_snapshot, 1 = S_sweep.
+ * pairs2 receives body indices (a, b), a = earlier in iteration order.  *n = number of pairs in the
+ * set even if cap is smaller (then only cap pairs are written). */
+gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint64_t cap, uint64_t* n);
+
+/* ---- helpers ---- */
+void gp_damping_factors(float dt, float* out3);
+/* page-locked host buffers for the mirror (faster gp_upload/gp_set_state/gp_download) */
+void* gp_host_alloc(size_t bytes);
+void gp_host_free(void* p);
+/* device time of the last gp_step / gp_step_async batch in milliseconds (CUDA events on the step stream) */
+gp_status gp_last_step_ms(gp_world* w, float* ms);
+/* number of kernels launched by this handle since creation (for launch accounting) */
+uint64_t gp_kernel_launches(const gp_world* w);
+
+/* ---- multi-GPU: spatial slabs along x, one handle per GPU / process, NCCL point-to-point ---- */
+#define GP_UNIQUE_ID_BYTES 128
+gp_status gp_comm_unique_id(uint8_t id[GP_UNIQUE_ID_BYTES]);
+/* Collective over all ranks.  slab = [x_lo, x_hi): this rank owns bodies whose AABB centre x lies in it. */
+gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks,
+                       float x_lo, float x_hi);
+/* global ids of the bodies currently owned by this rank, in device order (after migration) */
+gp_status gp_owned_count(gp_world* w, uint32_t* n);
+gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3);
+
+/* ---- test hooks (used by tests/ only; stable but not part of the drop-in surface) ---- */
+gp_status gp_test_radix_sort(int32_t device, uint32_t n, uint32_t key_bits, uint32_t* keys_inout,
+                             uint32_t* vals_inout);
+gp_status gp_test_radix_sort64(int32_t device, uint32_t n, uint32_t key_bits, uint64_t* keys_inout,
+                               uint32_t* vals_inout);
+gp_status gp_test_exclusive_scan(int32_t device, uint32_t n, uint32_t* data_inout, uint32_t* total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEARS_PHYSICS_CUDA_H */
