@@ -47,9 +47,9 @@ struct gp_world {
     uint32_t lb_cap = 0;
     Gap* gaps = nullptr;
     uint32_t gap_cap = 0;
-    GridParams grid{};
+    uint32_t max_cells = 0;
     int key_bits = 1;
-    float thr = 0.f, cell = 0.f;
+    float thr = 0.f;
     // chains + sweep
     uint32_t *chain_cnt = nullptr, *offs = nullptr, *tile_sums = nullptr;
     uint4* pairs = nullptr;
@@ -289,38 +289,23 @@ static gp_status setup_grid(gp_world* w) {
                                c.grid_max[1] == 0 && c.grid_max[2] == 0);
     if (user_bounds)
         for (int k = 0; k < 3; ++k) lo[k] = c.grid_min[k], hi[k] = c.grid_max[k];
-    const float base = isfinite(thr) ? thr : 1.0f;  // typical body extent
-    float m_max = c.margin_max > 0 ? c.margin_max : 0.25f * base;
-    float m_init = c.margin_init > 0 ? c.margin_init : 0.05f * base;
+    // margins are relative to each body's own extent (a contact moves a body by at most 0.4 of the overlap,
+    // which is bounded by the body's extent)
+    float m_max = c.margin_max > 0 ? c.margin_max : 2.0f;
+    float m_init = c.margin_init > 0 ? c.margin_init : 0.05f;
     if (m_init > m_max) m_init = m_max;
-    float maxabs = 0.f;
-    for (int k = 0; k < 3; ++k) maxabs = fmaxf(maxabs, fmaxf(fabsf(lo[k]), fabsf(hi[k])));
-    // the 27-neighbourhood needs cell >= extent + 2 m_max; slack covers rounding of centre / cell index
-    float need = (base + 2.0f * m_max) * 1.002f + 8.0f * maxabs * 1.2e-7f;
-    float cell = c.cell_size > need ? c.cell_size : need;
-    // grow the cell until the table fits 2^28 cells
-    int dx, dy, dz;
-    for (;;) {
-        double ex[3];
-        for (int k = 0; k < 3; ++k) ex[k] = floor(((double)hi[k] - (double)lo[k]) / cell) + 1.0 + 4.0 + 2.0;
-        if (ex[0] * ex[1] * ex[2] <= 268435456.0 && ex[0] < 2e9 && ex[1] < 2e9 && ex[2] < 2e9) {
-            dx = (int)ex[0], dy = (int)ex[1], dz = (int)ex[2];
-            break;
-        }
-        cell *= 1.25f;
-    }
-    w->cell = cell;
-    w->grid.inv_cell = 1.0f / cell;
-    w->grid.ox = lo[0] - 2.0f * cell, w->grid.oy = lo[1] - 2.0f * cell, w->grid.oz = lo[2] - 2.0f * cell;
-    w->grid.dx = dx, w->grid.dy = dy, w->grid.dz = dz;
-    w->grid.ncells = (uint32_t)dx * (uint32_t)dy * (uint32_t)dz;
+    if (!isfinite(thr)) return fail(w, GP_ERR_BAD_ARG, "gp_upload: more than max_big bodies have a non-finite extent");
+    const float ext_max = thr;  // upper bound of every grid-class extent
+    // the cell table is sized for the finest grid (margin = m_init); coarser grids reuse it
+    const uint32_t MAXC = 1u << 28;
+    GridParams g0 = make_grid(lo, hi, ext_max, m_init, c.cell_size, MAXC);
     int bits = 1;
-    while ((1ull << bits) <= (uint64_t)w->grid.ncells) ++bits;
+    while ((1ull << bits) <= (uint64_t)g0.ncells) ++bits;
     w->key_bits = bits;
-    if (w->grid.ncells + 2 > w->lb_cap) {
-        CK(dmalloc(&w->LB, (size_t)w->grid.ncells + 2));
-        w->lb_cap = w->grid.ncells + 2;
-        w->gap_cap = w->grid.ncells / GAP_DIRECT + 1024;
+    if (g0.ncells + 2 > w->lb_cap) {
+        CK(dmalloc(&w->LB, (size_t)g0.ncells + 2));
+        w->lb_cap = g0.ncells + 2;
+        w->gap_cap = g0.ncells / GAP_DIRECT + 1024;
         CK(dmalloc(&w->gaps, w->gap_cap));
     }
     // control block
@@ -328,6 +313,12 @@ static gp_status setup_grid(gp_world* w) {
     hc.margin = m_init;
     hc.margin_min = m_init;
     hc.margin_max = m_max;
+    for (int k = 0; k < 3; ++k) hc.lo[k] = lo[k], hc.hi[k] = hi[k];
+    hc.ext_max = ext_max;
+    hc.cell_cfg = c.cell_size;
+    hc.max_cells = g0.ncells;
+    hc.grid = g0;
+    w->max_cells = g0.ncells;
     CK(cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st));
     CK(cudaStreamSynchronize(w->st));
     w->steps_total = 0;
@@ -507,15 +498,15 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
     const int c = w->cur, o = c ^ 1;
     if (n) {
         k_integrate<<<cdiv(n, 256), 256, 0, st>>>(n, w->P[c], w->V[c], w->A, w->Lo, w->Hi, w->P[o], w->V[o], w->box,
-                                                  w->key[0], w->chain_cnt, w->grid, dt, d[0], d[1], d[2]);
+                                                  w->key[0], w->chain_cnt, w->ctl, dt, d[0], d[1], d[2]);
         w->launches++;
         const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], n, w->key_bits, true, w->hist,
                                         w->sm_count, st, &w->launches);
-        k_gather_cells<<<cdiv(n, 256), 256, 0, st>>>(n, w->key[r], w->val[r], w->box, w->sbox, w->LB, w->grid.ncells,
-                                                     w->gaps, w->gap_cap, w->ctl);
+        k_gather_cells<<<cdiv(n, 256), 256, 0, st>>>(n, w->key[r], w->val[r], w->box, w->sbox, w->LB, w->gaps,
+                                                     w->gap_cap, w->ctl);
         k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
-        k_find_pairs<<<cdiv(n, 128), 128, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->grid, w->pairs, w->pending,
-                                                   w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+        k_find_pairs<<<cdiv(n, 128), 128, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt,
+                                                   (uint32_t)w->pair_cap, w->ctl);
         w->launches += 3;
         exclusive_scan_u32(w->chain_cnt, n, w->offs, w->tile_sums, st, &w->launches);
         k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
@@ -556,8 +547,8 @@ static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
     s.margin = c.margin;
     uint32_t mb = c.max_disp_bits;
     memcpy(&s.max_displacement, &mb, 4);
-    s.cell_size = w->cell;
-    s.grid_dim[0] = w->grid.dx, s.grid_dim[1] = w->grid.dy, s.grid_dim[2] = w->grid.dz;
+    s.cell_size = 1.0f / c.grid.inv_cell;
+    s.grid_dim[0] = c.grid.dx, s.grid_dim[1] = c.grid.dy, s.grid_dim[2] = c.grid.dz;
     s.n_heavy = c.n_heavy;
     s.steps_total = w->steps_total;
     s.steps_inexact = c.steps_inexact;
@@ -603,8 +594,8 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
                 fill_stats(w, c, retries);
                 if (stats) *stats = w->last;
                 return fail(w, GP_ERR_MARGIN,
-                            "an AABB moved %.6g during contact resolution, more than the broad-phase margin %.6g "
-                            "(margin_max %.6g): step not applied",
+                            "an AABB moved %.6g of its extent during contact resolution, more than the broad-phase "
+                            "margin %.6g (margin_max %.6g): step not applied",
                             w->last.max_displacement, c.margin, c.margin_max);
             }
             ++retries;  // k_finish_step already doubled the margin; re-run from the untouched input buffers

@@ -52,13 +52,14 @@ struct GridParams {
 // Device-resident control block: everything the kernels of one step communicate through, so that a
 // step needs no host round trip.
 struct Ctl {
-    float margin;             // m used by the current step (K4 inflation, K6 verification)
+    float margin;             // relative margin mu of the current step: body x's AABB is inflated by
+                              // mu * (largest extent of x) in K4, and K6 verifies it never moves further
     float margin_min, margin_max;
     uint32_t n_pairs;         // candidate pairs emitted by K4 (may exceed capacity: then overflow)
     uint32_t n_snapshot;
     uint32_t n_contacts;
     uint32_t n_rounds;
-    uint32_t max_disp_bits;   // max per-axis AABB displacement during the sweep (float bits, >= 0)
+    uint32_t max_disp_bits;   // max over bodies of (per-axis AABB displacement / body extent) during the sweep
     uint32_t frontier_n[3];   // rotating: round r consumes [r%3], fills [(r+1)%3], clears [(r+2)%3]
     uint32_t n_heavy;
     uint32_t n_gaps;
@@ -67,7 +68,37 @@ struct Ctl {
     uint32_t sticky_flags;    // OR of step_flags over async steps
     uint32_t steps_inexact;
     uint32_t steps_total;
+    // uniform grid of the current step; re-derived by k_finish_step whenever the margin changes
+    GridParams grid;
+    float lo[3], hi[3];       // bounds of grid-class body centres (from upload / config)
+    float ext_max;            // upper bound of every grid-class body extent
+    float cell_cfg;           // user cell size (0 = auto)
+    uint32_t max_cells;       // capacity of the cell table
 };
+
+// The 27-neighbourhood search is complete iff cell >= (largest grid-class extent) * (1 + 2*margin); the slack
+// covers the rounding of centre and cell index.  Cells grow until the table fits.
+__host__ __device__ inline GridParams make_grid(const float* lo, const float* hi, float ext_max, float margin,
+                                                float cell_cfg, uint32_t max_cells) {
+    float maxabs = 0.f;
+    for (int k = 0; k < 3; ++k) maxabs = fmaxf(maxabs, fmaxf(fabsf(lo[k]), fabsf(hi[k])));
+    const float need = (ext_max * (1.0f + 2.0f * margin)) * 1.002f + 8.0f * maxabs * 1.2e-7f;
+    float cell = cell_cfg > need ? cell_cfg : need;
+    GridParams g;
+    for (;;) {
+        double ex[3];
+        for (int k = 0; k < 3; ++k) ex[k] = floor(((double)hi[k] - (double)lo[k]) / (double)cell) + 7.0;
+        if (ex[0] * ex[1] * ex[2] <= (double)max_cells && ex[0] < 2.0e9 && ex[1] < 2.0e9 && ex[2] < 2.0e9) {
+            g.dx = (int)ex[0], g.dy = (int)ex[1], g.dz = (int)ex[2];
+            break;
+        }
+        cell *= 1.25f;
+    }
+    g.inv_cell = 1.0f / cell;
+    g.ox = lo[0] - 2.0f * cell, g.oy = lo[1] - 2.0f * cell, g.oz = lo[2] - 2.0f * cell;
+    g.ncells = (uint32_t)g.dx * (uint32_t)g.dy * (uint32_t)g.dz;
+    return g;
+}
 constexpr uint32_t SF_PAIR_OVERFLOW = 1u;
 constexpr uint32_t SF_MARGIN = 2u;       // displacement exceeded the margin used
 constexpr uint32_t SF_MARGIN_MAX = 4u;   // ... and the margin was already margin_max
@@ -285,9 +316,11 @@ __global__ void __launch_bounds__(256)
     k_integrate(uint32_t n, const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
                 const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* __restrict__ P1,
                 float4* __restrict__ V1, float4* __restrict__ box, uint32_t* __restrict__ key,
-                uint32_t* __restrict__ chain_cnt, GridParams g, float dt, float d16, float d18, float d35) {
+                uint32_t* __restrict__ chain_cnt, const Ctl* __restrict__ ctl, float dt, float d16, float d18,
+                float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const GridParams g = ctl->grid;
     float4 p = P0[i], v = V0[i];
     const float4 a = A[i], lo = Lo[i], hi = Hi[i];
     const uint32_t flags = __float_as_uint(a.w);
@@ -357,9 +390,10 @@ __device__ __forceinline__ void fill_cells(uint32_t* LB, uint32_t c0, uint32_t l
 __global__ void __launch_bounds__(256)
     k_gather_cells(uint32_t n, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sval,
                    const float4* __restrict__ box, float4* __restrict__ sbox, uint32_t* __restrict__ LB,
-                   uint32_t ncells, Gap* gaps, uint32_t gap_cap, Ctl* ctl) {
+                   Gap* gaps, uint32_t gap_cap, Ctl* ctl) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t ncells = ctl->grid.ncells;
     const uint32_t v = sval[i];
     const float4 lo = box[2 * (size_t)v], hi = box[2 * (size_t)v + 1];
     sbox[2 * (size_t)i] = lo;
@@ -413,10 +447,16 @@ __device__ __forceinline__ void emit_pair(uint4 rec, bool dyn_a, bool dyn_b, uin
     }
 }
 
-__device__ __forceinline__ void test_candidate(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi,
-                                               float m2, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
-                                               uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
-    // inflated test: (a.lo - b.hi) < 2m on every axis and direction
+__device__ __forceinline__ float box_extent(const float4 lo, const float4 hi) {
+    return fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+}
+
+__device__ __forceinline__ void test_candidate(const float4 alo, const float4 ahi, const float ma, const float4 blo,
+                                               const float4 bhi, float mu, uint4* __restrict__ pairs,
+                                               uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt,
+                                               uint32_t pair_cap, Ctl* ctl) {
+    // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x)
+    const float m2 = ma + mu * box_extent(blo, bhi);
     const bool cand = (alo.x - bhi.x < m2) && (blo.x - ahi.x < m2) && (alo.y - bhi.y < m2) && (blo.y - ahi.y < m2) &&
                       (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
     if (!cand) return;
@@ -434,13 +474,15 @@ __device__ __forceinline__ void test_candidate(const float4 alo, const float4 ah
 
 __global__ void __launch_bounds__(128)
     k_find_pairs(uint32_t n, const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
-                 const uint32_t* __restrict__ LB, GridParams g, uint4* __restrict__ pairs,
-                 uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+                 const uint32_t* __restrict__ LB, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
+                 uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const float m2 = 2.0f * ctl->margin;
+    const GridParams g = ctl->grid;
+    const float mu = ctl->margin;
     const uint32_t n_small = LB[g.ncells];
     const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+    const float ma = mu * box_extent(alo, ahi);
     if (p < n_small) {
         const uint32_t k = skey[p];
         const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
@@ -455,14 +497,14 @@ __global__ void __launch_bounds__(128)
         for (int r = 0; r < 5; ++r) {
             for (uint32_t q = r0[r]; q < r1[r]; ++q) {
                 const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-                test_candidate(alo, ahi, blo, bhi, m2, pairs, pending, chain_cnt, pair_cap, ctl);
+                test_candidate(alo, ahi, ma, blo, bhi, mu, pairs, pending, chain_cnt, pair_cap, ctl);
             }
         }
     }
     // big list: every grid body tests all big bodies; big bodies test the big bodies after them
     for (uint32_t q = max(p + 1, n_small); q < n; ++q) {
         const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-        test_candidate(alo, ahi, blo, bhi, m2, pairs, pending, chain_cnt, pair_cap, ctl);
+        test_candidate(alo, ahi, ma, blo, bhi, mu, pairs, pending, chain_cnt, pair_cap, ctl);
     }
 }
 
@@ -533,14 +575,17 @@ __global__ void __launch_bounds__(256)
         const uint32_t b = offs[x], d = offs[x + 1] - b;
         uint32_t m = 1;
         while (m < d) m <<= 1;
+        // bitonic network in its all-ascending form (first sub-step of each stage mirrors the partner:
+        // l = i ^ (k-1), the rest use l = i ^ j).  Every compare-exchange moves the smaller key to the
+        // lower index, so the virtual +inf padding at [d, m) never has to move.
         for (uint32_t k = 2; k <= m; k <<= 1) {
             for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
                 for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                    const uint32_t l = i ^ j;
-                    if (l > i && l < d) {  // virtual padding (> every key) never moves down
+                    const uint32_t l = i ^ mask;
+                    if (l > i && l < d) {
                         const unsigned long long vi = adj[b + i], vl = adj[b + l];
-                        const bool up = ((i & k) == 0);
-                        if ((vi > vl) == up) {
+                        if (vi > vl) {
                             adj[b + i] = vl;
                             adj[b + l] = vi;
                         }
@@ -630,8 +675,12 @@ __device__ __forceinline__ void frontier_push(uint32_t q, uint32_t* __restrict__
     frontier[base + g.thread_rank()] = q;
 }
 
-__device__ __forceinline__ float max_abs_disp(V3 lo_now, float4 lo_snap) {
-    return fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
+// displacement of an AABB since the K1 snapshot, relative to the body's largest extent
+__device__ __forceinline__ float rel_disp(const BodyRW& x, float4 lo_snap) {
+    const V3 lo_now = x.omin + x.pos;
+    const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
+    const float e = fmaxf(x.omax.x - x.omin.x, fmaxf(x.omax.y - x.omin.y, x.omax.z - x.omin.z));
+    return d / e;  // e == 0 and d > 0 gives +inf: flagged, as it must be
 }
 
 __global__ void __launch_bounds__(256)
@@ -690,9 +739,9 @@ __global__ void __launch_bounds__(256)
                     __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
                 }
                 if (moved) {
-                    // superset check: every AABB must stay within its K1 snapshot inflated by the margin
-                    if (!a.is_static) maxd = fmaxf(maxd, max_abs_disp(a.omin + a.pos, box[2 * (size_t)ia]));
-                    if (!b.is_static) maxd = fmaxf(maxd, max_abs_disp(b.omin + b.pos, box[2 * (size_t)ib]));
+                    // superset check: every AABB must stay within its K1 snapshot inflated by mu * extent
+                    if (!a.is_static) maxd = fmaxf(maxd, rel_disp(a, box[2 * (size_t)ia]));
+                    if (!b.is_static) maxd = fmaxf(maxd, rel_disp(b, box[2 * (size_t)ib]));
                 }
                 if (record_hits) pairs[pid].w = rec.w | TOPBIT;
             }
@@ -745,6 +794,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     float m = fmaxf(2.5f * maxd, 0.9f * c.margin);
     if (c.step_flags & SF_MARGIN) m = fmaxf(m, 2.0f * c.margin);
     c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
+    c.grid = make_grid(c.lo, c.hi, c.ext_max, c.margin, c.cell_cfg, c.max_cells);
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.n_gaps = 0, c.step_flags = 0;
     *ctl = c;

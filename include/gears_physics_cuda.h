@@ -59,9 +59,11 @@ typedef struct gp_config {
     int32_t device;       /* CUDA device ordinal                                                      */
     uint32_t max_bodies;  /* capacity; 0 = sized by the first gp_upload                               */
     uint64_t max_pairs;   /* candidate-pair capacity; 0 = 16 * max_bodies (min 1 Mi)                   */
-    float margin_init;    /* initial broad-phase AABB inflation m; <=0 = auto (0.05 * body extent)    */
-    float margin_max;     /* upper bound for the adaptive m;      <=0 = auto (0.25 * body extent)     */
-    float cell_size;      /* uniform-grid cell edge; <=0 = auto (largest grid-class extent + 2 m_max) */
+    float margin_init;    /* initial (and minimum) broad-phase margin mu, RELATIVE: every AABB is     */
+                          /* inflated by mu * (its largest extent); <=0 = 0.05.  Adapts per step.     */
+    float margin_max;     /* upper bound for the adaptive mu; <=0 = 2.0                               */
+    float cell_size;      /* minimum uniform-grid cell edge; <=0 = auto: (largest grid-class extent)  */
+                          /* * (1 + 2 mu), re-derived on the device whenever mu changes               */
     uint32_t max_big;     /* bodies larger than the cell go to a brute-force list of at most this     */
                           /* many (0 = 64); the cell grows until the rest fit                         */
     uint32_t flags;
@@ -76,8 +78,8 @@ typedef struct gp_step_stats {
     uint64_t n_contacts;     /* |S_sweep|: pairs whose exact test was true at their turn              */
     uint32_t n_rounds;       /* dependency levels executed by the contact sweep                       */
     uint32_t n_retries;      /* times this step was re-run (margin / capacity)                        */
-    float margin;            /* m used for this step                                                  */
-    float max_displacement;  /* largest per-axis move of any AABB during the sweep                    */
+    float margin;            /* relative margin mu used for this step                                 */
+    float max_displacement;  /* largest per-axis move of any AABB during the sweep / its extent       */
     float cell_size;
     uint32_t grid_dim[3];
     uint32_t n_heavy;        /* bodies whose contact chain needed the block-wide sort                 */
