@@ -16,6 +16,9 @@ GP_ERR_BAD_ARG, GP_ERR_CUDA, GP_ERR_NO_DEVICE, GP_ERR_CAPACITY = -1, -2, -3, -4
 GP_ERR_PAIR_OVERFLOW, GP_ERR_MARGIN, GP_ERR_NCCL, GP_ERR_STATE = -5, -6, -7, -8
 GP_FLAG_RECORD_PAIRS = 0x1
 GP_FLAG_NO_RETRY = 0x2
+GP_FLAG_PROFILE = 0x4
+GP_NUM_KERNEL_GROUPS = 8
+KERNEL_GROUPS = ["integrate", "radix_sort", "cells_gather", "find_pairs", "chains", "sweep", "finish", "exchange"]
 GP_UNIQUE_ID_BYTES = 128
 
 f32p = C.POINTER(C.c_float)
@@ -47,11 +50,15 @@ class GpStepStats(C.Structure):
         return d
 
 
+class GpKernelTimes(C.Structure):
+    _fields_ = [("steps", C.c_uint32), ("ms", C.c_float * 8), ("launches", C.c_uint32 * 8)]
+
+
 # every symbol declared in include/gears_physics_cuda.h
 SYMBOLS = [
     "gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_upload", "gp_set_state", "gp_update_dirty",
     "gp_update_shape", "gp_step", "gp_step_async", "gp_sync", "gp_download", "gp_pairs", "gp_damping_factors",
-    "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_comm_unique_id", "gp_comm_init",
+    "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_kernel_times_read", "gp_comm_unique_id", "gp_comm_init",
     "gp_owned_count", "gp_download_owned", "gp_test_radix_sort", "gp_test_radix_sort64", "gp_test_exclusive_scan",
 ]
 
@@ -102,6 +109,8 @@ def lib():
     L.gp_last_step_ms.restype = C.c_int32
     L.gp_kernel_launches.argtypes = [vp]
     L.gp_kernel_launches.restype = C.c_uint64
+    L.gp_kernel_times_read.argtypes = [vp, C.POINTER(GpKernelTimes)]
+    L.gp_kernel_times_read.restype = C.c_int32
     L.gp_comm_unique_id.argtypes = [C.c_void_p]
     L.gp_comm_unique_id.restype = C.c_int32
     L.gp_comm_init.argtypes = [vp, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float]

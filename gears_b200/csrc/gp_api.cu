@@ -58,6 +58,9 @@ struct gp_world {
     uint32_t* frontier[2] = {nullptr, nullptr};
     uint32_t* heavy = nullptr;
     uint32_t heavy_cap = 0;
+    float* dmax = nullptr;        // per body: largest displacement during the current sweep (escapees only, else 0)
+    float* reach = nullptr;       // per body: largest displacement over the earlier sweeps of this step
+    uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0;
     // control
     Ctl *ctl = nullptr, *ctl_snap = nullptr;
@@ -66,6 +69,14 @@ struct gp_world {
     // staging for host-layout arrays
     unsigned char* stage = nullptr;
     size_t stage_bytes = 0;
+
+    // profiling (GP_FLAG_PROFILE): events between kernel groups
+    static constexpr int PROF_STEPS = 512;
+    std::vector<cudaEvent_t> prof_ev;  // (GP_NUM_KERNEL_GROUPS + 1) per step
+    uint32_t prof_n = 0;               // steps recorded since the last read
+    uint32_t prof_launch[GP_NUM_KERNEL_GROUPS] = {};
+    uint64_t prof_mark_launches = 0;
+    int prof_group = -1;
 
     gp_step_stats last{};
     uint64_t steps_total = 0;
@@ -111,7 +122,7 @@ static void free_all(gp_world* w) {
     void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A,     w->Lo,        w->Hi,     w->ext,
                     w->box,    w->sbox,  w->key[0],     w->key[1],     w->val[0], w->val[1],    w->hist,   w->LB,
                     w->gaps,   w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
-                    w->frontier[0], w->frontier[1], w->heavy, w->ctl, w->ctl_snap, w->d_small, w->stage};
+                    w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
@@ -192,6 +203,7 @@ extern "C" void gp_destroy(gp_world* w) {
     if (w->st) cudaStreamSynchronize(w->st);
     if (w->multi) gp_multi_destroy(w->multi);
     free_all(w);
+    for (auto& e : w->prof_ev) cudaEventDestroy(e);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     if (w->st) cudaStreamDestroy(w->st);
@@ -224,6 +236,11 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     CK(dmalloc(&w->chain_cnt, (size_t)cap + 1));
     CK(dmalloc(&w->offs, (size_t)cap + 2));
     CK(dmalloc(&w->tile_sums, (size_t)cdiv(cap, SC_TILE) + 1));
+    CK(dmalloc(&w->dmax, cap));
+    CK(dmalloc(&w->reach, cap));
+    CK(cudaMemset(w->reach, 0, sizeof(float) * (size_t)cap));
+    CK(dmalloc(&w->escapees, cap));
+    CK(cudaMemset(w->dmax, 0, sizeof(float) * (size_t)cap));
     w->cap = cap;
     return GP_OK;
 }
@@ -389,6 +406,8 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
         w->launches++;
         CK(cudaGetLastError());
     }
+    CK(cudaMemsetAsync(w->dmax, 0, sizeof(float) * (size_t)w->cap, w->st));
+    CK(cudaMemsetAsync(w->reach, 0, sizeof(float) * (size_t)w->cap, w->st));
     s = setup_grid(w);
     if (s != GP_OK) return s;
     w->uploaded = true;
@@ -486,8 +505,110 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
     return GP_OK;
 }
 
+// ---- profiling marks: event e(step, g) is recorded BEFORE group g; e(step, NUM) after the last ----
+static inline bool prof_on(const gp_world* w) {
+    return (w->cfg.flags & GP_FLAG_PROFILE) && w->prof_n < (uint32_t)gp_world::PROF_STEPS;
+}
+static void prof_begin_step(gp_world* w) {
+    if (!prof_on(w)) return;
+    if (w->prof_ev.empty()) {
+        w->prof_ev.resize((size_t)gp_world::PROF_STEPS * (GP_NUM_KERNEL_GROUPS + 1));
+        for (auto& e : w->prof_ev) cudaEventCreate(&e);
+    }
+    w->prof_group = -1;
+}
+static void prof_mark(gp_world* w, int group) {  // everything enqueued from here on belongs to `group`
+    if (!prof_on(w)) return;
+    cudaEvent_t* ev = &w->prof_ev[(size_t)w->prof_n * (GP_NUM_KERNEL_GROUPS + 1)];
+    if (w->prof_group >= 0) w->prof_launch[w->prof_group] += (uint32_t)(w->launches - w->prof_mark_launches);
+    // groups may be skipped: give skipped groups a zero-length interval
+    for (int g = w->prof_group + 1; g <= group; ++g) cudaEventRecord(ev[g], w->st);
+    w->prof_group = group;
+    w->prof_mark_launches = w->launches;
+}
+static void prof_end_step(gp_world* w) {
+    if (!prof_on(w)) return;
+    prof_mark(w, GP_NUM_KERNEL_GROUPS);
+    w->prof_n++;
+}
+
+extern "C" gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out) {
+    if (!w || !out) return GP_ERR_BAD_ARG;
+    if (!(w->cfg.flags & GP_FLAG_PROFILE)) return fail(w, GP_ERR_STATE, "gp_kernel_times_read needs GP_FLAG_PROFILE");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->st));
+    memset(out, 0, sizeof *out);
+    out->steps = w->prof_n;
+    for (uint32_t s = 0; s < w->prof_n; ++s) {
+        cudaEvent_t* ev = &w->prof_ev[(size_t)s * (GP_NUM_KERNEL_GROUPS + 1)];
+        for (int g = 0; g < GP_NUM_KERNEL_GROUPS; ++g) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[g], ev[g + 1]));
+            out->ms[g] += ms;
+        }
+    }
+    for (int g = 0; g < GP_NUM_KERNEL_GROUPS; ++g) out->launches[g] = w->prof_launch[g], w->prof_launch[g] = 0;
+    w->prof_n = 0;
+    return GP_OK;
+}
+
+// K5 + K6: chain offsets, fill, sort, cooperative sweep.  gate != nullptr: every kernel is a no-op
+// unless *gate != 0 (repair rounds that turn out not to be needed cost a few empty launches).
+static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
+    const uint32_t n = w->n;
+    cudaStream_t st = w->st;
+    const int o = w->cur ^ 1;
+    exclusive_scan_u32(w->chain_cnt, n, w->offs, w->tile_sums, st, &w->launches, gate);
+    k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
+                                                   w->ctl, gate);
+    k_sort_chains<<<cdiv(n, 256), 256, 0, st>>>(n, w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
+    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
+    w->launches += 3;
+    if (!gate) prof_mark(w, 5);
+    float4 *Pn = w->P[o], *Vn = w->V[o];
+    const float4 *Lo = w->Lo, *Hi = w->Hi, *box = w->box;
+    uint4* pairs = w->pairs;
+    uint32_t pair_cap = (uint32_t)w->pair_cap;
+    const uint32_t* offs = w->offs;
+    uint32_t* chain_cnt = w->chain_cnt;
+    const unsigned long long* adj = w->adj;
+    uint32_t* pending = w->pending;
+    uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
+    Ctl* ctl = w->ctl;
+    float* dmax = w->dmax;
+    const float* reach = w->reach;
+    uint32_t* esc = w->escapees;
+    uint32_t esc_cap = w->cap;
+    void* args[] = {&Pn, &Vn, &Lo, &Hi, &box, &pairs, &pair_cap, &offs, &chain_cnt, &adj, &pending,
+                    &f0, &f1, &ctl, &dmax, &reach, &esc, &esc_cap, &gate};
+    CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
+    w->launches++;
+    return GP_OK;
+}
+
+// One repair round (all kernels gated on ctl->repair_needed), ending with a fresh k_requery.
+static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
+    const uint32_t n = w->n;
+    cudaStream_t st = w->st;
+    const int c = w->cur, o = c ^ 1;
+    const uint32_t* gate = &w->ctl->repair_needed;
+    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->P[c], w->V[c], w->A, w->P[o],
+                                               w->V[o], w->chain_cnt, w->pending, w->dmax, w->reach, w->escapees, w->cap,
+                                               w->ctl, dt, d[0], d[1], d[2]);
+    k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
+    k_repair_reset<<<1, 1, 0, st>>>(w->ctl);
+    w->launches += 3;
+    gp_status s = enqueue_chains_and_sweep(w, gate);
+    if (s != GP_OK) return s;
+    k_repair_done<<<1, 1, 0, st>>>(w->ctl);
+    k_requery<<<w->sm_count * 4, 256, 0, st>>>(n, w->box, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap, w->pairs,
+                                               w->pending, (uint32_t)w->pair_cap, w->ctl);
+    w->launches += 2;
+    return GP_OK;
+}
+
 // Enqueue the kernels of one step.  Reads P/V[cur], leaves the result in P/V[cur^1].
-static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch) {
+static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch, int repair_rounds) {
     const uint32_t n = w->n;
     cudaStream_t st = w->st;
     float d[3];
@@ -496,41 +617,38 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
     else
         gp_damping_factors(dt, d);
     const int c = w->cur, o = c ^ 1;
+    prof_begin_step(w);
     if (n) {
+        prof_mark(w, 0);
         k_integrate<<<cdiv(n, 256), 256, 0, st>>>(n, w->P[c], w->V[c], w->A, w->Lo, w->Hi, w->P[o], w->V[o], w->box,
                                                   w->key[0], w->chain_cnt, w->ctl, dt, d[0], d[1], d[2]);
         w->launches++;
+        prof_mark(w, 1);
         const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], n, w->key_bits, true, w->hist,
                                         w->sm_count, st, &w->launches);
+        prof_mark(w, 2);
         k_gather_cells<<<cdiv(n, 256), 256, 0, st>>>(n, w->key[r], w->val[r], w->box, w->sbox, w->LB, w->gaps,
                                                      w->gap_cap, w->ctl);
         k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
+        w->launches += 2;
+        prof_mark(w, 3);
         k_find_pairs<<<cdiv(n, 128), 128, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt,
                                                    (uint32_t)w->pair_cap, w->ctl);
-        w->launches += 3;
-        exclusive_scan_u32(w->chain_cnt, n, w->offs, w->tile_sums, st, &w->launches);
-        k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
-                                                       w->ctl);
-        k_sort_chains<<<cdiv(n, 256), 256, 0, st>>>(n, w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl);
-        k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl);
-        w->launches += 3;
-        float4 *Pn = w->P[o], *Vn = w->V[o];
-        const float4 *Lo = w->Lo, *Hi = w->Hi, *box = w->box;
-        uint4* pairs = w->pairs;
-        uint32_t pair_cap = (uint32_t)w->pair_cap;
-        const uint32_t* offs = w->offs;
-        uint32_t* chain_cnt = w->chain_cnt;
-        const unsigned long long* adj = w->adj;
-        uint32_t* pending = w->pending;
-        uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
-        Ctl* ctl = w->ctl;
-        int record = (w->cfg.flags & GP_FLAG_RECORD_PAIRS) ? 1 : 0;
-        void* args[] = {&Pn, &Vn, &Lo, &Hi, &box, &pairs, &pair_cap, &offs, &chain_cnt, &adj, &pending, &f0, &f1, &ctl, &record};
-        CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
+        w->launches += 1;
+        prof_mark(w, 4);
+        enqueue_chains_and_sweep(w, nullptr);
+        // speculative broad phase: look for pairs the margin missed, repair, look again
+        k_requery<<<w->sm_count * 4, 256, 0, st>>>(n, w->box, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap, w->pairs,
+                                                   w->pending, (uint32_t)w->pair_cap, w->ctl);
+        w->launches++;
+        for (int r = 0; r < repair_rounds; ++r) enqueue_repair_round(w, dt, d);
+        k_clear_escapees<<<w->sm_count, 256, 0, st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, latch);
         w->launches++;
     }
+    prof_mark(w, 6);
     k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
     w->launches++;
+    prof_end_step(w);
     CK(cudaGetLastError());
     return GP_OK;
 }
@@ -543,7 +661,7 @@ static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
     s.n_snapshot = c.n_snapshot;
     s.n_contacts = c.n_contacts;
     s.n_rounds = c.n_rounds;
-    s.n_retries = retries;
+    s.n_retries = retries + c.n_repairs;
     s.margin = c.margin;
     uint32_t mb = c.max_disp_bits;
     memcpy(&s.max_displacement, &mb, 4);
@@ -561,6 +679,8 @@ static gp_status read_ctl(gp_world* w) {
     return GP_OK;
 }
 
+static const int REPAIR_ROUNDS_ENQUEUED = 2;  // gated repair rounds pre-enqueued per step (no-ops when not needed)
+
 extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_stats* stats) {
     if (!w) return GP_ERR_BAD_ARG;
     if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_step before gp_upload");
@@ -568,16 +688,35 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
     if (w->multi) return gp_multi_step(w->multi, dt, damp3, stats);
     gp_status result = GP_OK;
     uint32_t retries = 0;
+    float d[3];
+    if (damp3)
+        d[0] = damp3[0], d[1] = damp3[1], d[2] = damp3[2];
+    else
+        gp_damping_factors(dt, d);
+    const bool no_retry = (w->cfg.flags & GP_FLAG_NO_RETRY) != 0;
     CK(cudaEventRecord(w->ev0, w->st));
     for (;;) {
-        gp_status s = enqueue_step(w, dt, damp3, 0);
+        gp_status s = enqueue_step(w, dt, damp3, 0, no_retry ? 0 : REPAIR_ROUNDS_ENQUEUED);
         if (s != GP_OK) return s;
         s = read_ctl(w);
         if (s != GP_OK) return s;
+        // the candidate set was still growing: keep repairing until k_requery finds nothing (exact result)
+        int extra = 0;
+        while (w->h_ctl->step_flags == SF_MARGIN && !no_retry && extra < 64) {
+            for (int r = 0; r < 2; ++r) {
+                s = enqueue_repair_round(w, dt, d);
+                if (s != GP_OK) return s;
+            }
+            k_clear_escapees<<<w->sm_count, 256, 0, w->st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, 0);
+            k_finish_step<<<1, 1, 0, w->st>>>(w->ctl, w->ctl_snap, 0);
+            w->launches += 2;
+            s = read_ctl(w);
+            if (s != GP_OK) return s;
+            ++extra;
+        }
         const Ctl& c = *w->h_ctl;
         const uint32_t f = c.step_flags;
-        const bool no_retry = (w->cfg.flags & GP_FLAG_NO_RETRY) != 0;
-        if (f & (SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW))
+        if (f & (SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW))
             return fail(w, GP_ERR_CAPACITY, "internal work list overflow (flags 0x%x)", f);
         if (f & SF_PAIR_OVERFLOW) {
             if (no_retry || retries >= 8)
@@ -587,21 +726,23 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
             if (a != GP_OK) return a;
             ++retries;
             result = GP_WARN_MARGIN_RETRIED;
-            continue;
+            continue;  // k_finish_step reset the step; re-run it from the untouched input buffers
         }
         if (f & SF_MARGIN) {
-            if ((f & SF_MARGIN_MAX) || no_retry || retries >= 16) {
-                fill_stats(w, c, retries);
-                if (stats) *stats = w->last;
-                return fail(w, GP_ERR_MARGIN,
-                            "an AABB moved %.6g of its extent during contact resolution, more than the broad-phase "
-                            "margin %.6g (margin_max %.6g): step not applied",
-                            w->last.max_displacement, c.margin, c.margin_max);
-            }
-            ++retries;  // k_finish_step already doubled the margin; re-run from the untouched input buffers
-            result = GP_WARN_MARGIN_RETRIED;
-            continue;
+            fill_stats(w, c, retries);
+            if (stats) *stats = w->last;
+            const uint32_t nrep = c.n_repairs;
+            const float mrg = c.margin;
+            // give up on this step: drop the escapee marks and per-step counters (input buffers are untouched)
+            k_clear_escapees<<<w->sm_count, 256, 0, w->st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, 1);
+            k_finish_step<<<1, 1, 0, w->st>>>(w->ctl, w->ctl_snap, 2);
+            w->launches += 2;
+            CK(cudaStreamSynchronize(w->st));
+            return fail(w, GP_ERR_MARGIN,
+                        "the candidate pair set was still growing after %u repair sweeps (margin %.4g): step not applied",
+                        nrep, mrg);
         }
+        if (c.n_repairs) result = GP_WARN_MARGIN_RETRIED;
         w->cur ^= 1;
         w->steps_total++;
         fill_stats(w, c, retries);
@@ -620,7 +761,7 @@ extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, ui
     if (w->multi) return gp_multi_step_async(w->multi, dt, damp3, nsteps);
     CK(cudaEventRecord(w->ev0, w->st));
     for (uint32_t s = 0; s < nsteps; ++s) {
-        gp_status r = enqueue_step(w, dt, damp3, 1);
+        gp_status r = enqueue_step(w, dt, damp3, 1, REPAIR_ROUNDS_ENQUEUED);
         if (r != GP_OK) return r;
         w->cur ^= 1;
         w->steps_total++;
@@ -653,8 +794,9 @@ extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
             return fail(w, GP_ERR_PAIR_OVERFLOW, "%u async step(s) were inexact: candidate pairs exceeded max_pairs",
                         c.steps_inexact);
         if (f & SF_MARGIN)
-            return fail(w, GP_ERR_MARGIN, "%u async step(s) were inexact: an AABB moved further than the margin",
-                        c.steps_inexact);
+            return fail(w, GP_ERR_MARGIN,
+                        "%u async step(s) were inexact: the candidate pair set was still growing when the "
+                        "pre-enqueued repair sweeps ran out", c.steps_inexact);
         return fail(w, GP_ERR_CAPACITY, "%u async step(s) hit an internal work list overflow (0x%x)", c.steps_inexact, f);
     }
     return GP_OK;

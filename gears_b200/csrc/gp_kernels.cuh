@@ -68,6 +68,13 @@ struct Ctl {
     uint32_t sticky_flags;    // OR of step_flags over async steps
     uint32_t steps_inexact;
     uint32_t steps_total;
+    // speculative broad phase: bodies that left their margin during the sweep, and the repair loop
+    uint32_t n_escapees;
+    uint32_t max_abs_disp_bits;  // largest absolute per-axis displacement of any escapee this sweep
+    uint32_t repair_needed;      // set by k_requery when it appended pairs; gates the repair kernels
+    uint32_t n_repairs;          // repair sweeps executed this step
+    uint32_t n_pairs_swept;      // pairs covered by the last sweep (k_requery appends after them)
+    uint32_t n_escapees_total;   // stats: escapees of the first sweep
     // uniform grid of the current step; re-derived by k_finish_step whenever the margin changes
     GridParams grid;
     float lo[3], hi[3];       // bounds of grid-class body centres (from upload / config)
@@ -100,10 +107,11 @@ __host__ __device__ inline GridParams make_grid(const float* lo, const float* hi
     return g;
 }
 constexpr uint32_t SF_PAIR_OVERFLOW = 1u;
-constexpr uint32_t SF_MARGIN = 2u;       // displacement exceeded the margin used
-constexpr uint32_t SF_MARGIN_MAX = 4u;   // ... and the margin was already margin_max
+constexpr uint32_t SF_MARGIN = 2u;       // the candidate set was still growing when the repair rounds ran out
+constexpr uint32_t SF_MARGIN_MAX = 4u;   // (unused)
 constexpr uint32_t SF_GAP_OVERFLOW = 8u;
 constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
+constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
 
 struct V3 {
     float x, y, z;
@@ -308,6 +316,34 @@ __global__ void k_unpack(uint32_t n, const float4* __restrict__ P, const float4*
     }
 }
 
+// RigidBody::update_pos, physics.rs:405-462 (a.w carries the flags; static bodies are untouched)
+__device__ __forceinline__ void integrate_body(float4& p, float4& v, const float4 a, float dt, float d16, float d18,
+                                               float d35) {
+    if (__float_as_uint(a.w) & F_STATIC) return;
+    const bool falling = v.y < 0.0f;
+    const bool near_apex = fabsf(v.y) < 2.0f && v.y > 0.0f;
+    const float gm = falling ? FALL_MULTIPLIER : (near_apex ? APEX_MULTIPLIER : 1.0f);
+    v.y = v.y - ((GRAVITY_ACCELERATION * gm) * dt);
+    const bool accelerating = len3(mk(a.x, a.y, a.z)) > 0.01f;
+    const float d = accelerating ? d16 : (falling ? d18 : d35);
+    if (falling) {
+        v.x = v.x * d;
+        v.z = v.z * d;
+    } else {
+        v.x = v.x * d;
+        v.y = v.y * d;
+        v.z = v.z * d;
+    }
+    v.x = v.x + a.x * dt;
+    v.z = v.z + a.z * dt;
+    if (len3(mk(v.x, v.y, v.z)) < 0.005f) {
+        v.x = 0.0f, v.y = 0.0f, v.z = 0.0f;
+    }
+    p.x = p.x + v.x * dt;
+    p.y = p.y + v.y * dt;
+    p.z = p.z + v.z * dt;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: fused integrate + world AABB + cell key.  One thread per body, float4 (128-bit) coalesced
 // access on every array.  R 80 B (P,V,A,Lo,Hi) + W 32 (P',V') + W 32 (box) + W 4 (key) + W 4 (chain counter).
@@ -324,31 +360,7 @@ __global__ void __launch_bounds__(256)
     float4 p = P0[i], v = V0[i];
     const float4 a = A[i], lo = Lo[i], hi = Hi[i];
     const uint32_t flags = __float_as_uint(a.w);
-    if (!(flags & F_STATIC)) {
-        // physics.rs:405-462
-        const bool falling = v.y < 0.0f;
-        const bool near_apex = fabsf(v.y) < 2.0f && v.y > 0.0f;
-        const float gm = falling ? FALL_MULTIPLIER : (near_apex ? APEX_MULTIPLIER : 1.0f);
-        v.y = v.y - ((GRAVITY_ACCELERATION * gm) * dt);
-        const bool accelerating = len3(mk(a.x, a.y, a.z)) > 0.01f;
-        const float d = accelerating ? d16 : (falling ? d18 : d35);
-        if (falling) {
-            v.x = v.x * d;
-            v.z = v.z * d;
-        } else {
-            v.x = v.x * d;
-            v.y = v.y * d;
-            v.z = v.z * d;
-        }
-        v.x = v.x + a.x * dt;
-        v.z = v.z + a.z * dt;
-        if (len3(mk(v.x, v.y, v.z)) < 0.005f) {
-            v.x = 0.0f, v.y = 0.0f, v.z = 0.0f;
-        }
-        p.x = p.x + v.x * dt;
-        p.y = p.y + v.y * dt;
-        p.z = p.z + v.z * dt;
-    }
+    integrate_body(p, v, a, dt, d16, d18, d35);
     P1[i] = p;
     V1[i] = v;
     // world AABB = offsets + position
@@ -451,15 +463,18 @@ __device__ __forceinline__ float box_extent(const float4 lo, const float4 hi) {
     return fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
 }
 
+__device__ __forceinline__ bool inflated_overlap(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi,
+                                                 float m2) {
+    return (alo.x - bhi.x < m2) && (blo.x - ahi.x < m2) && (alo.y - bhi.y < m2) && (blo.y - ahi.y < m2) &&
+           (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
+}
+
 __device__ __forceinline__ void test_candidate(const float4 alo, const float4 ahi, const float ma, const float4 blo,
                                                const float4 bhi, float mu, uint4* __restrict__ pairs,
                                                uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt,
                                                uint32_t pair_cap, Ctl* ctl) {
     // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x)
-    const float m2 = ma + mu * box_extent(blo, bhi);
-    const bool cand = (alo.x - bhi.x < m2) && (blo.x - ahi.x < m2) && (alo.y - bhi.y < m2) && (blo.y - ahi.y < m2) &&
-                      (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
-    if (!cand) return;
+    if (!inflated_overlap(alo, ahi, blo, bhi, ma + mu * box_extent(blo, bhi))) return;
     const uint32_t ta = __float_as_uint(alo.w), tb = __float_as_uint(blo.w);
     if ((ta & tb) & TOPBIT) return;  // static-static: no-op in the reference (physics.rs:225)
     const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
@@ -516,7 +531,9 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_fill_chains(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
-                  uint32_t* __restrict__ chain_cnt, unsigned long long* __restrict__ adj, const Ctl* ctl) {
+                  uint32_t* __restrict__ chain_cnt, unsigned long long* __restrict__ adj, const Ctl* ctl,
+                  const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < np; pid += gridDim.x * blockDim.x) {
         const uint4 r = pairs[pid];
@@ -538,7 +555,9 @@ constexpr uint32_t CHAIN_INLINE = 48;  // longer chains go to the block-wide sor
 
 __global__ void __launch_bounds__(256)
     k_sort_chains(uint32_t n, const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj,
-                  uint32_t* __restrict__ pending, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl) {
+                  uint32_t* __restrict__ pending, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl,
+                  const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
     const uint32_t b = offs[x], e = offs[x + 1];
@@ -568,7 +587,9 @@ __global__ void __launch_bounds__(256)
 // one CTA per heavy body: bitonic sort of its segment in global memory (any length)
 __global__ void __launch_bounds__(256)
     k_sort_heavy(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending,
-                 const uint32_t* __restrict__ heavy, uint32_t heavy_cap, const Ctl* ctl) {
+                 const uint32_t* __restrict__ heavy, uint32_t heavy_cap, const Ctl* ctl,
+                 const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const uint32_t nh = min(ctl->n_heavy, heavy_cap);
     for (uint32_t hi = blockIdx.x; hi < nh; hi += gridDim.x) {
         const uint32_t x = heavy[hi];
@@ -675,12 +696,31 @@ __device__ __forceinline__ void frontier_push(uint32_t q, uint32_t* __restrict__
     frontier[base + g.thread_rank()] = q;
 }
 
-// displacement of an AABB since the K1 snapshot, relative to the body's largest extent
-__device__ __forceinline__ float rel_disp(const BodyRW& x, float4 lo_snap) {
+// A body whose AABB leaves its K1 snapshot inflated by mu*extent is an ESCAPEE: the candidate set built
+// from the snapshot may miss pairs it reaches.  dmax[x] keeps the largest per-axis displacement it had at
+// any time in the current sweep (its swept AABB is inside snapshot (+) dmax); reach[x] is the largest dmax of
+// the earlier sweeps of this step.  k_requery looks for the pairs the candidate set missed.
+// Only one thread touches a dynamic body per round, so plain (L2) accesses suffice.
+__device__ __forceinline__ void track_escape(const BodyRW& x, uint32_t ix, float4 lo_snap, float mu_verify,
+                                             float* __restrict__ dmax, const float* __restrict__ reach,
+                                             uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl,
+                                             float& maxrel, float& maxabs) {
     const V3 lo_now = x.omin + x.pos;
     const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
     const float e = fmaxf(x.omax.x - x.omin.x, fmaxf(x.omax.y - x.omin.y, x.omax.z - x.omin.z));
-    return d / e;  // e == 0 and d > 0 gives +inf: flagged, as it must be
+    maxrel = fmaxf(maxrel, d / e);
+    if (!(d <= mu_verify * e)) {
+        const float old = __ldcg(&dmax[ix]);
+        if (old == 0.0f && reach[ix] == 0.0f) {  // first escape of this body in this step
+            const uint32_t s = atomicAdd(&ctl->n_escapees, 1u);
+            if (s < esc_cap)
+                escapees[s] = ix;
+            else
+                atomicOr(&ctl->step_flags, SF_ESCAPEE_OVERFLOW);
+        }
+        if (d > old) __stcg(&dmax[ix], d);
+        maxabs = fmaxf(maxabs, d);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -688,7 +728,9 @@ __global__ void __launch_bounds__(256)
             const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
             const uint32_t* __restrict__ offs, uint32_t* __restrict__ chain_cnt,
             const unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending, uint32_t* __restrict__ frontier0,
-            uint32_t* __restrict__ frontier1, Ctl* ctl, int record_hits) {
+            uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax, const float* __restrict__ reach,
+            uint32_t* __restrict__ escapees, uint32_t esc_cap, const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // uniform across the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -698,7 +740,7 @@ __global__ void __launch_bounds__(256)
     grid.sync();
     const float mverify = 0.98f * ctl->margin;
     uint32_t rounds = 0, contacts = 0;
-    float maxd = 0.0f;
+    float maxd = 0.0f, maxabs = 0.0f;
     while (true) {
         const uint32_t ci = rounds % 3u, co = (rounds + 1u) % 3u, cz = (rounds + 2u) % 3u;
         const uint32_t nf = __ldcg(&ctl->frontier_n[ci]);
@@ -739,11 +781,12 @@ __global__ void __launch_bounds__(256)
                     __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
                 }
                 if (moved) {
-                    // superset check: every AABB must stay within its K1 snapshot inflated by mu * extent
-                    if (!a.is_static) maxd = fmaxf(maxd, rel_disp(a, box[2 * (size_t)ia]));
-                    if (!b.is_static) maxd = fmaxf(maxd, rel_disp(b, box[2 * (size_t)ib]));
+                    if (!a.is_static)
+                        track_escape(a, ia, box[2 * (size_t)ia], mverify, dmax, reach, escapees, esc_cap, ctl, maxd, maxabs);
+                    if (!b.is_static)
+                        track_escape(b, ib, box[2 * (size_t)ib], mverify, dmax, reach, escapees, esc_cap, ctl, maxd, maxabs);
                 }
-                if (record_hits) pairs[pid].w = rec.w | TOPBIT;
+                pairs[pid].w = rec.w | TOPBIT;  // S_sweep flag; also tells k_restore which bodies were written
             }
             // pop the chains; wake pairs that reached the head everywhere
 #pragma unroll
@@ -768,35 +811,205 @@ __global__ void __launch_bounds__(256)
     for (int o = 16; o > 0; o >>= 1) {
         contacts += __shfl_xor_sync(0xffffffffu, contacts, o);
         maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        maxabs = fmaxf(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, o));
     }
     if ((threadIdx.x & 31) == 0) {
         if (contacts) atomicAdd(&ctl->n_contacts, contacts);
         if (maxd > 0.0f) atomicMax(&ctl->max_disp_bits, __float_as_uint(maxd));
-        if (maxd > mverify) atomicOr(&ctl->step_flags, SF_MARGIN);
+        if (maxabs > 0.0f) atomicMax(&ctl->max_abs_disp_bits, __float_as_uint(maxabs));
     }
-    if (gtid == 0) ctl->n_rounds = rounds;
+    if (gtid == 0) {
+        ctl->n_rounds = rounds;
+        ctl->n_pairs_swept = np;
+    }
 }
 
-// End of step: latch failures, adapt the margin for the next step, reset per-step counters.
+// ---------------------------------------------------------------------------------------------
+// Repair loop of the speculative broad phase.
+//  k_requery : for every escapee x, find the bodies y with swept(x) ^ swept(y) != {} that are NOT
+//              candidates yet, append those pairs, raise ctl->repair_needed.  One warp per escapee; the
+//              grid rows its query box covers are contiguous runs of the cell-sorted AABB array.
+//  k_restore : (gated) undo the sweep: re-integrate the bodies written by hit pairs from the untouched
+//              input buffers, clear hit flags / chain counters / pending / escapee marks.
+//  k_recount : (gated) chain degrees over old + new pairs.  Then scan, fill, sort and sweep run again.
+// When k_requery appends nothing the last sweep saw every pair that could intersect at its turn: the
+// result equals the reference's full O(N^2) sweep.
+// ---------------------------------------------------------------------------------------------
+// Candidate predicate of the whole step: overlap(snap x, snap y, r_x + r_y), r_x = max(mu*extent(x), reach[x]).
+// K4 built the set for reach = 0; a sweep in which x moved by dmax[x] > reach[x] extends it.  The pairs that
+// pass with the grown reaches but not with the old ones are exactly the new ones (no duplicates).
+constexpr float REACH_SLACK = 1.0001f;  // covers the rounding of the measured displacement
+
+__global__ void __launch_bounds__(256)
+    k_requery(uint32_t n, const float4* __restrict__ box, const float4* __restrict__ sbox,
+              const uint32_t* __restrict__ LB, const float* __restrict__ dmax, const float* __restrict__ reach,
+              const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint4* __restrict__ pairs,
+              uint32_t* __restrict__ pending, uint32_t pair_cap, Ctl* ctl) {
+    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+    if (ne == 0) return;
+    const GridParams g = ctl->grid;
+    const float mu = ctl->margin;
+    const float ext_max = ctl->ext_max;
+    const float partner_reach = fmaxf(mu * ext_max, __uint_as_float(ctl->max_abs_disp_bits) * REACH_SLACK);
+    const uint32_t n_small = LB[g.ncells];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t ei = warp; ei < ne; ei += nwarps) {
+        const uint32_t x = escapees[ei];
+        const float rx_prev = reach[x];
+        const float rx_now = dmax[x] * REACH_SLACK;
+        if (!(rx_now > rx_prev)) continue;  // did not move further than in an earlier sweep
+        const float4 alo = box[2 * (size_t)x], ahi = box[2 * (size_t)x + 1];
+        const float ma = mu * box_extent(alo, ahi);
+        const float ra_old = fmaxf(ma, rx_prev), ra_new = fmaxf(ma, rx_now);
+        const uint32_t ta = __float_as_uint(alo.w), ra = __float_as_uint(ahi.w);
+        // partner centres lie within the query box grown by the partner's own reach and half extent
+        const float grow = (ra_new + partner_reach) * 1.001f + 0.5f * ext_max * 1.001f;
+        int c0[3], c1[3];
+        {
+            const float lo3[3] = {alo.x - grow, alo.y - grow, alo.z - grow};
+            const float hi3[3] = {ahi.x + grow, ahi.y + grow, ahi.z + grow};
+            const float o3[3] = {g.ox, g.oy, g.oz};
+            const int d3[3] = {g.dx, g.dy, g.dz};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                c0[k] = min(max(__float2int_rd((lo3[k] - o3[k]) * g.inv_cell) + 1, 1), d3[k] - 2);
+                c1[k] = min(max(__float2int_rd((hi3[k] - o3[k]) * g.inv_cell) + 1, 1), d3[k] - 2);
+            }
+        }
+        auto test = [&](uint32_t q) {
+            const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
+            const uint32_t tb = __float_as_uint(blo.w);
+            const uint32_t y = tb & ~TOPBIT;
+            if (y == x) return;
+            const float mb = mu * box_extent(blo, bhi);
+            const float ry_prev = reach[y], ry_now = dmax[y] * REACH_SLACK;
+            const float rb_old = fmaxf(mb, ry_prev), rb_new = fmaxf(rb_old, ry_now);
+            if (inflated_overlap(alo, ahi, blo, bhi, ra_old + rb_old)) return;   // found in an earlier round / by K4
+            if (!inflated_overlap(alo, ahi, blo, bhi, ra_new + rb_new)) return;  // still out of reach
+            if (ry_now > ry_prev && y < x) return;  // y grew too: its own query reports the pair
+            const uint32_t rb = __float_as_uint(bhi.w);
+            uint4 rec = (ra < rb) ? make_uint4(ta, tb, ra, rb) : make_uint4(tb, ta, rb, ra);
+            cg::coalesced_group cgp = cg::coalesced_threads();
+            uint32_t base = 0;
+            if (cgp.thread_rank() == 0) base = atomicAdd(&ctl->n_pairs, cgp.size());
+            base = cgp.shfl(base, 0);
+            const uint32_t slot = base + cgp.thread_rank();
+            if (slot < pair_cap) {
+                pairs[slot] = rec;
+                pending[slot] = 0;
+            } else {
+                atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+            }
+            ctl->repair_needed = 1u;
+        };
+        for (int z = c0[2]; z <= c1[2]; ++z)
+            for (int y = c0[1]; y <= c1[1]; ++y) {
+                const uint32_t rowk = (uint32_t)g.dx * ((uint32_t)y + (uint32_t)g.dy * (uint32_t)z);
+                const uint32_t q0 = LB[rowk + (uint32_t)c0[0]], q1 = LB[rowk + (uint32_t)c1[0] + 1u];
+                for (uint32_t q = q0 + lane; q < q1; q += 32) test(q);
+            }
+        for (uint32_t q = n_small + lane; q < n; q += 32) test(q);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const float4* __restrict__ P0, const float4* __restrict__ V0,
+              const float4* __restrict__ A, float4* __restrict__ P1, float4* __restrict__ V1,
+              uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ pending, float* __restrict__ dmax,
+              float* __restrict__ reach, const uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl, float dt,
+              float d16, float d18, float d35) {
+    if (ctl->repair_needed == 0) return;
+    const uint32_t np = min(ctl->n_pairs, pair_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t pid = gtid; pid < np; pid += gsz) {
+        uint4 r = pairs[pid];
+        pending[pid] = 0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t t = s ? r.y : r.x;
+            if (t & TOPBIT) continue;
+            chain_cnt[t] = 0;
+            if (r.w & TOPBIT) {  // the sweep wrote this body: recompute its post-integration state (idempotent)
+                float4 p = P0[t], v = V0[t];
+                integrate_body(p, v, A[t], dt, d16, d18, d35);
+                P1[t] = p;
+                V1[t] = v;
+            }
+        }
+        if (r.w & TOPBIT) pairs[pid].w = r.w & ~TOPBIT;
+    }
+    // the pairs within the grown reaches are now candidates: commit the reaches, start a fresh sweep record
+    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+    for (uint32_t e = gtid; e < ne; e += gsz) {
+        const uint32_t x = escapees[e];
+        reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
+        dmax[x] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_recount(const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ chain_cnt, Ctl* ctl) {
+    if (ctl->repair_needed == 0) return;
+    const uint32_t np = min(ctl->n_pairs, pair_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t pid = gtid; pid < np; pid += gsz) {
+        const uint4 r = pairs[pid];
+        if (!(r.x & TOPBIT)) atomicAdd(&chain_cnt[r.x], 1u);
+        if (!(r.y & TOPBIT)) atomicAdd(&chain_cnt[r.y], 1u);
+    }
+}
+
+// between k_recount and the repair sweep: per-sweep counters back to zero (after every reader of them ran)
+__global__ void k_repair_reset(Ctl* ctl) {
+    if (ctl->repair_needed == 0) return;
+    ctl->max_disp_bits = 0;
+    ctl->n_contacts = 0;
+    ctl->n_heavy = 0;
+    ctl->frontier_n[0] = ctl->frontier_n[1] = ctl->frontier_n[2] = 0;
+    ctl->n_repairs += 1;
+}
+// after the repair sweep: the next k_requery decides again
+__global__ void k_repair_done(Ctl* ctl) { ctl->repair_needed = 0; }
+
+// escapee marks are only read by k_requery; clear them once the last one ran (k_restore does the same)
+__global__ void __launch_bounds__(256)
+    k_clear_escapees(float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ escapees,
+                     uint32_t esc_cap, const Ctl* ctl, int force) {
+    if (!force && ctl->repair_needed) return;  // the repair loop goes on (sync mode): k_restore needs the marks
+    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        dmax[escapees[e]] = 0.0f;
+        reach[escapees[e]] = 0.0f;
+    }
+}
+
+// End of step: a last k_requery has run; if it still found pairs the step is inexact (async) or the host
+// runs more repair rounds (sync).  Adapt the margin, reset per-step counters, clear escapee marks.
 __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     Ctl c = *ctl;
-    const float maxd = __uint_as_float(c.max_disp_bits);
-    if ((c.step_flags & SF_MARGIN) && c.margin >= c.margin_max) c.step_flags |= SF_MARGIN_MAX;
-    if (latch) {  // async stepping: failures are latched, the host looks later
-        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW)) {
+    if (c.repair_needed) c.step_flags |= SF_MARGIN;
+    if (latch == 1) {  // async stepping: failures are latched, the host looks later
+        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW)) {
             c.steps_inexact += 1;
             c.sticky_flags |= c.step_flags;
         }
         c.steps_total += 1;
     }
     *snapshot_out = c;  // what the host reads (stats of THIS step)
-    // next margin: at least twice what was just needed, slow decay otherwise
-    float m = fmaxf(2.5f * maxd, 0.9f * c.margin);
-    if (c.step_flags & SF_MARGIN) m = fmaxf(m, 2.0f * c.margin);
+    if (latch == 0 && c.step_flags == SF_MARGIN) return;  // sync mode: the host continues the repair loop
+    // (latch == 2: the host gave up on this step; just reset)
+    // margin: grow when the step needed repair sweeps, relax slowly otherwise
+    float m = c.margin;
+    if (c.n_repairs > 0)
+        m *= 1.5f;
+    else
+        m *= 0.97f;
     c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
     c.grid = make_grid(c.lo, c.hi, c.ext_max, c.margin, c.cell_cfg, c.max_cells);
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.n_gaps = 0, c.step_flags = 0;
+    c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
     *ctl = c;
 }
 

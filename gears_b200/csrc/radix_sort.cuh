@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const KeyT* __restrict_
 }
 
 // exclusive scan of m counters in place, one CTA
-__global__ void __launch_bounds__(RS_SCAN_THREADS) rs_scan(uint32_t* __restrict__ hist, uint32_t m) {
+__global__ void __launch_bounds__(RS_SCAN_THREADS) rs_scan(uint32_t* __restrict__ hist, uint32_t m,
+                                                           const uint32_t* __restrict__ gate = nullptr) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+    if (gate && *gate == 0) return;
     const uint32_t per = (m + RS_SCAN_THREADS - 1) / RS_SCAN_THREADS;
     const uint32_t b = threadIdx.x * per;
     const uint32_t e = (b + per < m) ? b + per : m;
@@ -96,7 +97,6 @@ __global__ void __launch_bounds__(RS_SCAN_THREADS) rs_scan(uint32_t* __restrict_
             if (lane >= o) vi += t;
         }
         warp_sums[lane] = vi - v;  // exclusive
-        if (lane == 31) carry_s = vi;
     }
     __syncthreads();
     uint32_t run = warp_sums[warp] + inc - s;

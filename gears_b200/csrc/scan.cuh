@@ -41,8 +41,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 __global__ void __launch_bounds__(SC_THREADS) sc_reduce(const uint32_t* __restrict__ in, uint32_t n,
-                                                        uint32_t* __restrict__ tile_sums) {
+                                                        uint32_t* __restrict__ tile_sums,
+                                                        const uint32_t* __restrict__ gate) {
     __shared__ uint32_t sm[33];
+    if (gate && *gate == 0) return;
     const uint64_t base = (uint64_t)blockIdx.x * SC_TILE;
     uint32_t s = 0;
 #pragma unroll
@@ -58,8 +60,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_reduce(const uint32_t* __restri
 // out[i] = sum_{j<i} in[j]; the last tile also writes out[n] = grand total.
 __global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* __restrict__ in, uint32_t n,
                                                       const uint32_t* __restrict__ tile_offsets,
-                                                      uint32_t* __restrict__ out) {
+                                                      uint32_t* __restrict__ out, const uint32_t* __restrict__ gate) {
     __shared__ uint32_t sm[33];
+    if (gate && *gate == 0) return;
     const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
     uint32_t v[SC_ITEMS];
     uint32_t s = 0;
@@ -78,16 +81,17 @@ __global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* __restrict
 }
 
 // tile_sums: ceil(n/SC_TILE) u32 of scratch.  out has n+1 entries.  in may alias nothing in out.
+// gate (device pointer, may be null): all three kernels return immediately when *gate == 0.
 static inline void exclusive_scan_u32(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums,
-                                      cudaStream_t st, uint64_t* launches) {
+                                      cudaStream_t st, uint64_t* launches, const uint32_t* gate = nullptr) {
     if (n == 0) {
         cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
         return;
     }
     const uint32_t tiles = (n + SC_TILE - 1) / SC_TILE;
-    sc_reduce<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums);
-    rs_scan<<<1, RS_SCAN_THREADS, 0, st>>>(tile_sums, tiles);
-    sc_scan<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums, out);
+    sc_reduce<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums, gate);
+    rs_scan<<<1, RS_SCAN_THREADS, 0, st>>>(tile_sums, tiles, gate);
+    sc_scan<<<tiles, SC_THREADS, 0, st>>>(in, n, tile_sums, out, gate);
     if (launches) *launches += 3;
 }
 

@@ -35,7 +35,7 @@ def _f32(a, cols=None):
 class PhysicsWorld:
     def __init__(self, device: int = 0, max_bodies: int = 0, max_pairs: int = 0, margin_init: float = 0.0,
                  margin_max: float = 0.0, cell_size: float = 0.0, max_big: int = 0, record_pairs: bool = False,
-                 no_retry: bool = False, grid_min=None, grid_max=None):
+                 no_retry: bool = False, profile: bool = False, grid_min=None, grid_max=None):
         self._lib = capi.lib()
         cfg = capi.GpConfig()
         cfg.struct_size = C.sizeof(capi.GpConfig)
@@ -46,7 +46,8 @@ class PhysicsWorld:
         cfg.margin_max = margin_max
         cfg.cell_size = cell_size
         cfg.max_big = max_big
-        cfg.flags = (capi.GP_FLAG_RECORD_PAIRS if record_pairs else 0) | (capi.GP_FLAG_NO_RETRY if no_retry else 0)
+        cfg.flags = (capi.GP_FLAG_RECORD_PAIRS if record_pairs else 0) | (capi.GP_FLAG_NO_RETRY if no_retry else 0) | \
+            (capi.GP_FLAG_PROFILE if profile else 0)
         if grid_min is not None:
             cfg.grid_min[:] = [float(x) for x in grid_min]
             cfg.grid_max[:] = [float(x) for x in grid_max]
@@ -134,6 +135,13 @@ class PhysicsWorld:
         ms = C.c_float()
         self._check(self._lib.gp_last_step_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def kernel_times(self) -> dict:
+        """Per-kernel-group device ms summed over the steps since the last call (needs profile=True)."""
+        kt = capi.GpKernelTimes()
+        self._check(self._lib.gp_kernel_times_read(self._h, C.byref(kt)))
+        return dict(steps=int(kt.steps), ms={g: float(kt.ms[i]) for i, g in enumerate(capi.KERNEL_GROUPS)},
+                    launches={g: int(kt.launches[i]) for i, g in enumerate(capi.KERNEL_GROUPS)})
 
     def kernel_launches(self) -> int:
         return int(self._lib.gp_kernel_launches(self._h))

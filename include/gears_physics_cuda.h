@@ -53,6 +53,8 @@ typedef enum gp_status {
 /* gp_config.flags */
 #define GP_FLAG_RECORD_PAIRS 0x1u /* keep S_snapshot / S_sweep flags so gp_pairs can be called       */
 #define GP_FLAG_NO_RETRY 0x2u     /* never re-run a step: report GP_ERR_MARGIN/PAIR_OVERFLOW instead  */
+#define GP_FLAG_PROFILE 0x4u      /* bracket every kernel group of a step with CUDA events on the step */
+                                  /* stream; read the sums with gp_kernel_times                        */
 
 typedef struct gp_config {
     uint32_t struct_size; /* = sizeof(gp_config); lets the library version the struct                */
@@ -148,6 +150,18 @@ void gp_host_free(void* p);
 gp_status gp_last_step_ms(gp_world* w, float* ms);
 /* number of kernels launched by this handle since creation (for launch accounting) */
 uint64_t gp_kernel_launches(const gp_world* w);
+
+/* Per-kernel-group device time (needs GP_FLAG_PROFILE): sums over the steps enqueued since the last
+ * call, measured with CUDA events recorded on the step stream between the groups. */
+#define GP_NUM_KERNEL_GROUPS 8
+typedef struct gp_kernel_times {
+    uint32_t steps;                       /* steps covered by the sums                                */
+    float ms[GP_NUM_KERNEL_GROUPS];       /* 0 integrate (K1), 1 radix sort (K2), 2 cell table+gather  */
+                                          /* (K3), 3 pair find (K4), 4 chain build (K5: scan, fill,    */
+                                          /* sort), 5 contact sweep (K6), 6 finish, 7 exchange (multi) */
+    uint32_t launches[GP_NUM_KERNEL_GROUPS]; /* kernel launches per group over those steps            */
+} gp_kernel_times;
+gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
 
 /* ---- multi-GPU: spatial slabs along x, one handle per GPU / process, NCCL point-to-point ---- */
 #define GP_UNIQUE_ID_BYTES 128

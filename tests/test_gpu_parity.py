@@ -230,7 +230,7 @@ def test_margin_retry_is_transparent(oracle):
 def test_margin_violation_is_reported_not_hidden():
     from gears_b200.world import GpError
     s = scenes.uniform(5000, L=14.0, seed=51, rank_seed=52)
-    with world(margin_init=1e-4, margin_max=1e-4) as w:
+    with world(margin_init=1e-4, no_retry=True) as w:  # no repair sweeps allowed: must say so, not guess
         w.upload(s)
         with pytest.raises(GpError) as e:
             w.step(DT)
