@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -258,6 +259,12 @@ static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
     return GP_OK;
 }
 
+static bool user_bounds_degenerate(const float* lo, const float* hi) {
+    for (int k = 0; k < 3; ++k)
+        if (!(hi[k] > lo[k])) return true;
+    return false;
+}
+
 // Choose the extent threshold / cell size and the grid from what was uploaded.
 static gp_status setup_grid(gp_world* w) {
     const uint32_t n = w->n;
@@ -313,9 +320,23 @@ static gp_status setup_grid(gp_world* w) {
     if (m_init > m_max) m_init = m_max;
     if (!isfinite(thr)) return fail(w, GP_ERR_BAD_ARG, "gp_upload: more than max_big bodies have a non-finite extent");
     const float ext_max = thr;  // upper bound of every grid-class extent
+    // Sparse scenes: cells no finer than ~GP_TARGET_OCC bodies per cell keep the cell table small enough to
+    // stay L2-resident (10 table lookups per body in K4) at the price of a few more AABB tests per body.
+    float cell_min = c.cell_size;
+    {
+        uint64_t n_grid = 0;
+        for (int k = 0; k <= b; ++k) n_grid += h_small[k];
+        const double vol = std::max(1e-30, ((double)hi[0] - lo[0]) * ((double)hi[1] - lo[1]) * ((double)hi[2] - lo[2]));
+        const char* env = getenv("GP_TARGET_OCC");
+        const double occ = env ? atof(env) : 1.0;
+        if (n_grid > 0 && occ > 0 && !user_bounds_degenerate(lo, hi)) {
+            const float auto_cell = (float)cbrt(occ * vol / (double)n_grid);
+            if (auto_cell > cell_min) cell_min = auto_cell;
+        }
+    }
     // the cell table is sized for the finest grid (margin = m_init); coarser grids reuse it
     const uint32_t MAXC = 1u << 28;
-    GridParams g0 = make_grid(lo, hi, ext_max, m_init, c.cell_size, MAXC);
+    GridParams g0 = make_grid(lo, hi, ext_max, m_init, cell_min, MAXC);
     int bits = 1;
     while ((1ull << bits) <= (uint64_t)g0.ncells) ++bits;
     w->key_bits = bits;
@@ -332,7 +353,7 @@ static gp_status setup_grid(gp_world* w) {
     hc.margin_max = m_max;
     for (int k = 0; k < 3; ++k) hc.lo[k] = lo[k], hc.hi[k] = hi[k];
     hc.ext_max = ext_max;
-    hc.cell_cfg = c.cell_size;
+    hc.cell_cfg = cell_min;
     hc.max_cells = g0.ncells;
     hc.grid = g0;
     w->max_cells = g0.ncells;
@@ -632,7 +653,7 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
         k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
         w->launches += 2;
         prof_mark(w, 3);
-        k_find_pairs<<<cdiv(n, 128), 128, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt,
+        k_find_pairs<<<cdiv(n, FP_THREADS), FP_THREADS, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt,
                                                    (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);

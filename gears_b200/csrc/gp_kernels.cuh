@@ -440,25 +440,6 @@ __global__ void __launch_bounds__(256) k_fill_gaps(const Gap* __restrict__ gaps,
 // Pairs are appended with warp-aggregated atomics (one atomicAdd per warp-wide ballot).
 // Pair record: x = a | static<<31, y = b | static<<31, z = rank_a | snapshot<<31, w = rank_b (| hit<<31 in K6).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_pair(uint4 rec, bool dyn_a, bool dyn_b, uint4* __restrict__ pairs,
-                                          uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt,
-                                          uint32_t pair_cap, Ctl* ctl) {
-    cg::coalesced_group g = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (g.thread_rank() == 0) base = atomicAdd(&ctl->n_pairs, g.size());
-    base = g.shfl(base, 0);
-    const uint32_t slot = base + g.thread_rank();
-    if (slot < pair_cap) {
-        pairs[slot] = rec;
-        pending[slot] = 0;
-        if (dyn_a) atomicAdd(&chain_cnt[rec.x & ~TOPBIT], 1u);
-        if (dyn_b) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
-        if (rec.z & TOPBIT) atomicAdd(&ctl->n_snapshot, 1u);
-    } else {
-        atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
-    }
-}
-
 __device__ __forceinline__ float box_extent(const float4 lo, const float4 hi) {
     return fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
 }
@@ -469,58 +450,118 @@ __device__ __forceinline__ bool inflated_overlap(const float4 alo, const float4 
            (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
 }
 
-__device__ __forceinline__ void test_candidate(const float4 alo, const float4 ahi, const float ma, const float4 blo,
-                                               const float4 bhi, float mu, uint4* __restrict__ pairs,
-                                               uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt,
-                                               uint32_t pair_cap, Ctl* ctl) {
+// candidate test of one (a, b): returns true and fills rec if the pair must be emitted
+__device__ __forceinline__ bool test_candidate(const float4 alo, const float4 ahi, const float ma, const float4 blo,
+                                               const float4 bhi, float mu, uint4& rec) {
     // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x)
-    if (!inflated_overlap(alo, ahi, blo, bhi, ma + mu * box_extent(blo, bhi))) return;
+    if (!inflated_overlap(alo, ahi, blo, bhi, ma + mu * box_extent(blo, bhi))) return false;
     const uint32_t ta = __float_as_uint(alo.w), tb = __float_as_uint(blo.w);
-    if ((ta & tb) & TOPBIT) return;  // static-static: no-op in the reference (physics.rs:225)
+    if ((ta & tb) & TOPBIT) return false;  // static-static: no-op in the reference (physics.rs:225)
     const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
     const uint32_t ra = __float_as_uint(ahi.w), rb = __float_as_uint(bhi.w);
-    uint4 rec;
     if (ra < rb)
         rec = make_uint4(ta, tb, ra | (snap ? TOPBIT : 0u), rb);
     else
         rec = make_uint4(tb, ta, rb | (snap ? TOPBIT : 0u), ra);
-    emit_pair(rec, !(rec.x & TOPBIT), !(rec.y & TOPBIT), pairs, pending, chain_cnt, pair_cap, ctl);
+    return true;
 }
 
-__global__ void __launch_bounds__(128)
+// write `cnt` (<= 32) staged pair records of this warp with ONE global atomic and coalesced 16 B stores
+__device__ __forceinline__ void flush_pairs(const uint4* __restrict__ stage, uint32_t cnt, int lane,
+                                            uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
+                                            uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->n_pairs, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((uint32_t)lane < cnt) {
+        const uint32_t slot = base + lane;
+        if (slot < pair_cap) {
+            const uint4 rec = stage[lane];
+            pairs[slot] = rec;
+            pending[slot] = 0;
+            if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
+            if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
+        } else {
+            atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+        }
+    }
+}
+
+constexpr int FP_THREADS = 128;
+
+__global__ void __launch_bounds__(FP_THREADS)
     k_find_pairs(uint32_t n, const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
                  const uint32_t* __restrict__ LB, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
                  uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    // warp-synchronous: the 32 lanes walk their candidate ranges in lock step, hits are compacted with a
+    // ballot into a per-warp shared-memory stage and leave in full 32-record (512 B) bursts.
+    __shared__ uint4 stage_all[FP_THREADS / 32][64];
+    const int lane = threadIdx.x & 31;
+    uint4* stage = stage_all[threadIdx.x >> 5];
+    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    const bool live = p < n;
     const GridParams g = ctl->grid;
     const float mu = ctl->margin;
     const uint32_t n_small = LB[g.ncells];
-    const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
-    const float ma = mu * box_extent(alo, ahi);
-    if (p < n_small) {
-        const uint32_t k = skey[p];
-        const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
-        // forward half of the 27-neighbourhood as 5 contiguous ranges of sorted positions
-        uint32_t r0[5], r1[5];
-        r0[0] = p + 1, r1[0] = LB[k + 2];
-        r0[1] = LB[k + row - 1], r1[1] = LB[k + row + 2];
-        r0[2] = LB[k + slab - row - 1], r1[2] = LB[k + slab - row + 2];
-        r0[3] = LB[k + slab - 1], r1[3] = LB[k + slab + 2];
-        r0[4] = LB[k + slab + row - 1], r1[4] = LB[k + slab + row + 2];
+    float4 alo = make_float4(0, 0, 0, 0), ahi = alo;
+    float ma = 0.f;
+    uint32_t k = 0;
+    if (live) {
+        alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+        ma = mu * box_extent(alo, ahi);
+        if (p < n_small) k = skey[p];
+    }
+    const bool in_grid = live && p < n_small;
+    const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
+    uint32_t cnt = 0, nsnap = 0;
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            for (uint32_t q = r0[r]; q < r1[r]; ++q) {
+    for (int r = 0; r < 6; ++r) {
+        // forward half of the 27-neighbourhood as 5 contiguous ranges of sorted positions, then the big list
+        uint32_t q0 = 0, q1 = 0;
+        if (r == 5) {
+            if (live) q0 = max(p + 1, n_small), q1 = n;
+        } else if (in_grid) {
+            if (r == 0) q0 = p + 1, q1 = LB[k + 2];
+            if (r == 1) q0 = LB[k + row - 1], q1 = LB[k + row + 2];
+            if (r == 2) q0 = LB[k + slab - row - 1], q1 = LB[k + slab - row + 2];
+            if (r == 3) q0 = LB[k + slab - 1], q1 = LB[k + slab + 2];
+            if (r == 4) q0 = LB[k + slab + row - 1], q1 = LB[k + slab + row + 2];
+        }
+        const uint32_t len = q1 > q0 ? q1 - q0 : 0u;
+        const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+        for (uint32_t it = 0; it < maxlen; ++it) {
+            bool hit = false;
+            uint4 rec = make_uint4(0, 0, 0, 0);
+            if (it < len) {
+                const uint32_t q = q0 + it;
                 const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-                test_candidate(alo, ahi, ma, blo, bhi, mu, pairs, pending, chain_cnt, pair_cap, ctl);
+                hit = test_candidate(alo, ahi, ma, blo, bhi, mu, rec);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (hit) {
+                    stage[cnt + __popc(m & lt)] = rec;  // cnt <= 31 here, so the slot is < 64
+                    nsnap += (rec.z >> 31);
+                }
+                cnt += __popc(m);
+                __syncwarp();
+                if (cnt >= 32) {
+                    flush_pairs(stage, 32, lane, pairs, pending, chain_cnt, pair_cap, ctl);
+                    __syncwarp();
+                    const uint4 carry = stage[32 + lane];
+                    __syncwarp();
+                    stage[lane] = carry;
+                    cnt -= 32;
+                    __syncwarp();
+                }
             }
         }
     }
-    // big list: every grid body tests all big bodies; big bodies test the big bodies after them
-    for (uint32_t q = max(p + 1, n_small); q < n; ++q) {
-        const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-        test_candidate(alo, ahi, ma, blo, bhi, mu, pairs, pending, chain_cnt, pair_cap, ctl);
-    }
+    if (cnt) flush_pairs(stage, cnt, lane, pairs, pending, chain_cnt, pair_cap, ctl);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsnap += __shfl_xor_sync(0xffffffffu, nsnap, o);
+    if (lane == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1000,11 +1041,13 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     if (latch == 0 && c.step_flags == SF_MARGIN) return;  // sync mode: the host continues the repair loop
     // (latch == 2: the host gave up on this step; just reset)
     // margin: grow when the step needed repair sweeps, relax slowly otherwise
+    // a small margin keeps the candidate set (and every pair-proportional kernel) small; a repair sweep
+    // costs about one more sweep.  Grow only when the pre-enqueued repair rounds were nearly used up.
     float m = c.margin;
-    if (c.n_repairs > 0)
+    if (c.n_repairs >= 2)
         m *= 1.5f;
-    else
-        m *= 0.97f;
+    else if (c.n_repairs == 0)
+        m *= 0.9f;
     c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
     c.grid = make_grid(c.lo, c.hi, c.ext_max, c.margin, c.cell_cfg, c.max_cells);
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
