@@ -35,13 +35,16 @@ struct gp_world {
     uint64_t pair_cap = 0;
     bool uploaded = false;
 
-    // body state (SoA of float4)
-    float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr};
-    float4 *A = nullptr, *Lo = nullptr, *Hi = nullptr;
+    // body state: two sets of five float4 arrays; every step gathers set `cur` into set `cur^1` in cell order
+    float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *A[2] = {nullptr, nullptr};
+    float4 *Lo[2] = {nullptr, nullptr}, *Hi[2] = {nullptr, nullptr};
     int cur = 0;
     float* ext = nullptr;
+    uint32_t* slot_of = nullptr;  // body id -> current slot (rebuilt on demand: slots change every step)
+    bool slot_valid = false;
     // broad phase
-    float4 *box = nullptr, *sbox = nullptr;
+    float4* sbox = nullptr;       // world AABBs of the current step in cell order (lo|tag, hi|rank)
+    int sorted_r = 0;             // which (key,val) buffer holds the sorted keys / permutation of the current step
     uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr};
     uint32_t* hist = nullptr;
     uint32_t* LB = nullptr;
@@ -120,8 +123,9 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 static void free_all(gp_world* w) {
-    void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A,     w->Lo,        w->Hi,     w->ext,
-                    w->box,    w->sbox,  w->key[0],     w->key[1],     w->val[0], w->val[1],    w->hist,   w->LB,
+    void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A[0],  w->A[1],      w->Lo[0],  w->Lo[1],
+                    w->Hi[0],  w->Hi[1], w->ext,        w->slot_of,
+                    w->sbox,  w->key[0],     w->key[1],     w->val[0], w->val[1],    w->hist,   w->LB,
                     w->gaps,   w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
                     w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
@@ -219,15 +223,15 @@ static gp_status ensure_stage(gp_world* w, size_t bytes) {
 }
 
 static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
-    CK(dmalloc(&w->P[0], cap));
-    CK(dmalloc(&w->P[1], cap));
-    CK(dmalloc(&w->V[0], cap));
-    CK(dmalloc(&w->V[1], cap));
-    CK(dmalloc(&w->A, cap));
-    CK(dmalloc(&w->Lo, cap));
-    CK(dmalloc(&w->Hi, cap));
+    for (int i = 0; i < 2; ++i) {
+        CK(dmalloc(&w->P[i], cap));
+        CK(dmalloc(&w->V[i], cap));
+        CK(dmalloc(&w->A[i], cap));
+        CK(dmalloc(&w->Lo[i], cap));
+        CK(dmalloc(&w->Hi[i], cap));
+    }
     CK(dmalloc(&w->ext, cap));
-    CK(dmalloc(&w->box, 2 * (size_t)cap));
+    CK(dmalloc(&w->slot_of, cap));
     CK(dmalloc(&w->sbox, 2 * (size_t)cap));
     for (int i = 0; i < 2; ++i) {
         CK(dmalloc(&w->key[i], cap));
@@ -294,7 +298,7 @@ static gp_status setup_grid(gp_world* w) {
     uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, w->st));
     if (n) {
-        k_classify<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->ext, thr, w->P[w->cur], w->Lo, w->Hi, w->A, d_bounds);
+        k_classify<<<cdiv(n, 256), 256, 0, w->st>>>(n, thr, w->P[w->cur], w->Lo[w->cur], w->Hi[w->cur], w->A[w->cur], d_bounds);
         w->launches++;
     }
     uint32_t hb[6];
@@ -338,11 +342,11 @@ static gp_status setup_grid(gp_world* w) {
     const uint32_t MAXC = 1u << 28;
     GridParams g0 = make_grid(lo, hi, ext_max, m_init, cell_min, MAXC);
     int bits = 1;
-    while ((1ull << bits) <= (uint64_t)g0.ncells) ++bits;
+    while ((1ull << bits) <= (uint64_t)g0.ncells + 1) ++bits;  // keys: cells, ncells = big list, ncells+1 = dead
     w->key_bits = bits;
-    if (g0.ncells + 2 > w->lb_cap) {
-        CK(dmalloc(&w->LB, (size_t)g0.ncells + 2));
-        w->lb_cap = g0.ncells + 2;
+    if (g0.ncells + 3 > w->lb_cap) {
+        CK(dmalloc(&w->LB, (size_t)g0.ncells + 3));
+        w->lb_cap = g0.ncells + 3;
         w->gap_cap = g0.ncells / GAP_DIRECT + 1024;
         CK(dmalloc(&w->gaps, w->gap_cap));
     }
@@ -356,6 +360,7 @@ static gp_status setup_grid(gp_world* w) {
     hc.cell_cfg = cell_min;
     hc.max_cells = g0.ncells;
     hc.grid = g0;
+    hc.n_in = n, hc.n = n;
     w->max_cells = g0.ncells;
     CK(cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st));
     CK(cudaStreamSynchronize(w->st));
@@ -423,7 +428,7 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
             acc3 ? (const float*)(sg + o_acc) : nullptr, (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
             (const float*)(sg + o_mass), (const float*)(sg + o_rest), (const uint8_t*)(sg + o_stat),
             entity ? (const uint32_t*)(sg + o_ent) : nullptr, rank ? (const uint32_t*)(sg + o_rank) : nullptr, w->P[0],
-            w->V[0], w->A, w->Lo, w->Hi, w->ext, 0);
+            w->V[0], w->A[0], w->Lo[0], w->Hi[0], w->ext, 0, nullptr);
         w->launches++;
         CK(cudaGetLastError());
     }
@@ -432,16 +437,32 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
     s = setup_grid(w);
     if (s != GP_OK) return s;
     w->uploaded = true;
+    w->slot_valid = false;
     w->last = gp_step_stats{};
     w->last_np = 0;
+    return GP_OK;
+}
+
+// body id -> slot map of the current set (slots change with every step)
+static gp_status ensure_slot_map(gp_world* w) {
+    if (w->slot_valid || w->n == 0) return GP_OK;
+    k_slot_map<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->Lo[w->cur], w->slot_of);
+    w->launches++;
+    CK(cudaGetLastError());
+    w->slot_valid = true;
     return GP_OK;
 }
 
 static gp_status stage_state(gp_world* w, uint32_t k, const uint32_t* idx, const float* pos3, const float* vel3,
                              const float* acc3) {
     if (!w || !w->uploaded) return w ? fail(w, GP_ERR_STATE, "no bodies uploaded") : GP_ERR_BAD_ARG;
+    if (w->multi) return fail(w, GP_ERR_STATE, "per-index state updates are not available on a slab world");
     CK(cudaSetDevice(w->device));
     if (k == 0) return GP_OK;
+    if (idx) {
+        gp_status sm = ensure_slot_map(w);
+        if (sm != GP_OK) return sm;
+    }
     const size_t b3 = 3 * sizeof(float) * (size_t)k;
     const size_t a3 = (b3 + 255) & ~(size_t)255;
     gp_status s = ensure_stage(w, 3 * a3 + (((size_t)k * 4 + 255) & ~(size_t)255) + 256);
@@ -451,11 +472,11 @@ static gp_status stage_state(gp_world* w, uint32_t k, const uint32_t* idx, const
     if (vel3) CK(cudaMemcpyAsync(sg + a3, vel3, b3, cudaMemcpyHostToDevice, w->st));
     if (acc3) CK(cudaMemcpyAsync(sg + 2 * a3, acc3, b3, cudaMemcpyHostToDevice, w->st));
     if (idx) CK(cudaMemcpyAsync(sg + 3 * a3, idx, (size_t)k * 4, cudaMemcpyHostToDevice, w->st));
-    k_set_state<<<cdiv(k, 256), 256, 0, w->st>>>(k, idx ? (const uint32_t*)(sg + 3 * a3) : nullptr,
+    k_set_state<<<cdiv(k, 256), 256, 0, w->st>>>(k, idx ? (const uint32_t*)(sg + 3 * a3) : nullptr, w->slot_of,
                                                  pos3 ? (const float*)sg : nullptr,
                                                  vel3 ? (const float*)(sg + a3) : nullptr,
                                                  acc3 ? (const float*)(sg + 2 * a3) : nullptr, w->P[w->cur],
-                                                 w->V[w->cur], w->A);
+                                                 w->V[w->cur], w->A[w->cur], w->Lo[w->cur]);
     w->launches++;
     CK(cudaGetLastError());
     return GP_OK;
@@ -487,7 +508,12 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
         return fail(w, GP_ERR_BAD_ARG, "gp_update_shape: a required array is NULL");
     for (uint32_t i = 0; i < k; ++i)
         if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_update_shape: idx[%u]=%u out of range", i, idx[i]);
+    if (w->multi) return fail(w, GP_ERR_STATE, "per-index shape updates are not available on a slab world");
     CK(cudaSetDevice(w->device));
+    {
+        gp_status sm = ensure_slot_map(w);
+        if (sm != GP_OK) return sm;
+    }
     const size_t f = sizeof(float);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -515,12 +541,12 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
                                             (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
                                             (const float*)(sg + o_mass), (const float*)(sg + o_rest),
                                             (const uint8_t*)(sg + o_stat), nullptr, nullptr, w->P[w->cur], w->V[w->cur],
-                                            w->A, w->Lo, w->Hi, w->ext, 1);
+                                            w->A[w->cur], w->Lo[w->cur], w->Hi[w->cur], nullptr, 1, w->slot_of);
     w->launches++;
     CK(cudaGetLastError());
     // a body that outgrew the cell joins the big list; the grid itself is kept
-    k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->ext, w->thr, w->P[w->cur], w->Lo, w->Hi, w->A,
-                                                   w->d_small + EXT_BUCKETS);
+    k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->thr, w->P[w->cur], w->Lo[w->cur], w->Hi[w->cur],
+                                                   w->A[w->cur], w->d_small + EXT_BUCKETS);
     w->launches++;
     CK(cudaStreamSynchronize(w->st));
     return GP_OK;
@@ -573,21 +599,24 @@ extern "C" gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out) {
     return GP_OK;
 }
 
+// Upper bound of the live body count that sizes the grids (the exact count is device-resident: ctl->n).
+static inline uint32_t n_bound(const gp_world* w) { return w->multi ? w->cap : w->n; }
+
 // K5 + K6: chain offsets, fill, sort, cooperative sweep.  gate != nullptr: every kernel is a no-op
 // unless *gate != 0 (repair rounds that turn out not to be needed cost a few empty launches).
 static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
-    const uint32_t n = w->n;
+    const uint32_t nb = n_bound(w);
     cudaStream_t st = w->st;
     const int o = w->cur ^ 1;
-    exclusive_scan_u32(w->chain_cnt, n, w->offs, w->tile_sums, st, &w->launches, gate);
+    exclusive_scan_u32(w->chain_cnt, nb, w->offs, w->tile_sums, st, &w->launches, gate);
     k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
                                                    w->ctl, gate);
-    k_sort_chains<<<cdiv(n, 256), 256, 0, st>>>(n, w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
+    k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
     k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
     w->launches += 3;
     if (!gate) prof_mark(w, 5);
     float4 *Pn = w->P[o], *Vn = w->V[o];
-    const float4 *Lo = w->Lo, *Hi = w->Hi, *box = w->box;
+    const float4 *Lo = w->Lo[o], *Hi = w->Hi[o], *box = w->sbox;
     uint4* pairs = w->pairs;
     uint32_t pair_cap = (uint32_t)w->pair_cap;
     const uint32_t* offs = w->offs;
@@ -609,28 +638,26 @@ static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
 
 // One repair round (all kernels gated on ctl->repair_needed), ending with a fresh k_requery.
 static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
-    const uint32_t n = w->n;
     cudaStream_t st = w->st;
     const int c = w->cur, o = c ^ 1;
     const uint32_t* gate = &w->ctl->repair_needed;
-    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->P[c], w->V[c], w->A, w->P[o],
-                                               w->V[o], w->chain_cnt, w->pending, w->dmax, w->reach, w->escapees, w->cap,
-                                               w->ctl, dt, d[0], d[1], d[2]);
+    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->val[w->sorted_r], w->P[c], w->V[c],
+                                               w->A[c], w->P[o], w->V[o], w->chain_cnt, w->pending, w->dmax, w->reach,
+                                               w->escapees, w->cap, w->ctl, dt, d[0], d[1], d[2]);
     k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
     k_repair_reset<<<1, 1, 0, st>>>(w->ctl);
     w->launches += 3;
     gp_status s = enqueue_chains_and_sweep(w, gate);
     if (s != GP_OK) return s;
     k_repair_done<<<1, 1, 0, st>>>(w->ctl);
-    k_requery<<<w->sm_count * 4, 256, 0, st>>>(n, w->box, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap, w->pairs,
-                                               w->pending, (uint32_t)w->pair_cap, w->ctl);
+    k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
+                                               w->pairs, w->pending, (uint32_t)w->pair_cap, w->ctl);
     w->launches += 2;
     return GP_OK;
 }
 
-// Enqueue the kernels of one step.  Reads P/V[cur], leaves the result in P/V[cur^1].
+// Enqueue the kernels of one step.  Reads set `cur`, leaves the result (in cell order) in set `cur^1`.
 static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch, int repair_rounds) {
-    const uint32_t n = w->n;
     cudaStream_t st = w->st;
     float d[3];
     if (damp3)
@@ -638,31 +665,35 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
     else
         gp_damping_factors(dt, d);
     const int c = w->cur, o = c ^ 1;
+    const uint32_t nb = n_bound(w);  // grids are sized for this; kernels stop at the device-resident counts
     prof_begin_step(w);
-    if (n) {
+    w->slot_valid = false;
+    if (nb) {
         prof_mark(w, 0);
-        k_integrate<<<cdiv(n, 256), 256, 0, st>>>(n, w->P[c], w->V[c], w->A, w->Lo, w->Hi, w->P[o], w->V[o], w->box,
-                                                  w->key[0], w->chain_cnt, w->ctl, dt, d[0], d[1], d[2]);
+        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c], w->key[0], w->ctl, dt, d[0],
+                                              d[1], d[2]);
         w->launches++;
         prof_mark(w, 1);
-        const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], n, w->key_bits, true, w->hist,
-                                        w->sm_count, st, &w->launches);
+        const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], nb, w->key_bits, true, w->hist,
+                                        w->sm_count, st, &w->launches, &w->ctl->n_in);
+        w->sorted_r = r;
         prof_mark(w, 2);
-        k_gather_cells<<<cdiv(n, 256), 256, 0, st>>>(n, w->key[r], w->val[r], w->box, w->sbox, w->LB, w->gaps,
-                                                     w->gap_cap, w->ctl);
+        k_gather_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key[r], w->val[r], w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c],
+                                                      w->P[o], w->V[o], w->A[o], w->Lo[o], w->Hi[o], w->sbox, w->chain_cnt,
+                                                      w->LB, w->gaps, w->gap_cap, w->ctl, dt, d[0], d[1], d[2]);
         k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
         w->launches += 2;
         prof_mark(w, 3);
-        k_find_pairs<<<cdiv(n, FP_THREADS), FP_THREADS, 0, st>>>(n, w->key[r], w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt,
-                                                   (uint32_t)w->pair_cap, w->ctl);
+        k_find_pairs<<<cdiv(nb, FP_THREADS), FP_THREADS, 0, st>>>(w->key[r], w->sbox, w->LB, w->pairs, w->pending,
+                                                                  w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
         enqueue_chains_and_sweep(w, nullptr);
         // speculative broad phase: look for pairs the margin missed, repair, look again
-        k_requery<<<w->sm_count * 4, 256, 0, st>>>(n, w->box, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap, w->pairs,
-                                                   w->pending, (uint32_t)w->pair_cap, w->ctl);
+        k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
+                                                   w->pairs, w->pending, (uint32_t)w->pair_cap, w->ctl);
         w->launches++;
-        for (int r = 0; r < repair_rounds; ++r) enqueue_repair_round(w, dt, d);
+        for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
         k_clear_escapees<<<w->sm_count, 256, 0, st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, latch);
         w->launches++;
     }
@@ -843,7 +874,8 @@ extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
     if (s != GP_OK) return s;
     float* dp = (float*)w->stage;
     float* dv = (float*)(w->stage + a3);
-    k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->P[w->cur], w->V[w->cur], pos3 ? dp : nullptr, vel3 ? dv : nullptr);
+    k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->P[w->cur], w->V[w->cur], w->Lo[w->cur], pos3 ? dp : nullptr,
+                                              vel3 ? dv : nullptr, nullptr, 1);
     w->launches++;
     if (pos3) CK(cudaMemcpyAsync(pos3, dp, b3, cudaMemcpyDeviceToHost, w->st));
     if (vel3) CK(cudaMemcpyAsync(vel3, dv, b3, cudaMemcpyDeviceToHost, w->st));
@@ -881,7 +913,7 @@ extern "C" gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint
         *n_out = m;
         if (m == 0) break;
         const int r = rs_sort<unsigned long long>(k0, v0, k1, v1, m, 63, false, hist, w->sm_count, w->st, &w->launches);
-        k_gather_pairs<<<cdiv(m, 256), 256, 0, w->st>>>(w->pairs, r ? v1 : v0, m, outp);
+        k_gather_pairs<<<cdiv(m, 256), 256, 0, w->st>>>(w->pairs, r ? v1 : v0, m, w->Lo[w->cur], outp);
         w->launches++;
         const uint64_t ncopy = std::min<uint64_t>(m, cap);
         if (pairs2 && ncopy) cudaMemcpyAsync(pairs2, outp, ncopy * sizeof(uint2), cudaMemcpyDeviceToHost, w->st);

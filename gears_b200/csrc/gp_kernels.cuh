@@ -30,6 +30,7 @@ namespace gp {
 constexpr uint32_t F_STATIC = 1u;
 constexpr uint32_t F_BIG = 2u;     // extent above the grid cell: brute-force list
 constexpr uint32_t F_GHOST = 4u;   // multi-GPU halo copy: resolved here but owned elsewhere
+constexpr uint32_t F_INTEGRATED = 8u;  // multi-GPU: record received this step, already integrated by its sender
 
 constexpr uint32_t TOPBIT = 0x80000000u;
 
@@ -52,6 +53,10 @@ struct GridParams {
 // Device-resident control block: everything the kernels of one step communicate through, so that a
 // step needs no host round trip.
 struct Ctl {
+    // device-resident body counts: kernels never take n from the host, so a step needs no host round trip even
+    // when bodies arrive / leave between steps (multi-GPU slabs)
+    uint32_t n_in;            // bodies entering the step (live bodies of the last step + received ones)
+    uint32_t n;               // live bodies of the current step (set by K3 after the sort dropped dead keys)
     float margin;             // relative margin mu of the current step: body x's AABB is inflated by
                               // mu * (largest extent of x) in K4, and K6 verifies it never moves further
     float margin_min, margin_max;
@@ -169,10 +174,11 @@ __global__ void k_pack(uint32_t k, const uint32_t* __restrict__ idx, const float
                        const float* __restrict__ acc3, const float* __restrict__ bmin3, const float* __restrict__ bmax3,
                        const float* __restrict__ mass, const float* __restrict__ rest, const uint8_t* __restrict__ stat,
                        const uint32_t* __restrict__ entity, const uint32_t* __restrict__ rank, float4* P, float4* V,
-                       float4* A, float4* Lo, float4* Hi, float* ext, int shape_only) {
+                       float4* A, float4* Lo, float4* Hi, float* ext, int shape_only,
+                       const uint32_t* __restrict__ slot_of) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k) return;
-    const uint32_t i = idx ? idx[t] : t;
+    const uint32_t i = idx ? slot_of[idx[t]] : t;  // bodies are re-sorted every step: caller index -> current slot
     const V3 bmin = mk(bmin3[3 * t], bmin3[3 * t + 1], bmin3[3 * t + 2]);
     const V3 bmax = mk(bmax3[3 * t], bmax3[3 * t + 1], bmax3[3 * t + 2]);
     const float4 q = rot4 ? make_float4(rot4[4 * t], rot4[4 * t + 1], rot4[4 * t + 2], rot4[4 * t + 3])
@@ -194,7 +200,8 @@ __global__ void k_pack(uint32_t k, const uint32_t* __restrict__ idx, const float
         V[i] = make_float4(vel3[3 * t], vel3[3 * t + 1], vel3[3 * t + 2], rest[t]);
         A[i] = make_float4(acc3 ? acc3[3 * t] : 0.f, acc3 ? acc3[3 * t + 1] : 0.f, acc3 ? acc3[3 * t + 2] : 0.f,
                            __uint_as_float(fl_static));
-        Lo[i] = make_float4(omin.x, omin.y, omin.z, __uint_as_float(entity ? entity[t] : i));
+        Lo[i] = make_float4(omin.x, omin.y, omin.z, __uint_as_float(i));  // .w = body id (caller index)
+        (void)entity;
         Hi[i] = make_float4(omax.x, omax.y, omax.z, __uint_as_float(rank ? rank[t] : i));
     }
     if (ext) ext[i] = fmaxf(omax.x - omin.x, fmaxf(omax.y - omin.y, omax.z - omin.z));
@@ -240,7 +247,7 @@ __host__ __device__ inline float ord2f(uint32_t u) {
 }
 
 // classify by extent threshold and reduce the bounds of grid-class body centres
-__global__ void k_classify(uint32_t n, const float* __restrict__ ext, float thr, const float4* __restrict__ P,
+__global__ void k_classify(uint32_t n, float thr, const float4* __restrict__ P,
                            const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* A,
                            uint32_t* __restrict__ bounds /*6: min xyz, max xyz (ordered uints)*/) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +255,8 @@ __global__ void k_classify(uint32_t n, const float* __restrict__ ext, float thr,
     if (i < n) {
         float4 a = A[i];
         uint32_t f = __float_as_uint(a.w) & ~F_BIG;
-        const bool big = !(ext[i] <= thr);
+        const float4 l4 = Lo[i], h4 = Hi[i];
+        const bool big = !(fmaxf(h4.x - l4.x, fmaxf(h4.y - l4.y, h4.z - l4.z)) <= thr);
         if (big) f |= F_BIG;
         a.w = __uint_as_float(f);
         A[i] = a;
@@ -278,42 +286,60 @@ __global__ void k_classify(uint32_t n, const float* __restrict__ ext, float thr,
     }
 }
 
-// bulk refresh of mutable state from host-layout arrays (gp_set_state / gp_update_dirty)
-__global__ void k_set_state(uint32_t k, const uint32_t* __restrict__ idx, const float* __restrict__ pos3,
-                            const float* __restrict__ vel3, const float* __restrict__ acc3, float4* P, float4* V,
-                            float4* A) {
+// The body arrays are physically re-sorted into cell order by every step (K3), so the slot of a body changes.
+// Lo[slot].w keeps the body id (the caller's index at upload; the global entity id in multi-GPU mode).
+__global__ void k_slot_map(uint32_t n, const float4* __restrict__ Lo, uint32_t* __restrict__ slot_of) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_of[__float_as_uint(Lo[i].w)] = i;
+}
+
+// bulk refresh of mutable state from host-layout arrays (gp_set_state: idx == nullptr, every slot gathers the
+// row of its body id;  gp_update_dirty: row t belongs to body idx[t])
+__global__ void k_set_state(uint32_t k, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ slot_of,
+                            const float* __restrict__ pos3, const float* __restrict__ vel3,
+                            const float* __restrict__ acc3, float4* P, float4* V, float4* A,
+                            const float4* __restrict__ Lo) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k) return;
-    const uint32_t i = idx ? idx[t] : t;
+    uint32_t i, r;
+    if (idx) {
+        i = slot_of[idx[t]], r = t;
+    } else {
+        i = t, r = __float_as_uint(Lo[t].w);
+    }
     if (pos3) {
         float4 p = P[i];
-        p.x = pos3[3 * t], p.y = pos3[3 * t + 1], p.z = pos3[3 * t + 2];
+        p.x = pos3[3 * (size_t)r], p.y = pos3[3 * (size_t)r + 1], p.z = pos3[3 * (size_t)r + 2];
         P[i] = p;
     }
     if (vel3) {
         float4 v = V[i];
-        v.x = vel3[3 * t], v.y = vel3[3 * t + 1], v.z = vel3[3 * t + 2];
+        v.x = vel3[3 * (size_t)r], v.y = vel3[3 * (size_t)r + 1], v.z = vel3[3 * (size_t)r + 2];
         V[i] = v;
     }
     if (acc3) {
         float4 a = A[i];
-        a.x = acc3[3 * t], a.y = acc3[3 * t + 1], a.z = acc3[3 * t + 2];
+        a.x = acc3[3 * (size_t)r], a.y = acc3[3 * (size_t)r + 1], a.z = acc3[3 * (size_t)r + 2];
         A[i] = a;
     }
 }
 
-__global__ void k_unpack(uint32_t n, const float4* __restrict__ P, const float4* __restrict__ V, float* pos3,
-                         float* vel3) {
+// device -> host layout.  by_id: row = body id (gp_download); else row = slot (gp_download_owned, + ids)
+__global__ void k_unpack(uint32_t n, const float4* __restrict__ P, const float4* __restrict__ V,
+                         const float4* __restrict__ Lo, float* pos3, float* vel3, uint32_t* ids, int by_id) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t id = __float_as_uint(Lo[i].w);
+    const size_t r = by_id ? id : i;
     if (pos3) {
         const float4 p = P[i];
-        pos3[3 * i] = p.x, pos3[3 * i + 1] = p.y, pos3[3 * i + 2] = p.z;
+        pos3[3 * r] = p.x, pos3[3 * r + 1] = p.y, pos3[3 * r + 2] = p.z;
     }
     if (vel3) {
         const float4 v = V[i];
-        vel3[3 * i] = v.x, vel3[3 * i + 1] = v.y, vel3[3 * i + 2] = v.z;
+        vel3[3 * r] = v.x, vel3[3 * r + 1] = v.y, vel3[3 * r + 2] = v.z;
     }
+    if (ids) ids[i] = id;
 }
 
 // RigidBody::update_pos, physics.rs:405-462 (a.w carries the flags; static bodies are untouched)
@@ -345,38 +371,43 @@ __device__ __forceinline__ void integrate_body(float4& p, float4& v, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: fused integrate + world AABB + cell key.  One thread per body, float4 (128-bit) coalesced
-// access on every array.  R 80 B (P,V,A,Lo,Hi) + W 32 (P',V') + W 32 (box) + W 4 (key) + W 4 (chain counter).
+// Data layout.  The body state lives in two sets of five float4 arrays (P = pos|mass, V = vel|restitution,
+// A = acc|flags, Lo = min offset|id, Hi = max offset|rank; 80 B/body).  Every step physically re-sorts the
+// bodies into uniform-grid cell order: K1 computes the cell key of the integrated position, K2 sorts
+// (key, slot), K3 gathers the previous set through the permutation, integrates on the fly and writes the
+// next set + the world AABBs in cell order.  The contact sweep (K6) then works on bodies whose partners sit
+// a few slots away: its accesses hit L2 instead of random DRAM sectors.  Bodies move a fraction of a cell per
+// step, so the permutation is nearly the identity and the gather is nearly coalesced.
 // ---------------------------------------------------------------------------------------------
+// K1: integrate (registers only) + world AABB centre -> cell key.  R 80 B (P,V,A,Lo,Hi) + W 4 B (key).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t body_key(const GridParams& g, const float4 p, const float4 lo, const float4 hi,
+                                             uint32_t flags) {
+    if (flags & F_BIG) return g.ncells;
+    const float lx = lo.x + p.x, ly = lo.y + p.y, lz = lo.z + p.z;
+    const float hx = hi.x + p.x, hy = hi.y + p.y, hz = hi.z + p.z;
+    return cell_key(g, (lx + hx) * 0.5f, (ly + hy) * 0.5f, (lz + hz) * 0.5f);
+}
+
 __global__ void __launch_bounds__(256)
-    k_integrate(uint32_t n, const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
-                const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* __restrict__ P1,
-                float4* __restrict__ V1, float4* __restrict__ box, uint32_t* __restrict__ key,
-                uint32_t* __restrict__ chain_cnt, const Ctl* __restrict__ ctl, float dt, float d16, float d18,
-                float d35) {
+    k_keys(const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
+           const float4* __restrict__ Lo, const float4* __restrict__ Hi, uint32_t* __restrict__ key,
+           const Ctl* __restrict__ ctl, float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= ctl->n_in) return;
     const GridParams g = ctl->grid;
     float4 p = P0[i], v = V0[i];
     const float4 a = A[i], lo = Lo[i], hi = Hi[i];
     const uint32_t flags = __float_as_uint(a.w);
-    integrate_body(p, v, a, dt, d16, d18, d35);
-    P1[i] = p;
-    V1[i] = v;
-    // world AABB = offsets + position
-    const float lx = lo.x + p.x, ly = lo.y + p.y, lz = lo.z + p.z;
-    const float hx = hi.x + p.x, hy = hi.y + p.y, hz = hi.z + p.z;
-    const uint32_t tag = i | ((flags & F_STATIC) ? TOPBIT : 0u);
-    box[2 * (size_t)i] = make_float4(lx, ly, lz, __uint_as_float(tag));
-    box[2 * (size_t)i + 1] = make_float4(hx, hy, hz, hi.w /* rank */);
-    key[i] = (flags & F_BIG) ? g.ncells : cell_key(g, (lx + hx) * 0.5f, (ly + hy) * 0.5f, (lz + hz) * 0.5f);
-    chain_cnt[i] = 0;
+    if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
+    key[i] = body_key(g, p, lo, hi, flags);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: gather AABBs into cell order and build the cell lower-bound table LB[c] = first sorted
-// position whose key >= c (c in [0, ncells+1]).  Thread i owns cells (key[i-1], key[i]].
-// Long empty runs go to a gap list that k_fill_gaps spreads over the whole grid.
+// K3: gather the bodies into cell order, integrate, emit world AABBs, build the cell lower-bound table
+// LB[c] = first sorted position whose key >= c (c in [0, ncells+2]; key ncells = big list, key ncells+1 = dead).
+// Thread i owns cells (key[i-1], key[i]].  Long empty runs go to a gap list that k_fill_gaps spreads over the grid.
+// R 8 (key, slot) + R 80 (gather) + W 80 (next set) + W 32 (AABB) + W 4 (chain counter) + the cell table.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t GAP_DIRECT = 32;
 constexpr uint32_t GAP_CHUNK = 1u << 16;
@@ -400,25 +431,53 @@ __device__ __forceinline__ void fill_cells(uint32_t* LB, uint32_t c0, uint32_t l
 }
 
 __global__ void __launch_bounds__(256)
-    k_gather_cells(uint32_t n, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sval,
-                   const float4* __restrict__ box, float4* __restrict__ sbox, uint32_t* __restrict__ LB,
-                   Gap* gaps, uint32_t gap_cap, Ctl* ctl) {
+    k_gather_cells(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sval,
+                   const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A0,
+                   const float4* __restrict__ Lo0, const float4* __restrict__ Hi0, float4* __restrict__ P1,
+                   float4* __restrict__ V1, float4* __restrict__ A1, float4* __restrict__ Lo1, float4* __restrict__ Hi1,
+                   float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ LB, Gap* gaps,
+                   uint32_t gap_cap, Ctl* ctl, float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint32_t n_in = ctl->n_in;
     const uint32_t ncells = ctl->grid.ncells;
-    const uint32_t v = sval[i];
-    const float4 lo = box[2 * (size_t)v], hi = box[2 * (size_t)v + 1];
-    sbox[2 * (size_t)i] = lo;
-    sbox[2 * (size_t)i + 1] = hi;
-    const uint32_t k = skey[i];
-    const uint32_t first = (i == 0) ? 0u : skey[i - 1] + 1u;  // cells (prev, k]
-    if (k + 1u > first) fill_cells(LB, first, k + 1u - first, i, gaps, gap_cap, ctl);
-    if (i == n - 1) {
-        // cells above the last key up to ncells+1 (inclusive) -> n
-        if (ncells + 2u > k + 1u) fill_cells(LB, k + 1u, ncells + 2u - (k + 1u), n, gaps, gap_cap, ctl);
-        if (k < ncells) ctl->n_small = n;  // no big body: the fill above covered LB[ncells]
+    if (n_in == 0) {  // an empty world (a slab that owns nothing this step): every cell range is empty
+        if (i == 0) {
+            fill_cells(LB, 0u, ncells + 3u, 0u, gaps, gap_cap, ctl);
+            ctl->n = 0, ctl->n_small = 0;
+        }
+        return;
     }
-    if (k == ncells && (i == 0 || skey[i - 1] != ncells)) ctl->n_small = i;
+    if (i >= n_in) return;
+    const uint32_t k = skey[i];
+    const uint32_t prev1 = (i == 0) ? 0u : skey[i - 1] + 1u;  // this thread owns cells [prev1, k]
+    if (k + 1u > prev1) {
+        fill_cells(LB, prev1, k + 1u - prev1, i, gaps, gap_cap, ctl);
+        if (prev1 <= ncells && ncells <= k) ctl->n_small = i;
+        if (prev1 <= ncells + 1u && ncells + 1u <= k) ctl->n = i;
+    }
+    if (i == n_in - 1) {
+        // cells above the last key up to ncells+2 (inclusive) -> n_in
+        if (ncells + 3u > k + 1u) fill_cells(LB, k + 1u, ncells + 3u - (k + 1u), n_in, gaps, gap_cap, ctl);
+        if (k < ncells) ctl->n_small = n_in;
+        if (k < ncells + 1u) ctl->n = n_in;
+    }
+    if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here
+    const uint32_t s = sval[i];
+    float4 p = P0[s], v = V0[s], a = A0[s];
+    const float4 lo = Lo0[s], hi = Hi0[s];
+    uint32_t flags = __float_as_uint(a.w);
+    if (flags & F_INTEGRATED) {
+        flags &= ~F_INTEGRATED;
+        a.w = __uint_as_float(flags);
+    } else {
+        integrate_body(p, v, a, dt, d16, d18, d35);
+    }
+    P1[i] = p, V1[i] = v, A1[i] = a, Lo1[i] = lo, Hi1[i] = hi;
+    // world AABB = offsets + position (physics.rs:117: corner + pos; min/max commute with the rounding)
+    const uint32_t tag = i | ((flags & F_STATIC) ? TOPBIT : 0u);
+    sbox[2 * (size_t)i] = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, __uint_as_float(tag));
+    sbox[2 * (size_t)i + 1] = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, hi.w /* rank */);
+    chain_cnt[i] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_fill_gaps(const Gap* __restrict__ gaps, uint32_t gap_cap, const Ctl* ctl,
@@ -490,7 +549,7 @@ __device__ __forceinline__ void flush_pairs(const uint4* __restrict__ stage, uin
 constexpr int FP_THREADS = 128;
 
 __global__ void __launch_bounds__(FP_THREADS)
-    k_find_pairs(uint32_t n, const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
+    k_find_pairs(const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
                  const uint32_t* __restrict__ LB, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
                  uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
     // warp-synchronous: the 32 lanes walk their candidate ranges in lock step, hits are compacted with a
@@ -500,10 +559,12 @@ __global__ void __launch_bounds__(FP_THREADS)
     uint4* stage = stage_all[threadIdx.x >> 5];
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = ctl->n;
+    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA beyond the live bodies (grids are sized for capacity)
     const bool live = p < n;
     const GridParams g = ctl->grid;
     const float mu = ctl->margin;
-    const uint32_t n_small = LB[g.ncells];
+    const uint32_t n_small = ctl->n_small;
     float4 alo = make_float4(0, 0, 0, 0), ahi = alo;
     float ma = 0.f;
     uint32_t k = 0;
@@ -595,12 +656,12 @@ __global__ void __launch_bounds__(256)
 constexpr uint32_t CHAIN_INLINE = 48;  // longer chains go to the block-wide sorter
 
 __global__ void __launch_bounds__(256)
-    k_sort_chains(uint32_t n, const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj,
+    k_sort_chains(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj,
                   uint32_t* __restrict__ pending, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl,
                   const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
+    if (x >= ctl->n) return;
     const uint32_t b = offs[x], e = offs[x + 1];
     const uint32_t d = e - b;
     if (d == 0) return;
@@ -882,7 +943,7 @@ __global__ void __launch_bounds__(256)
 constexpr float REACH_SLACK = 1.0001f;  // covers the rounding of the measured displacement
 
 __global__ void __launch_bounds__(256)
-    k_requery(uint32_t n, const float4* __restrict__ box, const float4* __restrict__ sbox,
+    k_requery(const float4* __restrict__ box, const float4* __restrict__ sbox,
               const uint32_t* __restrict__ LB, const float* __restrict__ dmax, const float* __restrict__ reach,
               const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint4* __restrict__ pairs,
               uint32_t* __restrict__ pending, uint32_t pair_cap, Ctl* ctl) {
@@ -892,7 +953,7 @@ __global__ void __launch_bounds__(256)
     const float mu = ctl->margin;
     const float ext_max = ctl->ext_max;
     const float partner_reach = fmaxf(mu * ext_max, __uint_as_float(ctl->max_abs_disp_bits) * REACH_SLACK);
-    const uint32_t n_small = LB[g.ncells];
+    const uint32_t n_small = ctl->n_small, n = ctl->n;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t ei = warp; ei < ne; ei += nwarps) {
@@ -955,8 +1016,9 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const float4* __restrict__ P0, const float4* __restrict__ V0,
-              const float4* __restrict__ A, float4* __restrict__ P1, float4* __restrict__ V1,
+    k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ sval,
+              const float4* __restrict__ P0, const float4* __restrict__ V0,
+              const float4* __restrict__ A0, float4* __restrict__ P1, float4* __restrict__ V1,
               uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ pending, float* __restrict__ dmax,
               float* __restrict__ reach, const uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl, float dt,
               float d16, float d18, float d35) {
@@ -972,8 +1034,10 @@ __global__ void __launch_bounds__(256)
             if (t & TOPBIT) continue;
             chain_cnt[t] = 0;
             if (r.w & TOPBIT) {  // the sweep wrote this body: recompute its post-integration state (idempotent)
-                float4 p = P0[t], v = V0[t];
-                integrate_body(p, v, A[t], dt, d16, d18, d35);
+                const uint32_t s0 = sval[t];  // its slot in the untouched input set
+                float4 p = P0[s0], v = V0[s0];
+                const float4 a = A0[s0];
+                if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
                 P1[t] = p;
                 V1[t] = v;
             }
@@ -1037,6 +1101,8 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
         }
         c.steps_total += 1;
     }
+    // the live set of an accepted step is the input of the next one (ghosts and departed bodies were dropped)
+    if (latch == 1 || (latch == 0 && c.step_flags == 0)) c.n_in = c.n;
     *snapshot_out = c;  // what the host reads (stats of THIS step)
     if (latch == 0 && c.step_flags == SF_MARGIN) return;  // sync mode: the host continues the repair loop
     // (latch == 2: the host gave up on this step; just reset)
@@ -1074,11 +1140,12 @@ __global__ void k_export_pairs(const uint4* __restrict__ pairs, uint32_t np, int
 }
 
 __global__ void k_gather_pairs(const uint4* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t m,
-                               uint2* __restrict__ out) {
+                               const float4* __restrict__ Lo, uint2* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint4 r = pairs[order[i]];
-    out[i] = make_uint2(r.x & ~TOPBIT, r.y & ~TOPBIT);
+    // pair records hold slots of the current (cell-sorted) set; report body ids
+    out[i] = make_uint2(__float_as_uint(Lo[r.x & ~TOPBIT].w), __float_as_uint(Lo[r.y & ~TOPBIT].w));
 }
 
 }  // namespace gp

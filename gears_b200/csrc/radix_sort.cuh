@@ -46,15 +46,18 @@ static inline RsPlan rs_plan(uint32_t n, int sm_count) {
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const KeyT* __restrict__ keys, uint32_t n, int shift,
+__global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const KeyT* __restrict__ keys, uint32_t n_max,
+                                                         const uint32_t* __restrict__ n_dev, int shift,
                                                          uint32_t tiles_per_cta, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[RS_WARPS][RS_RADIX];
+    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;  // the element count may live on the device
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
     const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_cta * RS_TILE;
     uint64_t end = begin + (uint64_t)tiles_per_cta * RS_TILE;
     if (end > n) end = n;
+    if (begin > n) end = begin;
     // per-warp private histograms: shared atomics never collide across warps
     for (uint64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
         atomicAdd(&sh[warp][rs_digit(keys[i], shift)], 1u);
@@ -110,8 +113,9 @@ __global__ void __launch_bounds__(RS_SCAN_THREADS) rs_scan(uint32_t* __restrict_
 template <typename KeyT, bool IOTA>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_downsweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                 uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t tiles_per_cta,
-                 const uint32_t* __restrict__ hist) {
+                 uint32_t* __restrict__ vals_out, uint32_t n_max, const uint32_t* __restrict__ n_dev, int shift,
+                 uint32_t tiles_per_cta, const uint32_t* __restrict__ hist) {
+    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     KeyT* skeys = reinterpret_cast<KeyT*>(rs_smem);
     uint32_t* svals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);
@@ -223,12 +227,14 @@ static inline size_t rs_smem_bytes() {
     return (sizeof(KeyT) + sizeof(uint32_t)) * (size_t)RS_TILE;
 }
 
-// Temp storage: hist = RS_RADIX * grid u32.  Sorts `key_bits` low bits.  Ping-pongs between (k0,v0)
+// Temp storage: hist = RS_RADIX * grid u32.  Sorts `key_bits` low bits of the first min(n, *n_dev) elements
+// (n = host upper bound that sizes the grid; n_dev = optional device-resident count).  Ping-pongs between (k0,v0)
 // and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).  If iota_first, the values of
 // the first pass are the element indices (v0 is not read).  *launches is incremented per kernel.
 template <typename KeyT>
 static inline int rs_sort(KeyT* k0, uint32_t* v0, KeyT* k1, uint32_t* v1, uint32_t n, int key_bits, bool iota_first,
-                          uint32_t* hist, int sm_count, cudaStream_t st, uint64_t* launches) {
+                          uint32_t* hist, int sm_count, cudaStream_t st, uint64_t* launches,
+                          const uint32_t* n_dev = nullptr) {
     if (n == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -246,14 +252,14 @@ static inline int rs_sort(KeyT* k0, uint32_t* v0, KeyT* k1, uint32_t* v1, uint32
         const uint32_t* vi = cur ? v1 : v0;
         KeyT* ko = cur ? k0 : k1;
         uint32_t* vo = cur ? v0 : v1;
-        rs_upsweep<KeyT><<<p.grid, RS_THREADS, 0, st>>>(ki, n, shift, p.tiles_per_cta, hist);
+        rs_upsweep<KeyT><<<p.grid, RS_THREADS, 0, st>>>(ki, n, n_dev, shift, p.tiles_per_cta, hist);
         rs_scan<<<1, RS_SCAN_THREADS, 0, st>>>(hist, RS_RADIX * p.grid);
         if (iota_first && shift == 0)
             rs_downsweep<KeyT, true>
-                <<<p.grid, RS_THREADS, rs_smem_bytes<KeyT>(), st>>>(ki, vi, ko, vo, n, shift, p.tiles_per_cta, hist);
+                <<<p.grid, RS_THREADS, rs_smem_bytes<KeyT>(), st>>>(ki, vi, ko, vo, n, n_dev, shift, p.tiles_per_cta, hist);
         else
             rs_downsweep<KeyT, false>
-                <<<p.grid, RS_THREADS, rs_smem_bytes<KeyT>(), st>>>(ki, vi, ko, vo, n, shift, p.tiles_per_cta, hist);
+                <<<p.grid, RS_THREADS, rs_smem_bytes<KeyT>(), st>>>(ki, vi, ko, vo, n, n_dev, shift, p.tiles_per_cta, hist);
         if (launches) *launches += 3;
         cur ^= 1;
     }
