@@ -44,13 +44,11 @@ struct gp_world {
     bool slot_valid = false;
     // broad phase
     float4* sbox = nullptr;       // world AABBs of the current step in cell order (lo|tag, hi|rank)
-    int sorted_r = 0;             // which (key,val) buffer holds the sorted keys / permutation of the current step
-    uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr};
-    uint32_t* hist = nullptr;
-    uint32_t* LB = nullptr;
+    uint32_t *key = nullptr, *lrank = nullptr;  // per input slot: cell key, arrival rank within the cell
+    uint32_t* perm = nullptr;                   // per output slot: the input slot it came from
+    uint32_t* LB = nullptr;                     // cell histogram, scanned in place into cell start offsets
     uint32_t lb_cap = 0;
-    Gap* gaps = nullptr;
-    uint32_t gap_cap = 0;
+    uint32_t* lb_tiles = nullptr;               // scan scratch
     uint32_t max_cells = 0;
     int key_bits = 1;
     float thr = 0.f;
@@ -125,8 +123,8 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 static void free_all(gp_world* w) {
     void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A[0],  w->A[1],      w->Lo[0],  w->Lo[1],
                     w->Hi[0],  w->Hi[1], w->ext,        w->slot_of,
-                    w->sbox,  w->key[0],     w->key[1],     w->val[0], w->val[1],    w->hist,   w->LB,
-                    w->gaps,   w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
+                    w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
+                    w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
                     w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -233,11 +231,9 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     CK(dmalloc(&w->ext, cap));
     CK(dmalloc(&w->slot_of, cap));
     CK(dmalloc(&w->sbox, 2 * (size_t)cap));
-    for (int i = 0; i < 2; ++i) {
-        CK(dmalloc(&w->key[i], cap));
-        CK(dmalloc(&w->val[i], cap));
-    }
-    CK(dmalloc(&w->hist, (size_t)RS_RADIX * (size_t)w->sm_count * 4));
+    CK(dmalloc(&w->key, cap));
+    CK(dmalloc(&w->lrank, cap));
+    CK(dmalloc(&w->perm, cap));
     CK(dmalloc(&w->chain_cnt, (size_t)cap + 1));
     CK(dmalloc(&w->offs, (size_t)cap + 2));
     CK(dmalloc(&w->tile_sums, (size_t)cdiv(cap, SC_TILE) + 1));
@@ -345,10 +341,9 @@ static gp_status setup_grid(gp_world* w) {
     while ((1ull << bits) <= (uint64_t)g0.ncells + 1) ++bits;  // keys: cells, ncells = big list, ncells+1 = dead
     w->key_bits = bits;
     if (g0.ncells + 3 > w->lb_cap) {
-        CK(dmalloc(&w->LB, (size_t)g0.ncells + 3));
+        CK(dmalloc(&w->LB, (size_t)g0.ncells + 4));
         w->lb_cap = g0.ncells + 3;
-        w->gap_cap = g0.ncells / GAP_DIRECT + 1024;
-        CK(dmalloc(&w->gaps, w->gap_cap));
+        CK(dmalloc(&w->lb_tiles, (size_t)cdiv(w->lb_cap, SC_TILE) + 1));
     }
     // control block
     Ctl hc{};
@@ -641,7 +636,7 @@ static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     cudaStream_t st = w->st;
     const int c = w->cur, o = c ^ 1;
     const uint32_t* gate = &w->ctl->repair_needed;
-    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->val[w->sorted_r], w->P[c], w->V[c],
+    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->perm, w->P[c], w->V[c],
                                                w->A[c], w->P[o], w->V[o], w->chain_cnt, w->pending, w->dmax, w->reach,
                                                w->escapees, w->cap, w->ctl, dt, d[0], d[1], d[2]);
     k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
@@ -670,21 +665,22 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
     w->slot_valid = false;
     if (nb) {
         prof_mark(w, 0);
-        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c], w->key[0], w->ctl, dt, d[0],
-                                              d[1], d[2]);
+        // K1 + K2: one-pass radix (bucket) sort by cell key: histogram with the keys, scan, scatter
+        const uint32_t ncnt = w->max_cells + 2;  // counters: every cell of the finest grid + big list + dead
+        CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
+        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c], w->key, w->lrank, w->LB,
+                                              w->ctl, dt, d[0], d[1], d[2]);
         w->launches++;
         prof_mark(w, 1);
-        const int r = rs_sort<uint32_t>(w->key[0], w->val[0], w->key[1], w->val[1], nb, w->key_bits, true, w->hist,
-                                        w->sm_count, st, &w->launches, &w->ctl->n_in);
-        w->sorted_r = r;
+        exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
         prof_mark(w, 2);
-        k_gather_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key[r], w->val[r], w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c],
-                                                      w->P[o], w->V[o], w->A[o], w->Lo[o], w->Hi[o], w->sbox, w->chain_cnt,
-                                                      w->LB, w->gaps, w->gap_cap, w->ctl, dt, d[0], d[1], d[2]);
-        k_fill_gaps<<<w->sm_count * 4, 256, 0, st>>>(w->gaps, w->gap_cap, w->ctl, w->LB);
-        w->launches += 2;
+        k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c],
+                                                       w->P[o], w->V[o], w->A[o], w->Lo[o], w->Hi[o], w->sbox,
+                                                       w->chain_cnt, w->perm, w->dmax, w->reach, w->LB, w->ctl, dt, d[0],
+                                                       d[1], d[2]);
+        w->launches += 1;
         prof_mark(w, 3);
-        k_find_pairs<<<cdiv(nb, FP_THREADS), FP_THREADS, 0, st>>>(w->key[r], w->sbox, w->LB, w->pairs, w->pending,
+        k_find_pairs<<<cdiv(nb, FP_THREADS), FP_THREADS, 0, st>>>(w->sbox, w->LB, w->pairs, w->pending,
                                                                   w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
@@ -768,7 +764,7 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
         }
         const Ctl& c = *w->h_ctl;
         const uint32_t f = c.step_flags;
-        if (f & (SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW))
+        if (f & (SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW))
             return fail(w, GP_ERR_CAPACITY, "internal work list overflow (flags 0x%x)", f);
         if (f & SF_PAIR_OVERFLOW) {
             if (no_retry || retries >= 8)

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "scan.cuh"
+
 namespace cg = cooperative_groups;
 
 namespace gp {
@@ -67,7 +69,6 @@ struct Ctl {
     uint32_t max_disp_bits;   // max over bodies of (per-axis AABB displacement / body extent) during the sweep
     uint32_t frontier_n[3];   // rotating: round r consumes [r%3], fills [(r+1)%3], clears [(r+2)%3]
     uint32_t n_heavy;
-    uint32_t n_gaps;
     uint32_t step_flags;      // SF_* of the current step
     uint32_t n_small;         // bodies in the grid (sorted prefix); n - n_small = big list
     uint32_t sticky_flags;    // OR of step_flags over async steps
@@ -114,7 +115,6 @@ __host__ __device__ inline GridParams make_grid(const float* lo, const float* hi
 constexpr uint32_t SF_PAIR_OVERFLOW = 1u;
 constexpr uint32_t SF_MARGIN = 2u;       // the candidate set was still growing when the repair rounds ran out
 constexpr uint32_t SF_MARGIN_MAX = 4u;   // (unused)
-constexpr uint32_t SF_GAP_OVERFLOW = 8u;
 constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
 constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
 
@@ -392,7 +392,8 @@ __device__ __forceinline__ uint32_t body_key(const GridParams& g, const float4 p
 __global__ void __launch_bounds__(256)
     k_keys(const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
            const float4* __restrict__ Lo, const float4* __restrict__ Hi, uint32_t* __restrict__ key,
-           const Ctl* __restrict__ ctl, float dt, float d16, float d18, float d35) {
+           uint32_t* __restrict__ lrank, uint32_t* __restrict__ cell_cnt, const Ctl* __restrict__ ctl, float dt,
+           float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ctl->n_in) return;
     const GridParams g = ctl->grid;
@@ -400,71 +401,41 @@ __global__ void __launch_bounds__(256)
     const float4 a = A[i], lo = Lo[i], hi = Hi[i];
     const uint32_t flags = __float_as_uint(a.w);
     if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
-    key[i] = body_key(g, p, lo, hi, flags);
+    const uint32_t k = body_key(g, p, lo, hi, flags);
+    key[i] = k;
+    // K2 is a one-pass radix sort whose single digit is the whole cell key: this is its histogram.  The bodies
+    // arrive in last step's cell order, so the atomics of a warp fall on a few neighbouring L2 lines.
+    lrank[i] = atomicAdd(&cell_cnt[k], 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: gather the bodies into cell order, integrate, emit world AABBs, build the cell lower-bound table
-// LB[c] = first sorted position whose key >= c (c in [0, ncells+2]; key ncells = big list, key ncells+1 = dead).
-// Thread i owns cells (key[i-1], key[i]].  Long empty runs go to a gap list that k_fill_gaps spreads over the grid.
-// R 8 (key, slot) + R 80 (gather) + W 80 (next set) + W 32 (AABB) + W 4 (chain counter) + the cell table.
+// K2: exclusive scan of the cell histogram in place (scan.cuh) -> LB[c] = first slot of cell c, for
+// c in [0, ncells+2] (key ncells = big list, key ncells+1 = dead); LB[ncells+2] = bodies entering the step.
+// K3: scatter the bodies into cell order (slot = LB[key] + arrival rank within the cell), integrate, emit
+// world AABBs.  R 8 (key, rank) + R 80 (own record, coalesced) + W 80 (next set) + W 32 (AABB) + W 12.
+// The order inside a cell is the arrival order of the atomics: results do not depend on it (the contact
+// sweep orders by the reference's iteration rank, never by slot).
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t GAP_DIRECT = 32;
-constexpr uint32_t GAP_CHUNK = 1u << 16;
-struct Gap {
-    uint32_t c0, len, val;
-};
-
-__device__ __forceinline__ void fill_cells(uint32_t* LB, uint32_t c0, uint32_t len, uint32_t val, Gap* gaps,
-                                           uint32_t gap_cap, Ctl* ctl) {
-    if (len <= GAP_DIRECT) {
-        for (uint32_t c = 0; c < len; ++c) LB[c0 + c] = val;
-    } else {
-        for (uint32_t o = 0; o < len; o += GAP_CHUNK) {
-            const uint32_t slot = atomicAdd(&ctl->n_gaps, 1u);
-            if (slot < gap_cap)
-                gaps[slot] = Gap{c0 + o, min(GAP_CHUNK, len - o), val};
-            else
-                atomicOr(&ctl->step_flags, SF_GAP_OVERFLOW);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256)
-    k_gather_cells(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sval,
-                   const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A0,
-                   const float4* __restrict__ Lo0, const float4* __restrict__ Hi0, float4* __restrict__ P1,
-                   float4* __restrict__ V1, float4* __restrict__ A1, float4* __restrict__ Lo1, float4* __restrict__ Hi1,
-                   float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ LB, Gap* gaps,
-                   uint32_t gap_cap, Ctl* ctl, float dt, float d16, float d18, float d35) {
+    k_scatter_cells(const uint32_t* __restrict__ key, const uint32_t* __restrict__ lrank,
+                    const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A0,
+                    const float4* __restrict__ Lo0, const float4* __restrict__ Hi0, float4* __restrict__ P1,
+                    float4* __restrict__ V1, float4* __restrict__ A1, float4* __restrict__ Lo1, float4* __restrict__ Hi1,
+                    float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ perm,
+                    float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ LB, Ctl* ctl,
+                    float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_in = ctl->n_in;
     const uint32_t ncells = ctl->grid.ncells;
-    if (n_in == 0) {  // an empty world (a slab that owns nothing this step): every cell range is empty
-        if (i == 0) {
-            fill_cells(LB, 0u, ncells + 3u, 0u, gaps, gap_cap, ctl);
-            ctl->n = 0, ctl->n_small = 0;
-        }
-        return;
+    if (i == 0) {
+        ctl->n_small = LB[ncells];
+        ctl->n = LB[ncells + 1u];
     }
-    if (i >= n_in) return;
-    const uint32_t k = skey[i];
-    const uint32_t prev1 = (i == 0) ? 0u : skey[i - 1] + 1u;  // this thread owns cells [prev1, k]
-    if (k + 1u > prev1) {
-        fill_cells(LB, prev1, k + 1u - prev1, i, gaps, gap_cap, ctl);
-        if (prev1 <= ncells && ncells <= k) ctl->n_small = i;
-        if (prev1 <= ncells + 1u && ncells + 1u <= k) ctl->n = i;
-    }
-    if (i == n_in - 1) {
-        // cells above the last key up to ncells+2 (inclusive) -> n_in
-        if (ncells + 3u > k + 1u) fill_cells(LB, k + 1u, ncells + 3u - (k + 1u), n_in, gaps, gap_cap, ctl);
-        if (k < ncells) ctl->n_small = n_in;
-        if (k < ncells + 1u) ctl->n = n_in;
-    }
+    if (i >= ctl->n_in) return;
+    const uint32_t k = key[i];
     if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here
-    const uint32_t s = sval[i];
-    float4 p = P0[s], v = V0[s], a = A0[s];
-    const float4 lo = Lo0[s], hi = Hi0[s];
+    const uint32_t s = LB[k] + lrank[i];
+    float4 p = P0[i], v = V0[i], a = A0[i];
+    const float4 lo = Lo0[i], hi = Hi0[i];
     uint32_t flags = __float_as_uint(a.w);
     if (flags & F_INTEGRATED) {
         flags &= ~F_INTEGRATED;
@@ -472,21 +443,14 @@ __global__ void __launch_bounds__(256)
     } else {
         integrate_body(p, v, a, dt, d16, d18, d35);
     }
-    P1[i] = p, V1[i] = v, A1[i] = a, Lo1[i] = lo, Hi1[i] = hi;
+    P1[s] = p, V1[s] = v, A1[s] = a, Lo1[s] = lo, Hi1[s] = hi;
     // world AABB = offsets + position (physics.rs:117: corner + pos; min/max commute with the rounding)
-    const uint32_t tag = i | ((flags & F_STATIC) ? TOPBIT : 0u);
-    sbox[2 * (size_t)i] = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, __uint_as_float(tag));
-    sbox[2 * (size_t)i + 1] = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, hi.w /* rank */);
-    chain_cnt[i] = 0;
-}
-
-__global__ void __launch_bounds__(256) k_fill_gaps(const Gap* __restrict__ gaps, uint32_t gap_cap, const Ctl* ctl,
-                                                   uint32_t* __restrict__ LB) {
-    const uint32_t ng = min(ctl->n_gaps, gap_cap);
-    for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
-        const Gap g = gaps[gi];
-        for (uint32_t c = threadIdx.x; c < g.len; c += blockDim.x) LB[g.c0 + c] = g.val;
-    }
+    const uint32_t tag = s | ((flags & F_STATIC) ? TOPBIT : 0u);
+    sbox[2 * (size_t)s] = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, __uint_as_float(tag));
+    sbox[2 * (size_t)s + 1] = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, hi.w /* rank */);
+    chain_cnt[s] = 0;
+    perm[s] = i;  // slot in the input set: k_restore re-integrates from there
+    dmax[s] = 0.0f, reach[s] = 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -525,42 +489,63 @@ __device__ __forceinline__ bool test_candidate(const float4 alo, const float4 ah
     return true;
 }
 
-// write `cnt` (<= 32) staged pair records of this warp with ONE global atomic and coalesced 16 B stores
-__device__ __forceinline__ void flush_pairs(const uint4* __restrict__ stage, uint32_t cnt, int lane,
-                                            uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
-                                            uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&ctl->n_pairs, cnt);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((uint32_t)lane < cnt) {
-        const uint32_t slot = base + lane;
-        if (slot < pair_cap) {
-            const uint4 rec = stage[lane];
-            pairs[slot] = rec;
-            pending[slot] = 0;
-            if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
-            if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
-        } else {
-            atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+constexpr int FP_THREADS = 256;
+
+// Walk the candidate ranges of body p: the rest of its own cell + the 13 forward neighbour cells (5 contiguous
+// runs of slots through LB) + the big list.  EMIT = false: count the candidate pairs.  EMIT = true: write them
+// to out[0..count).  Both passes see the same (L1/L2-resident) data, so the counts agree.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_candidates(uint32_t p, uint32_t n, uint32_t n_small, bool in_grid,
+                                                    uint32_t k, const GridParams& g, float mu, const float4 alo,
+                                                    const float4 ahi, float ma, const float4* __restrict__ sbox,
+                                                    const uint32_t* __restrict__ LB, uint4* __restrict__ out,
+                                                    uint32_t out_room, uint32_t* __restrict__ pending_out,
+                                                    uint32_t* __restrict__ chain_cnt, uint32_t& nsnap) {
+    const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        uint32_t q0 = 0, q1 = 0;
+        if (r == 5) {
+            q0 = max(p + 1, n_small), q1 = n;
+        } else if (in_grid) {
+            if (r == 0) q0 = p + 1, q1 = LB[k + 2];
+            if (r == 1) q0 = LB[k + row - 1], q1 = LB[k + row + 2];
+            if (r == 2) q0 = LB[k + slab - row - 1], q1 = LB[k + slab - row + 2];
+            if (r == 3) q0 = LB[k + slab - 1], q1 = LB[k + slab + 2];
+            if (r == 4) q0 = LB[k + slab + row - 1], q1 = LB[k + slab + row + 2];
+            q1 = min(q1, n_small);
+        }
+        for (uint32_t q = q0; q < q1; ++q) {
+            const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
+            uint4 rec;
+            if (!test_candidate(alo, ahi, ma, blo, bhi, mu, rec)) continue;
+            if (EMIT) {
+                if (cnt < out_room) {
+                    out[cnt] = rec;
+                    pending_out[cnt] = 0;
+                    if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
+                    if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
+                    nsnap += rec.z >> 31;
+                }
+            }
+            ++cnt;
         }
     }
+    return cnt;
 }
 
-constexpr int FP_THREADS = 128;
-
+// One thread per body; a CTA counts, reserves ONE contiguous block of pair slots (a single global atomic per
+// 256 bodies: thousands of same-address atomics per launch instead of one per warp flush), then emits.
+// Pair ids are thereby deterministic up to the CTA arrival order.
 __global__ void __launch_bounds__(FP_THREADS)
-    k_find_pairs(const uint32_t* __restrict__ skey, const float4* __restrict__ sbox,
-                 const uint32_t* __restrict__ LB, uint4* __restrict__ pairs, uint32_t* __restrict__ pending,
-                 uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
-    // warp-synchronous: the 32 lanes walk their candidate ranges in lock step, hits are compacted with a
-    // ballot into a per-warp shared-memory stage and leave in full 32-record (512 B) bursts.
-    __shared__ uint4 stage_all[FP_THREADS / 32][64];
-    const int lane = threadIdx.x & 31;
-    uint4* stage = stage_all[threadIdx.x >> 5];
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
+                 uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    __shared__ uint32_t sm_scan[33];
+    __shared__ uint32_t sm_base;
     const uint32_t n = ctl->n;
     if (blockIdx.x * blockDim.x >= n) return;  // whole CTA beyond the live bodies (grids are sized for capacity)
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < n;
     const GridParams g = ctl->grid;
     const float mu = ctl->margin;
@@ -568,61 +553,34 @@ __global__ void __launch_bounds__(FP_THREADS)
     float4 alo = make_float4(0, 0, 0, 0), ahi = alo;
     float ma = 0.f;
     uint32_t k = 0;
+    const bool in_grid = live && p < n_small;
     if (live) {
         alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
         ma = mu * box_extent(alo, ahi);
-        if (p < n_small) k = skey[p];
+        // same expression as body_key() in K1: bit-identical cell
+        if (in_grid) k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
     }
-    const bool in_grid = live && p < n_small;
-    const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
-    uint32_t cnt = 0, nsnap = 0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        // forward half of the 27-neighbourhood as 5 contiguous ranges of sorted positions, then the big list
-        uint32_t q0 = 0, q1 = 0;
-        if (r == 5) {
-            if (live) q0 = max(p + 1, n_small), q1 = n;
-        } else if (in_grid) {
-            if (r == 0) q0 = p + 1, q1 = LB[k + 2];
-            if (r == 1) q0 = LB[k + row - 1], q1 = LB[k + row + 2];
-            if (r == 2) q0 = LB[k + slab - row - 1], q1 = LB[k + slab - row + 2];
-            if (r == 3) q0 = LB[k + slab - 1], q1 = LB[k + slab + 2];
-            if (r == 4) q0 = LB[k + slab + row - 1], q1 = LB[k + slab + row + 2];
-        }
-        const uint32_t len = q1 > q0 ? q1 - q0 : 0u;
-        const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
-        for (uint32_t it = 0; it < maxlen; ++it) {
-            bool hit = false;
-            uint4 rec = make_uint4(0, 0, 0, 0);
-            if (it < len) {
-                const uint32_t q = q0 + it;
-                const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-                hit = test_candidate(alo, ahi, ma, blo, bhi, mu, rec);
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                if (hit) {
-                    stage[cnt + __popc(m & lt)] = rec;  // cnt <= 31 here, so the slot is < 64
-                    nsnap += (rec.z >> 31);
-                }
-                cnt += __popc(m);
-                __syncwarp();
-                if (cnt >= 32) {
-                    flush_pairs(stage, 32, lane, pairs, pending, chain_cnt, pair_cap, ctl);
-                    __syncwarp();
-                    const uint4 carry = stage[32 + lane];
-                    __syncwarp();
-                    stage[lane] = carry;
-                    cnt -= 32;
-                    __syncwarp();
-                }
-            }
-        }
+    uint32_t nsnap = 0;
+    uint32_t cnt = 0;
+    if (live)
+        cnt = walk_candidates<false>(p, n, n_small, in_grid, k, g, mu, alo, ahi, ma, sbox, LB, nullptr, 0u, nullptr,
+                                     nullptr, nsnap);
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan_256(cnt, &total, sm_scan);
+    if (threadIdx.x == 0) sm_base = total ? atomicAdd(&ctl->n_pairs, total) : 0u;
+    __syncthreads();
+    if (total == 0) return;
+    const uint32_t base = sm_base;
+    if (threadIdx.x == 0 && base + total > pair_cap) atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+    if (cnt) {
+        const uint32_t first = base + excl;
+        const uint32_t room = first < pair_cap ? pair_cap - first : 0u;
+        walk_candidates<true>(p, n, n_small, in_grid, k, g, mu, alo, ahi, ma, sbox, LB, pairs + first, room,
+                              pending + first, chain_cnt, nsnap);
     }
-    if (cnt) flush_pairs(stage, cnt, lane, pairs, pending, chain_cnt, pair_cap, ctl);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsnap += __shfl_xor_sync(0xffffffffu, nsnap, o);
-    if (lane == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
+    if ((threadIdx.x & 31) == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -790,12 +748,28 @@ __device__ __forceinline__ bool resolve_pair(BodyRW& a, BodyRW& b, V3 amin, V3 a
     return moved;
 }
 
-__device__ __forceinline__ void frontier_push(uint32_t q, uint32_t* __restrict__ frontier, uint32_t* counter) {
-    cg::coalesced_group g = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
-    base = g.shfl(base, 0);
-    frontier[base + g.thread_rank()] = q;
+// Frontier appends are staged per CTA in shared memory and leave with ONE global atomic per flush: the
+// next-frontier counter is a single address, and same-address atomics serialise in L2.
+constexpr uint32_t FB_CAP = 2048;
+struct FrontierStage {
+    uint32_t buf[FB_CAP];
+    uint32_t cnt, base;
+};
+__device__ __forceinline__ void stage_push(FrontierStage& fs, uint32_t q) { fs.buf[atomicAdd(&fs.cnt, 1u)] = q; }
+// called by ALL threads of the CTA (contains barriers); room = pushes the next iteration may add
+__device__ __forceinline__ void stage_flush(FrontierStage& fs, uint32_t* __restrict__ frontier, uint32_t* counter,
+                                            uint32_t room) {
+    __syncthreads();
+    const uint32_t c = fs.cnt;
+    __syncthreads();  // everybody has read the count before anybody pushes again
+    if (c + room <= FB_CAP) return;
+    if (threadIdx.x == 0) fs.base = atomicAdd(counter, c);
+    __syncthreads();
+    const uint32_t base = fs.base;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) frontier[base + i] = fs.buf[i];
+    __syncthreads();
+    if (threadIdx.x == 0) fs.cnt = 0;
+    __syncthreads();
 }
 
 // A body whose AABB leaves its K1 snapshot inflated by mu*extent is an ESCAPEE: the candidate set built
@@ -834,11 +808,18 @@ __global__ void __launch_bounds__(256)
             uint32_t* __restrict__ escapees, uint32_t esc_cap, const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;  // uniform across the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
+    __shared__ FrontierStage fs;
+    if (threadIdx.x == 0) fs.cnt = 0;
+    __syncthreads();
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     // round 0 frontier: pairs at the head of all their chains
-    for (uint32_t pid = gtid; pid < np; pid += gsz)
-        if (__ldcg(&pending[pid]) == 0) frontier_push(pid, frontier0, &ctl->frontier_n[0]);
+    for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gsz) {
+        const uint32_t pid = p0 + threadIdx.x;
+        if (pid < np && __ldcg(&pending[pid]) == 0) stage_push(fs, pid);
+        stage_flush(fs, frontier0, &ctl->frontier_n[0], blockDim.x);
+    }
+    stage_flush(fs, frontier0, &ctl->frontier_n[0], FB_CAP);
     grid.sync();
     const float mverify = 0.98f * ctl->margin;
     uint32_t rounds = 0, contacts = 0;
@@ -852,59 +833,66 @@ __global__ void __launch_bounds__(256)
         if (gtid == 0) ctl->frontier_n[cz] = 0;
         const uint32_t* fin = (rounds & 1u) ? frontier1 : frontier0;
         uint32_t* fout = (rounds & 1u) ? frontier0 : frontier1;
-        for (uint32_t f = gtid; f < nf; f += gsz) {
-            const uint32_t pid = __ldcg(&fin[f]);
-            uint4 rec = pairs[pid];
-            const uint32_t ia = rec.x & ~TOPBIT, ib = rec.y & ~TOPBIT;
-            BodyRW a, b;
-            a.is_static = (rec.x & TOPBIT) != 0;
-            b.is_static = (rec.y & TOPBIT) != 0;
-            const float4 pa = ldcg4(&P[ia]), pb = ldcg4(&P[ib]);
-            const float4 loa = Lo[ia], hia = Hi[ia], lob = Lo[ib], hib = Hi[ib];
-            a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
-            b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
-            const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
-            const V3 bmin = b.omin + b.pos, bmax = b.omax + b.pos;
-            // physics.rs:159-164 on the CURRENT positions
-            const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y &&
-                             amin.z < bmax.z && amax.z > bmin.z;
-            if (hit) {
-                ++contacts;
-                const float4 va = ldcg4(&V[ia]), vb = ldcg4(&V[ib]);
-                a.vel = xyz(va), a.rest = va.w;
-                b.vel = xyz(vb), b.rest = vb.w;
-                const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
-                if (!a.is_static) {
-                    __stcg(&P[ia], make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass));
-                    __stcg(&V[ia], make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest));
+        for (uint32_t f0 = blockIdx.x * blockDim.x; f0 < nf; f0 += gsz) {
+            const uint32_t f = f0 + threadIdx.x;
+            if (f < nf) {
+                const uint32_t pid = __ldcg(&fin[f]);
+                uint4 rec = pairs[pid];
+                const uint32_t ia = rec.x & ~TOPBIT, ib = rec.y & ~TOPBIT;
+                BodyRW a, b;
+                a.is_static = (rec.x & TOPBIT) != 0;
+                b.is_static = (rec.y & TOPBIT) != 0;
+                const float4 pa = ldcg4(&P[ia]), pb = ldcg4(&P[ib]);
+                const float4 loa = Lo[ia], hia = Hi[ia], lob = Lo[ib], hib = Hi[ib];
+                a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
+                b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
+                const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
+                const V3 bmin = b.omin + b.pos, bmax = b.omax + b.pos;
+                // physics.rs:159-164 on the CURRENT positions
+                const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y &&
+                                 amin.z < bmax.z && amax.z > bmin.z;
+                if (hit) {
+                    ++contacts;
+                    const float4 va = ldcg4(&V[ia]), vb = ldcg4(&V[ib]);
+                    a.vel = xyz(va), a.rest = va.w;
+                    b.vel = xyz(vb), b.rest = vb.w;
+                    const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
+                    if (!a.is_static) {
+                        __stcg(&P[ia], make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass));
+                        __stcg(&V[ia], make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest));
+                    }
+                    if (!b.is_static) {
+                        __stcg(&P[ib], make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass));
+                        __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
+                    }
+                    if (moved) {
+                        if (!a.is_static)
+                            track_escape(a, ia, box[2 * (size_t)ia], mverify, dmax, reach, escapees, esc_cap, ctl, maxd,
+                                         maxabs);
+                        if (!b.is_static)
+                            track_escape(b, ib, box[2 * (size_t)ib], mverify, dmax, reach, escapees, esc_cap, ctl, maxd,
+                                         maxabs);
+                    }
+                    pairs[pid].w = rec.w | TOPBIT;  // S_sweep flag; also tells k_restore which bodies were written
                 }
-                if (!b.is_static) {
-                    __stcg(&P[ib], make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass));
-                    __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
-                }
-                if (moved) {
-                    if (!a.is_static)
-                        track_escape(a, ia, box[2 * (size_t)ia], mverify, dmax, reach, escapees, esc_cap, ctl, maxd, maxabs);
-                    if (!b.is_static)
-                        track_escape(b, ib, box[2 * (size_t)ib], mverify, dmax, reach, escapees, esc_cap, ctl, maxd, maxabs);
-                }
-                pairs[pid].w = rec.w | TOPBIT;  // S_sweep flag; also tells k_restore which bodies were written
-            }
-            // pop the chains; wake pairs that reached the head everywhere
+                // pop the chains; wake pairs that reached the head everywhere
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const bool st = s ? b.is_static : a.is_static;
-                if (st) continue;
-                const uint32_t x = s ? ib : ia;
-                const uint32_t h = __ldcg(&chain_cnt[x]) + 1u;
-                __stcg(&chain_cnt[x], h);
-                const uint32_t o0 = offs[x], o1 = offs[x + 1];
-                if (o0 + h < o1) {
-                    const uint32_t q = (uint32_t)adj[o0 + h];
-                    if (atomicSub(&pending[q], 1u) == 1u) frontier_push(q, fout, &ctl->frontier_n[co]);
+                for (int s = 0; s < 2; ++s) {
+                    const bool st = s ? b.is_static : a.is_static;
+                    if (st) continue;
+                    const uint32_t x = s ? ib : ia;
+                    const uint32_t h = __ldcg(&chain_cnt[x]) + 1u;
+                    __stcg(&chain_cnt[x], h);
+                    const uint32_t o0 = offs[x], o1 = offs[x + 1];
+                    if (o0 + h < o1) {
+                        const uint32_t q = (uint32_t)adj[o0 + h];
+                        if (atomicSub(&pending[q], 1u) == 1u) stage_push(fs, q);
+                    }
                 }
             }
+            stage_flush(fs, fout, &ctl->frontier_n[co], 2u * blockDim.x);
         }
+        stage_flush(fs, fout, &ctl->frontier_n[co], FB_CAP);
         ++rounds;
         grid.sync();
     }
@@ -1095,7 +1083,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     Ctl c = *ctl;
     if (c.repair_needed) c.step_flags |= SF_MARGIN;
     if (latch == 1) {  // async stepping: failures are latched, the host looks later
-        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_GAP_OVERFLOW | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW)) {
+        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW)) {
             c.steps_inexact += 1;
             c.sticky_flags |= c.step_flags;
         }
@@ -1117,7 +1105,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
     c.grid = make_grid(c.lo, c.hi, c.ext_max, c.margin, c.cell_cfg, c.max_cells);
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
-    c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.n_gaps = 0, c.step_flags = 0;
+    c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.step_flags = 0;
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
     *ctl = c;
 }

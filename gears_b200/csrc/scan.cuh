@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(SC_THREADS) sc_reduce(const uint32_t* __restri
 }
 
 // out[i] = sum_{j<i} in[j]; the last tile also writes out[n] = grand total.
-__global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* __restrict__ in, uint32_t n,
-                                                      const uint32_t* __restrict__ tile_offsets,
-                                                      uint32_t* __restrict__ out, const uint32_t* __restrict__ gate) {
+// `in` and `out` may be the same array (every thread reads its 16 elements before it writes them).
+__global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* in, uint32_t n,
+                                                      const uint32_t* __restrict__ tile_offsets, uint32_t* out,
+                                                      const uint32_t* __restrict__ gate) {
     __shared__ uint32_t sm[33];
     if (gate && *gate == 0) return;
     const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* __restrict
     }
 }
 
-// tile_sums: ceil(n/SC_TILE) u32 of scratch.  out has n+1 entries.  in may alias nothing in out.
+// tile_sums: ceil(n/SC_TILE) u32 of scratch.  out has n+1 entries; out == in (in place) is allowed.
 // gate (device pointer, may be null): all three kernels return immediately when *gate == 0.
 static inline void exclusive_scan_u32(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums,
                                       cudaStream_t st, uint64_t* launches, const uint32_t* gate = nullptr) {
