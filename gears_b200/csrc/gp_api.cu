@@ -63,7 +63,7 @@ struct gp_world {
     float* dmax = nullptr;        // per body: largest displacement during the current sweep (escapees only, else 0)
     float* reach = nullptr;       // per body: largest displacement over the earlier sweeps of this step
     uint32_t* escapees = nullptr;  // bodies that left their margin
-    int sweep_grid = 0;
+    int sweep_grid = 0, fp_grid = 0;
     // control
     Ctl *ctl = nullptr, *ctl_snap = nullptr;
     Ctl* h_ctl = nullptr;  // pinned
@@ -189,6 +189,15 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
             break;
         }
         w->sweep_grid = std::min(occ, 4) * w->sm_count;
+        if (cudaFuncSetAttribute(k_find_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(FindPairsSmem)) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs, FP_THREADS, sizeof(FindPairsSmem)) !=
+                cudaSuccess ||
+            occ < 1) {
+            rs = GP_ERR_NO_DEVICE;
+            break;
+        }
+        w->fp_grid = occ * w->sm_count;  // persistent CTAs: every SM slot filled once
     } while (0);
     if (rs != GP_OK) {
         fail(nullptr, rs, "gp_create: CUDA setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -680,8 +689,8 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
                                                        d[1], d[2]);
         w->launches += 1;
         prof_mark(w, 3);
-        k_find_pairs<<<cdiv(nb, FP_THREADS), FP_THREADS, 0, st>>>(w->sbox, w->LB, w->pairs, w->pending,
-                                                                  w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+        k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
+            w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
         enqueue_chains_and_sweep(w, nullptr);
@@ -764,6 +773,7 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
         }
         const Ctl& c = *w->h_ctl;
         const uint32_t f = c.step_flags;
+        if (f & SF_INTERNAL) return fail(w, GP_ERR_CUDA, "a device-side bounded wait expired (flags 0x%x)", f);
         if (f & (SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW))
             return fail(w, GP_ERR_CAPACITY, "internal work list overflow (flags 0x%x)", f);
         if (f & SF_PAIR_OVERFLOW) {

@@ -117,6 +117,7 @@ constexpr uint32_t SF_MARGIN = 2u;       // the candidate set was still growing 
 constexpr uint32_t SF_MARGIN_MAX = 4u;   // (unused)
 constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
 constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
+constexpr uint32_t SF_INTERNAL = 64u;     // a bounded wait expired (TMA copy never landed): result invalid
 
 struct V3 {
     float x, y, z;
@@ -489,98 +490,193 @@ __device__ __forceinline__ bool test_candidate(const float4 alo, const float4 ah
     return true;
 }
 
-constexpr int FP_THREADS = 256;
+constexpr int FP_THREADS = 256;   // bodies per tile = threads per CTA
+constexpr int FP_RANGES = 6;      // candidate slot ranges per body: 5 cell-row runs + the big list
+constexpr int FP_BATCH = 4;       // tests per thread per batch
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_WSTAGE = 192;    // staged pair records per warp (flushed above 64: a batch adds <= 128)
+constexpr int FP_NR = FP_THREADS * FP_RANGES;
 
-// Walk the candidate ranges of body p: the rest of its own cell + the 13 forward neighbour cells (5 contiguous
-// runs of slots through LB) + the big list.  EMIT = false: count the candidate pairs.  EMIT = true: write them
-// to out[0..count).  Both passes see the same (L1/L2-resident) data, so the counts agree.
-template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_candidates(uint32_t p, uint32_t n, uint32_t n_small, bool in_grid,
-                                                    uint32_t k, const GridParams& g, float mu, const float4 alo,
-                                                    const float4 ahi, float ma, const float4* __restrict__ sbox,
-                                                    const uint32_t* __restrict__ LB, uint4* __restrict__ out,
-                                                    uint32_t out_room, uint32_t* __restrict__ pending_out,
-                                                    uint32_t* __restrict__ chain_cnt, uint32_t& nsnap) {
-    const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        uint32_t q0 = 0, q1 = 0;
-        if (r == 5) {
-            q0 = max(p + 1, n_small), q1 = n;
-        } else if (in_grid) {
-            if (r == 0) q0 = p + 1, q1 = LB[k + 2];
-            if (r == 1) q0 = LB[k + row - 1], q1 = LB[k + row + 2];
-            if (r == 2) q0 = LB[k + slab - row - 1], q1 = LB[k + slab - row + 2];
-            if (r == 3) q0 = LB[k + slab - 1], q1 = LB[k + slab + 2];
-            if (r == 4) q0 = LB[k + slab + row - 1], q1 = LB[k + slab + row + 2];
-            q1 = min(q1, n_small);
-        }
-        for (uint32_t q = q0; q < q1; ++q) {
-            const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-            uint4 rec;
-            if (!test_candidate(alo, ahi, ma, blo, bhi, mu, rec)) continue;
-            if (EMIT) {
-                if (cnt < out_room) {
-                    out[cnt] = rec;
-                    pending_out[cnt] = 0;
-                    if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
-                    if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
-                    nsnap += rec.z >> 31;
-                }
-            }
-            ++cnt;
-        }
+// ---- TMA bulk copy (cp.async.bulk, 1-D) of a tile of AABBs into shared memory, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: a kernel of this library never spins forever (returns false after ~2^26 polls)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
     }
-    return cnt;
+    return false;
 }
 
-// One thread per body; a CTA counts, reserves ONE contiguous block of pair slots (a single global atomic per
-// 256 bodies: thousands of same-address atomics per launch instead of one per warp flush), then emits.
-// Pair ids are thereby deterministic up to the CTA arrival order.
+struct FindPairsSmem {
+    float4 abox[2 * FP_THREADS];  // AABBs of the tile's bodies (lo|tag, hi|rank), staged by TMA
+    uint32_t rstart[FP_NR];       // first candidate slot of range id = r * FP_THREADS + j
+    uint32_t roff[FP_NR + 1];     // exclusive scan of the range lengths: test t belongs to range id with roff[id] <= t
+    uint4 stage[FP_WARPS][FP_WSTAGE];  // per-warp pair records waiting for the next flush
+    uint32_t scan[33];
+    uint32_t stage_cnt[FP_WARPS];
+    uint64_t bar;
+};
+
+// Persistent CTAs; a tile is 256 consecutive slots (= bodies in cell order).  Per tile:
+//  1. one thread issues a TMA bulk copy of the tile's 8 KB of AABBs into shared memory; meanwhile every thread
+//     fetches the 10 cell-table entries of its body (independent loads) and publishes its 6 candidate ranges;
+//  2. a block scan over the 1536 range lengths flattens the tile's tests into [0, T);
+//  3. the tests are dealt out evenly, FP_BATCH consecutive tests per thread per batch (a thread finds its place
+//     with one binary search per batch and then walks): every lane is busy whatever the cell populations are;
+//  4. hits are staged per warp in shared memory and leave in bursts with ONE global atomic per flush; the warps
+//     of a CTA do not synchronise while they test.
 __global__ void __launch_bounds__(FP_THREADS)
     k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
                  uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
-    __shared__ uint32_t sm_scan[33];
-    __shared__ uint32_t sm_base;
+    extern __shared__ __align__(128) unsigned char fp_smem_raw[];
+    FindPairsSmem& sm = *reinterpret_cast<FindPairsSmem*>(fp_smem_raw);
+    const uint32_t tid = threadIdx.x;
     const uint32_t n = ctl->n;
-    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA beyond the live bodies (grids are sized for capacity)
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < n;
     const GridParams g = ctl->grid;
     const float mu = ctl->margin;
     const uint32_t n_small = ctl->n_small;
-    float4 alo = make_float4(0, 0, 0, 0), ahi = alo;
-    float ma = 0.f;
-    uint32_t k = 0;
-    const bool in_grid = live && p < n_small;
-    if (live) {
-        alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
-        ma = mu * box_extent(alo, ahi);
-        // same expression as body_key() in K1: bit-identical cell
-        if (in_grid) k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
-    }
-    uint32_t nsnap = 0;
-    uint32_t cnt = 0;
-    if (live)
-        cnt = walk_candidates<false>(p, n, n_small, in_grid, k, g, mu, alo, ahi, ma, sbox, LB, nullptr, 0u, nullptr,
-                                     nullptr, nsnap);
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan_256(cnt, &total, sm_scan);
-    if (threadIdx.x == 0) sm_base = total ? atomicAdd(&ctl->n_pairs, total) : 0u;
+    const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&sm.bar, 1);
+    if (lane == 0) sm.stage_cnt[warp] = 0;
     __syncthreads();
-    if (total == 0) return;
-    const uint32_t base = sm_base;
-    if (threadIdx.x == 0 && base + total > pair_cap) atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
-    if (cnt) {
-        const uint32_t first = base + excl;
-        const uint32_t room = first < pair_cap ? pair_cap - first : 0u;
-        walk_candidates<true>(p, n, n_small, in_grid, k, g, mu, alo, ahi, ma, sbox, LB, pairs + first, room,
-                              pending + first, chain_cnt, nsnap);
+    uint32_t parity = 0, nsnap = 0;
+    const uint32_t ntiles = (n + FP_THREADS - 1) / FP_THREADS;
+    uint4* const wstage = sm.stage[warp];
+    uint32_t* const wcnt = &sm.stage_cnt[warp];
+
+    auto flush = [&]() {  // warp-synchronous
+        __syncwarp();
+        const uint32_t c = *wcnt;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->n_pairs, c);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane == 0 && base + c > pair_cap) atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+        for (uint32_t i = lane; i < c; i += 32) {
+            const uint32_t slot = base + i;
+            if (slot < pair_cap) {
+                const uint4 rec = wstage[i];
+                pairs[slot] = rec;
+                pending[slot] = 0;
+                if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
+                if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
+                nsnap += rec.z >> 31;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *wcnt = 0;
+        __syncwarp();
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t p0 = tile * FP_THREADS;
+        const uint32_t valid = min((uint32_t)FP_THREADS, n - p0);
+        if (tid == 0) tma_load_1d(sm.abox, sbox + 2 * (size_t)p0, valid * 32u, &sm.bar);
+        const uint32_t p = p0 + tid;
+        const bool live = tid < valid;
+        // the cell of body p: the AABB is needed for the key, read it straight from global (the TMA copy of the
+        // same lines is in flight; both are served by one L2 fill)
+        uint32_t q0[FP_RANGES], len[FP_RANGES];
+#pragma unroll
+        for (int r = 0; r < FP_RANGES; ++r) q0[r] = 0, len[r] = 0;
+        if (live) {
+            if (p < n_small) {
+                const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+                // same expression as body_key() in K1: bit-identical cell
+                const uint32_t k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
+                // forward half of the 27-neighbourhood = 5 contiguous runs of slots
+                const uint32_t e0 = LB[k + 2];
+                const uint32_t b1 = LB[k + row - 1], e1 = LB[k + row + 2];
+                const uint32_t b2 = LB[k + slab - row - 1], e2 = LB[k + slab - row + 2];
+                const uint32_t b3 = LB[k + slab - 1], e3 = LB[k + slab + 2];
+                const uint32_t b4 = LB[k + slab + row - 1], e4 = LB[k + slab + row + 2];
+                q0[0] = p + 1, len[0] = e0 > p + 1 ? e0 - (p + 1) : 0u;
+                q0[1] = b1, len[1] = e1 - b1;
+                q0[2] = b2, len[2] = e2 - b2;
+                q0[3] = b3, len[3] = e3 - b3;
+                q0[4] = b4, len[4] = e4 - b4;
+            }
+            const uint32_t qb = max(p + 1, n_small);  // big list: every body tests the big bodies after it
+            q0[5] = qb, len[5] = n > qb ? n - qb : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < FP_RANGES; ++r) {
+            sm.rstart[r * FP_THREADS + tid] = q0[r];
+            sm.roff[r * FP_THREADS + tid] = len[r];
+        }
+        __syncthreads();
+        // exclusive scan of the 1536 lengths: thread t owns ids [6t, 6t+6)
+        uint32_t l6[FP_RANGES], s6 = 0;
+#pragma unroll
+        for (int i = 0; i < FP_RANGES; ++i) l6[i] = sm.roff[FP_RANGES * tid + i], s6 += l6[i];
+        uint32_t T;
+        uint32_t run = block_exclusive_scan_256(s6, &T, sm.scan);  // (contains the barriers that order the rewrite)
+#pragma unroll
+        for (int i = 0; i < FP_RANGES; ++i) {
+            sm.roff[FP_RANGES * tid + i] = run;
+            run += l6[i];
+        }
+        if (tid == FP_THREADS - 1) sm.roff[FP_NR] = run;
+        const bool tma_ok = mbar_wait(&sm.bar, parity);
+        parity ^= 1u;
+        if (!tma_ok && tid == 0) atomicOr(&ctl->step_flags, SF_INTERNAL);
+        __syncthreads();
+
+        for (uint32_t tb = warp * 32 * FP_BATCH; tb < T; tb += FP_THREADS * FP_BATCH) {
+            const uint32_t t0 = tb + lane * FP_BATCH;
+            if (t0 < T) {
+                // range that holds test t0: largest id with roff[id] <= t0
+                uint32_t lo_i = 0, hi_i = FP_NR;
+                while (hi_i - lo_i > 1) {
+                    const uint32_t mid = (lo_i + hi_i) >> 1;
+                    if (sm.roff[mid] <= t0) lo_i = mid; else hi_i = mid;
+                }
+                uint32_t id = lo_i;
+                uint32_t end_t = sm.roff[id + 1];
+                uint32_t q = sm.rstart[id] + (t0 - sm.roff[id]);
+                uint32_t j = id & (FP_THREADS - 1);
+                float4 alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
+                float ma = mu * box_extent(alo, ahi);
+                const uint32_t t1 = min(t0 + FP_BATCH, T);
+                for (uint32_t t = t0; t < t1; ++t, ++q) {
+                    if (t >= end_t) {
+                        do { ++id; end_t = sm.roff[id + 1]; } while (t >= end_t);  // skip empty ranges
+                        q = sm.rstart[id];
+                        j = id & (FP_THREADS - 1);
+                        alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
+                        ma = mu * box_extent(alo, ahi);
+                    }
+                    const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
+                    uint4 rec;
+                    if (test_candidate(alo, ahi, ma, blo, bhi, mu, rec)) wstage[atomicAdd(wcnt, 1u)] = rec;
+                }
+            }
+            __syncwarp();
+            if (*wcnt > 64u) flush();  // the next batch adds at most 32 * FP_BATCH = 128 records
+        }
+        __syncthreads();  // rstart/roff/abox are rewritten by the next tile
     }
+    if (*wcnt) flush();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsnap += __shfl_xor_sync(0xffffffffu, nsnap, o);
-    if ((threadIdx.x & 31) == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
+    if ((tid & 31) == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1083,7 +1179,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     Ctl c = *ctl;
     if (c.repair_needed) c.step_flags |= SF_MARGIN;
     if (latch == 1) {  // async stepping: failures are latched, the host looks later
-        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW)) {
+        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW | SF_INTERNAL)) {
             c.steps_inexact += 1;
             c.sticky_flags |= c.step_flags;
         }
