@@ -36,8 +36,8 @@ struct gp_world {
     bool uploaded = false;
 
     // body state: two sets of five float4 arrays; every step gathers set `cur` into set `cur^1` in cell order
-    float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *A[2] = {nullptr, nullptr};
-    float4 *Lo[2] = {nullptr, nullptr}, *Hi[2] = {nullptr, nullptr};
+    float4 *B[2] = {nullptr, nullptr};  // 64 B records: P, V, Lo, Hi (see struct Bodies)
+    float4 *A[2] = {nullptr, nullptr};  // acc | flags
     int cur = 0;
     float* ext = nullptr;
     uint32_t* slot_of = nullptr;  // body id -> current slot (rebuilt on demand: slots change every step)
@@ -56,7 +56,6 @@ struct gp_world {
     uint32_t *chain_cnt = nullptr, *offs = nullptr, *tile_sums = nullptr;
     uint4* pairs = nullptr;
     unsigned long long* adj = nullptr;
-    uint32_t* pending = nullptr;
     uint32_t* frontier[2] = {nullptr, nullptr};
     uint32_t* heavy = nullptr;
     uint32_t heavy_cap = 0;
@@ -121,10 +120,9 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 static void free_all(gp_world* w) {
-    void* ptrs[] = {w->P[0],   w->P[1],  w->V[0],       w->V[1],       w->A[0],  w->A[1],      w->Lo[0],  w->Lo[1],
-                    w->Hi[0],  w->Hi[1], w->ext,        w->slot_of,
+    void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
-                    w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,       w->pending,
+                    w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
                     w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -231,11 +229,8 @@ static gp_status ensure_stage(gp_world* w, size_t bytes) {
 
 static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     for (int i = 0; i < 2; ++i) {
-        CK(dmalloc(&w->P[i], cap));
-        CK(dmalloc(&w->V[i], cap));
+        CK(dmalloc(&w->B[i], 4 * (size_t)cap));
         CK(dmalloc(&w->A[i], cap));
-        CK(dmalloc(&w->Lo[i], cap));
-        CK(dmalloc(&w->Hi[i], cap));
     }
     CK(dmalloc(&w->ext, cap));
     CK(dmalloc(&w->slot_of, cap));
@@ -257,9 +252,8 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
 
 static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
     if (pair_cap > 0x7fff0000ull) pair_cap = 0x7fff0000ull;
-    CK(dmalloc(&w->pairs, pair_cap));
+    CK(dmalloc(&w->pairs, 2 * pair_cap));  // 32 B records
     CK(dmalloc(&w->adj, 2 * pair_cap));
-    CK(dmalloc(&w->pending, pair_cap));
     CK(dmalloc(&w->frontier[0], pair_cap));
     CK(dmalloc(&w->frontier[1], pair_cap));
     w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);
@@ -303,7 +297,7 @@ static gp_status setup_grid(gp_world* w) {
     uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, w->st));
     if (n) {
-        k_classify<<<cdiv(n, 256), 256, 0, w->st>>>(n, thr, w->P[w->cur], w->Lo[w->cur], w->Hi[w->cur], w->A[w->cur], d_bounds);
+        k_classify<<<cdiv(n, 256), 256, 0, w->st>>>(n, thr, Bodies{w->B[w->cur]}, w->A[w->cur], d_bounds);
         w->launches++;
     }
     uint32_t hb[6];
@@ -431,8 +425,8 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
             scale3 ? (const float*)(sg + o_scale) : nullptr, (const float*)(sg + o_vel),
             acc3 ? (const float*)(sg + o_acc) : nullptr, (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
             (const float*)(sg + o_mass), (const float*)(sg + o_rest), (const uint8_t*)(sg + o_stat),
-            entity ? (const uint32_t*)(sg + o_ent) : nullptr, rank ? (const uint32_t*)(sg + o_rank) : nullptr, w->P[0],
-            w->V[0], w->A[0], w->Lo[0], w->Hi[0], w->ext, 0, nullptr);
+            entity ? (const uint32_t*)(sg + o_ent) : nullptr, rank ? (const uint32_t*)(sg + o_rank) : nullptr,
+            Bodies{w->B[0]}, w->A[0], w->ext, 0, nullptr);
         w->launches++;
         CK(cudaGetLastError());
     }
@@ -450,7 +444,7 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
 // body id -> slot map of the current set (slots change with every step)
 static gp_status ensure_slot_map(gp_world* w) {
     if (w->slot_valid || w->n == 0) return GP_OK;
-    k_slot_map<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->Lo[w->cur], w->slot_of);
+    k_slot_map<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, Bodies{w->B[w->cur]}, w->slot_of);
     w->launches++;
     CK(cudaGetLastError());
     w->slot_valid = true;
@@ -479,8 +473,8 @@ static gp_status stage_state(gp_world* w, uint32_t k, const uint32_t* idx, const
     k_set_state<<<cdiv(k, 256), 256, 0, w->st>>>(k, idx ? (const uint32_t*)(sg + 3 * a3) : nullptr, w->slot_of,
                                                  pos3 ? (const float*)sg : nullptr,
                                                  vel3 ? (const float*)(sg + a3) : nullptr,
-                                                 acc3 ? (const float*)(sg + 2 * a3) : nullptr, w->P[w->cur],
-                                                 w->V[w->cur], w->A[w->cur], w->Lo[w->cur]);
+                                                 acc3 ? (const float*)(sg + 2 * a3) : nullptr,
+                                                 Bodies{w->B[w->cur]}, w->A[w->cur]);
     w->launches++;
     CK(cudaGetLastError());
     return GP_OK;
@@ -544,13 +538,13 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
                                             scale3 ? (const float*)(sg + o_scale) : nullptr, nullptr, nullptr,
                                             (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
                                             (const float*)(sg + o_mass), (const float*)(sg + o_rest),
-                                            (const uint8_t*)(sg + o_stat), nullptr, nullptr, w->P[w->cur], w->V[w->cur],
-                                            w->A[w->cur], w->Lo[w->cur], w->Hi[w->cur], nullptr, 1, w->slot_of);
+                                            (const uint8_t*)(sg + o_stat), nullptr, nullptr, Bodies{w->B[w->cur]},
+                                            w->A[w->cur], nullptr, 1, w->slot_of);
     w->launches++;
     CK(cudaGetLastError());
     // a body that outgrew the cell joins the big list; the grid itself is kept
-    k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->thr, w->P[w->cur], w->Lo[w->cur], w->Hi[w->cur],
-                                                   w->A[w->cur], w->d_small + EXT_BUCKETS);
+    k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->thr, Bodies{w->B[w->cur]}, w->A[w->cur],
+                                                   w->d_small + EXT_BUCKETS);
     w->launches++;
     CK(cudaStreamSynchronize(w->st));
     return GP_OK;
@@ -615,26 +609,21 @@ static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
     exclusive_scan_u32(w->chain_cnt, nb, w->offs, w->tile_sums, st, &w->launches, gate);
     k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
                                                    w->ctl, gate);
-    k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
-    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pending, w->heavy, w->heavy_cap, w->ctl, gate);
+    k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, gate);
+    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, gate);
     w->launches += 3;
     if (!gate) prof_mark(w, 5);
-    float4 *Pn = w->P[o], *Vn = w->V[o];
-    const float4 *Lo = w->Lo[o], *Hi = w->Hi[o], *box = w->sbox;
+    Bodies Bn{w->B[o]};
+    const float4* box = w->sbox;
     uint4* pairs = w->pairs;
     uint32_t pair_cap = (uint32_t)w->pair_cap;
-    const uint32_t* offs = w->offs;
-    uint32_t* chain_cnt = w->chain_cnt;
-    const unsigned long long* adj = w->adj;
-    uint32_t* pending = w->pending;
     uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
     Ctl* ctl = w->ctl;
     float* dmax = w->dmax;
     const float* reach = w->reach;
     uint32_t* esc = w->escapees;
     uint32_t esc_cap = w->cap;
-    void* args[] = {&Pn, &Vn, &Lo, &Hi, &box, &pairs, &pair_cap, &offs, &chain_cnt, &adj, &pending,
-                    &f0, &f1, &ctl, &dmax, &reach, &esc, &esc_cap, &gate};
+    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &reach, &esc, &esc_cap, &gate};
     CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
     w->launches++;
     return GP_OK;
@@ -645,8 +634,8 @@ static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     cudaStream_t st = w->st;
     const int c = w->cur, o = c ^ 1;
     const uint32_t* gate = &w->ctl->repair_needed;
-    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->perm, w->P[c], w->V[c],
-                                               w->A[c], w->P[o], w->V[o], w->chain_cnt, w->pending, w->dmax, w->reach,
+    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->perm, Bodies{w->B[c]},
+                                               w->A[c], Bodies{w->B[o]}, w->chain_cnt, w->dmax, w->reach,
                                                w->escapees, w->cap, w->ctl, dt, d[0], d[1], d[2]);
     k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
     k_repair_reset<<<1, 1, 0, st>>>(w->ctl);
@@ -655,7 +644,7 @@ static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     if (s != GP_OK) return s;
     k_repair_done<<<1, 1, 0, st>>>(w->ctl);
     k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
-                                               w->pairs, w->pending, (uint32_t)w->pair_cap, w->ctl);
+                                               w->pairs, (uint32_t)w->pair_cap, w->ctl);
     w->launches += 2;
     return GP_OK;
 }
@@ -677,26 +666,26 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
         // K1 + K2: one-pass radix (bucket) sort by cell key: histogram with the keys, scan, scatter
         const uint32_t ncnt = w->max_cells + 2;  // counters: every cell of the finest grid + big list + dead
         CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
-        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c], w->key, w->lrank, w->LB,
+        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB,
                                               w->ctl, dt, d[0], d[1], d[2]);
         w->launches++;
         prof_mark(w, 1);
         exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
         prof_mark(w, 2);
-        k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, w->P[c], w->V[c], w->A[c], w->Lo[c], w->Hi[c],
-                                                       w->P[o], w->V[o], w->A[o], w->Lo[o], w->Hi[o], w->sbox,
+        k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
+                                                       w->A[o], w->sbox,
                                                        w->chain_cnt, w->perm, w->dmax, w->reach, w->LB, w->ctl, dt, d[0],
                                                        d[1], d[2]);
         w->launches += 1;
         prof_mark(w, 3);
         k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
-            w->sbox, w->LB, w->pairs, w->pending, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+            w->sbox, w->LB, w->pairs, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
         enqueue_chains_and_sweep(w, nullptr);
         // speculative broad phase: look for pairs the margin missed, repair, look again
         k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
-                                                   w->pairs, w->pending, (uint32_t)w->pair_cap, w->ctl);
+                                                   w->pairs, (uint32_t)w->pair_cap, w->ctl);
         w->launches++;
         for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
         k_clear_escapees<<<w->sm_count, 256, 0, st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, latch);
@@ -880,7 +869,7 @@ extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
     if (s != GP_OK) return s;
     float* dp = (float*)w->stage;
     float* dv = (float*)(w->stage + a3);
-    k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->P[w->cur], w->V[w->cur], w->Lo[w->cur], pos3 ? dp : nullptr,
+    k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, pos3 ? dp : nullptr,
                                               vel3 ? dv : nullptr, nullptr, 1);
     w->launches++;
     if (pos3) CK(cudaMemcpyAsync(pos3, dp, b3, cudaMemcpyDeviceToHost, w->st));
@@ -919,7 +908,7 @@ extern "C" gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint
         *n_out = m;
         if (m == 0) break;
         const int r = rs_sort<unsigned long long>(k0, v0, k1, v1, m, 63, false, hist, w->sm_count, w->st, &w->launches);
-        k_gather_pairs<<<cdiv(m, 256), 256, 0, w->st>>>(w->pairs, r ? v1 : v0, m, w->Lo[w->cur], outp);
+        k_gather_pairs<<<cdiv(m, 256), 256, 0, w->st>>>(w->pairs, r ? v1 : v0, m, Bodies{w->B[w->cur]}, outp);
         w->launches++;
         const uint64_t ncopy = std::min<uint64_t>(m, cap);
         if (pairs2 && ncopy) cudaMemcpyAsync(pairs2, outp, ncopy * sizeof(uint2), cudaMemcpyDeviceToHost, w->st);

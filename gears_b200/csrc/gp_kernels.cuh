@@ -35,6 +35,15 @@ constexpr uint32_t F_GHOST = 4u;   // multi-GPU halo copy: resolved here but own
 constexpr uint32_t F_INTEGRATED = 8u;  // multi-GPU: record received this step, already integrated by its sender
 
 constexpr uint32_t TOPBIT = 0x80000000u;
+constexpr uint32_t NONE = 0xffffffffu;
+
+// Pair record, 32 B = one sector: pairs[2*pid] = (a | static<<31, b | static<<31, rank_a | snapshot<<31,
+// rank_b | hit<<31); pairs[2*pid+1] = (next pair in a's chain, next pair in b's chain, pending, unused).
+// The sweep follows the next links, so it never touches the per-body chain arrays.
+__device__ __forceinline__ uint32_t* pair_link(uint4* pairs, uint32_t pid) {
+    return reinterpret_cast<uint32_t*>(pairs + 2 * (size_t)pid + 1);
+}
+__device__ __forceinline__ uint4 link_init() { return make_uint4(NONE, NONE, 0u, 0u); }
 
 // physics.rs:7-20
 constexpr float POSITION_CORRECTION_FACTOR = 0.4f;
@@ -119,6 +128,17 @@ constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
 constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
 constexpr uint32_t SF_INTERNAL = 64u;     // a bounded wait expired (TMA copy never landed): result invalid
 
+// Body record (array of structures, 64 B = one DRAM burst): P = pos|mass, V = vel|restitution, Lo = min offset|id,
+// Hi = max offset|rank.  The contact sweep touches bodies at random; with the four float4 in one 64 B line a body
+// costs one burst instead of four.  Streaming kernels read the 4 x 16 B of a record with consecutive LDG.128.
+struct Bodies {
+    float4* b;
+    __device__ __forceinline__ float4& P(uint32_t i) const { return b[4 * (size_t)i]; }
+    __device__ __forceinline__ float4& V(uint32_t i) const { return b[4 * (size_t)i + 1]; }
+    __device__ __forceinline__ float4& Lo(uint32_t i) const { return b[4 * (size_t)i + 2]; }
+    __device__ __forceinline__ float4& Hi(uint32_t i) const { return b[4 * (size_t)i + 3]; }
+};
+
 struct V3 {
     float x, y, z;
 };
@@ -174,8 +194,8 @@ __global__ void k_pack(uint32_t k, const uint32_t* __restrict__ idx, const float
                        const float* __restrict__ rot4, const float* __restrict__ scale3, const float* __restrict__ vel3,
                        const float* __restrict__ acc3, const float* __restrict__ bmin3, const float* __restrict__ bmax3,
                        const float* __restrict__ mass, const float* __restrict__ rest, const uint8_t* __restrict__ stat,
-                       const uint32_t* __restrict__ entity, const uint32_t* __restrict__ rank, float4* P, float4* V,
-                       float4* A, float4* Lo, float4* Hi, float* ext, int shape_only,
+                       const uint32_t* __restrict__ entity, const uint32_t* __restrict__ rank, Bodies B,
+                       float4* A, float* ext, int shape_only,
                        const uint32_t* __restrict__ slot_of) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k) return;
@@ -189,21 +209,21 @@ __global__ void k_pack(uint32_t k, const uint32_t* __restrict__ idx, const float
     corner_offsets(bmin, bmax, q, sc, omin, omax);
     const uint32_t fl_static = stat[t] ? F_STATIC : 0u;
     if (shape_only) {
-        float4 p = P[i], v = V[i], a = A[i], lo = Lo[i], hi = Hi[i];
+        float4 p = B.P(i), v = B.V(i), a = A[i], lo = B.Lo(i), hi = B.Hi(i);
         p.w = mass[t];
         v.w = rest[t];
         a.w = __uint_as_float((__float_as_uint(a.w) & ~F_STATIC) | fl_static);
         lo = make_float4(omin.x, omin.y, omin.z, lo.w);
         hi = make_float4(omax.x, omax.y, omax.z, hi.w);
-        P[i] = p, V[i] = v, A[i] = a, Lo[i] = lo, Hi[i] = hi;
+        B.P(i) = p, B.V(i) = v, A[i] = a, B.Lo(i) = lo, B.Hi(i) = hi;
     } else {
-        P[i] = make_float4(pos3[3 * t], pos3[3 * t + 1], pos3[3 * t + 2], mass[t]);
-        V[i] = make_float4(vel3[3 * t], vel3[3 * t + 1], vel3[3 * t + 2], rest[t]);
+        B.P(i) = make_float4(pos3[3 * t], pos3[3 * t + 1], pos3[3 * t + 2], mass[t]);
+        B.V(i) = make_float4(vel3[3 * t], vel3[3 * t + 1], vel3[3 * t + 2], rest[t]);
         A[i] = make_float4(acc3 ? acc3[3 * t] : 0.f, acc3 ? acc3[3 * t + 1] : 0.f, acc3 ? acc3[3 * t + 2] : 0.f,
                            __uint_as_float(fl_static));
-        Lo[i] = make_float4(omin.x, omin.y, omin.z, __uint_as_float(i));  // .w = body id (caller index)
+        B.Lo(i) = make_float4(omin.x, omin.y, omin.z, __uint_as_float(i));  // .w = body id (caller index)
         (void)entity;
-        Hi[i] = make_float4(omax.x, omax.y, omax.z, __uint_as_float(rank ? rank[t] : i));
+        B.Hi(i) = make_float4(omax.x, omax.y, omax.z, __uint_as_float(rank ? rank[t] : i));
     }
     if (ext) ext[i] = fmaxf(omax.x - omin.x, fmaxf(omax.y - omin.y, omax.z - omin.z));
 }
@@ -248,21 +268,20 @@ __host__ __device__ inline float ord2f(uint32_t u) {
 }
 
 // classify by extent threshold and reduce the bounds of grid-class body centres
-__global__ void k_classify(uint32_t n, float thr, const float4* __restrict__ P,
-                           const float4* __restrict__ Lo, const float4* __restrict__ Hi, float4* A,
+__global__ void k_classify(uint32_t n, float thr, const Bodies B, float4* A,
                            uint32_t* __restrict__ bounds /*6: min xyz, max xyz (ordered uints)*/) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     if (i < n) {
         float4 a = A[i];
         uint32_t f = __float_as_uint(a.w) & ~F_BIG;
-        const float4 l4 = Lo[i], h4 = Hi[i];
+        const float4 l4 = B.Lo(i), h4 = B.Hi(i);
         const bool big = !(fmaxf(h4.x - l4.x, fmaxf(h4.y - l4.y, h4.z - l4.z)) <= thr);
         if (big) f |= F_BIG;
         a.w = __uint_as_float(f);
         A[i] = a;
         if (!big) {
-            const float4 p = P[i], l = Lo[i], h = Hi[i];
+            const float4 p = B.P(i), l = l4, h = h4;
             const float c[3] = {((l.x + p.x) + (h.x + p.x)) * 0.5f, ((l.y + p.y) + (h.y + p.y)) * 0.5f,
                                 ((l.z + p.z) + (h.z + p.z)) * 0.5f};
 #pragma unroll
@@ -289,34 +308,33 @@ __global__ void k_classify(uint32_t n, float thr, const float4* __restrict__ P,
 
 // The body arrays are physically re-sorted into cell order by every step (K3), so the slot of a body changes.
 // Lo[slot].w keeps the body id (the caller's index at upload; the global entity id in multi-GPU mode).
-__global__ void k_slot_map(uint32_t n, const float4* __restrict__ Lo, uint32_t* __restrict__ slot_of) {
+__global__ void k_slot_map(uint32_t n, const Bodies B, uint32_t* __restrict__ slot_of) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slot_of[__float_as_uint(Lo[i].w)] = i;
+    if (i < n) slot_of[__float_as_uint(B.Lo(i).w)] = i;
 }
 
 // bulk refresh of mutable state from host-layout arrays (gp_set_state: idx == nullptr, every slot gathers the
 // row of its body id;  gp_update_dirty: row t belongs to body idx[t])
 __global__ void k_set_state(uint32_t k, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ slot_of,
                             const float* __restrict__ pos3, const float* __restrict__ vel3,
-                            const float* __restrict__ acc3, float4* P, float4* V, float4* A,
-                            const float4* __restrict__ Lo) {
+                            const float* __restrict__ acc3, Bodies B, float4* A) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k) return;
     uint32_t i, r;
     if (idx) {
         i = slot_of[idx[t]], r = t;
     } else {
-        i = t, r = __float_as_uint(Lo[t].w);
+        i = t, r = __float_as_uint(B.Lo(t).w);
     }
     if (pos3) {
-        float4 p = P[i];
+        float4 p = B.P(i);
         p.x = pos3[3 * (size_t)r], p.y = pos3[3 * (size_t)r + 1], p.z = pos3[3 * (size_t)r + 2];
-        P[i] = p;
+        B.P(i) = p;
     }
     if (vel3) {
-        float4 v = V[i];
+        float4 v = B.V(i);
         v.x = vel3[3 * (size_t)r], v.y = vel3[3 * (size_t)r + 1], v.z = vel3[3 * (size_t)r + 2];
-        V[i] = v;
+        B.V(i) = v;
     }
     if (acc3) {
         float4 a = A[i];
@@ -326,18 +344,17 @@ __global__ void k_set_state(uint32_t k, const uint32_t* __restrict__ idx, const 
 }
 
 // device -> host layout.  by_id: row = body id (gp_download); else row = slot (gp_download_owned, + ids)
-__global__ void k_unpack(uint32_t n, const float4* __restrict__ P, const float4* __restrict__ V,
-                         const float4* __restrict__ Lo, float* pos3, float* vel3, uint32_t* ids, int by_id) {
+__global__ void k_unpack(uint32_t n, const Bodies B, float* pos3, float* vel3, uint32_t* ids, int by_id) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t id = __float_as_uint(Lo[i].w);
+    const uint32_t id = __float_as_uint(B.Lo(i).w);
     const size_t r = by_id ? id : i;
     if (pos3) {
-        const float4 p = P[i];
+        const float4 p = B.P(i);
         pos3[3 * r] = p.x, pos3[3 * r + 1] = p.y, pos3[3 * r + 2] = p.z;
     }
     if (vel3) {
-        const float4 v = V[i];
+        const float4 v = B.V(i);
         vel3[3 * r] = v.x, vel3[3 * r + 1] = v.y, vel3[3 * r + 2] = v.z;
     }
     if (ids) ids[i] = id;
@@ -391,15 +408,14 @@ __device__ __forceinline__ uint32_t body_key(const GridParams& g, const float4 p
 }
 
 __global__ void __launch_bounds__(256)
-    k_keys(const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A,
-           const float4* __restrict__ Lo, const float4* __restrict__ Hi, uint32_t* __restrict__ key,
+    k_keys(const Bodies B0, const float4* __restrict__ A, uint32_t* __restrict__ key,
            uint32_t* __restrict__ lrank, uint32_t* __restrict__ cell_cnt, const Ctl* __restrict__ ctl, float dt,
            float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ctl->n_in) return;
     const GridParams g = ctl->grid;
-    float4 p = P0[i], v = V0[i];
-    const float4 a = A[i], lo = Lo[i], hi = Hi[i];
+    float4 p = B0.P(i), v = B0.V(i);
+    const float4 a = A[i], lo = B0.Lo(i), hi = B0.Hi(i);
     const uint32_t flags = __float_as_uint(a.w);
     if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
     const uint32_t k = body_key(g, p, lo, hi, flags);
@@ -419,9 +435,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_scatter_cells(const uint32_t* __restrict__ key, const uint32_t* __restrict__ lrank,
-                    const float4* __restrict__ P0, const float4* __restrict__ V0, const float4* __restrict__ A0,
-                    const float4* __restrict__ Lo0, const float4* __restrict__ Hi0, float4* __restrict__ P1,
-                    float4* __restrict__ V1, float4* __restrict__ A1, float4* __restrict__ Lo1, float4* __restrict__ Hi1,
+                    const Bodies B0, const float4* __restrict__ A0, const Bodies B1, float4* __restrict__ A1,
                     float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ perm,
                     float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ LB, Ctl* ctl,
                     float dt, float d16, float d18, float d35) {
@@ -435,8 +449,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t k = key[i];
     if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here
     const uint32_t s = LB[k] + lrank[i];
-    float4 p = P0[i], v = V0[i], a = A0[i];
-    const float4 lo = Lo0[i], hi = Hi0[i];
+    float4 p = B0.P(i), v = B0.V(i), a = A0[i];
+    const float4 lo = B0.Lo(i), hi = B0.Hi(i);
     uint32_t flags = __float_as_uint(a.w);
     if (flags & F_INTEGRATED) {
         flags &= ~F_INTEGRATED;
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(256)
     } else {
         integrate_body(p, v, a, dt, d16, d18, d35);
     }
-    P1[s] = p, V1[s] = v, A1[s] = a, Lo1[s] = lo, Hi1[s] = hi;
+    B1.P(s) = p, B1.V(s) = v, A1[s] = a, B1.Lo(s) = lo, B1.Hi(s) = hi;
     // world AABB = offsets + position (physics.rs:117: corner + pos; min/max commute with the rounding)
     const uint32_t tag = s | ((flags & F_STATIC) ? TOPBIT : 0u);
     sbox[2 * (size_t)s] = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, __uint_as_float(tag));
@@ -544,7 +558,7 @@ struct FindPairsSmem {
 //     of a CTA do not synchronise while they test.
 __global__ void __launch_bounds__(FP_THREADS)
     k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
-                 uint32_t* __restrict__ pending, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+                 uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
     extern __shared__ __align__(128) unsigned char fp_smem_raw[];
     FindPairsSmem& sm = *reinterpret_cast<FindPairsSmem*>(fp_smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -573,8 +587,8 @@ __global__ void __launch_bounds__(FP_THREADS)
             const uint32_t slot = base + i;
             if (slot < pair_cap) {
                 const uint4 rec = wstage[i];
-                pairs[slot] = rec;
-                pending[slot] = 0;
+                pairs[2 * (size_t)slot] = rec;
+                pairs[2 * (size_t)slot + 1] = link_init();
                 if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
                 if (!(rec.y & TOPBIT)) atomicAdd(&chain_cnt[rec.y & ~TOPBIT], 1u);
                 nsnap += rec.z >> 31;
@@ -681,9 +695,10 @@ __global__ void __launch_bounds__(FP_THREADS)
 
 // ---------------------------------------------------------------------------------------------
 // K5: contact chains.  offs = exclusive scan of chain_cnt (host launches scan.cuh).  k_fill_chains
-// drops, for every pair and dynamic endpoint x, the entry (partner rank << 32 | pair id) into x's
+// drops, for every pair and dynamic endpoint x, the entry (partner rank << 32 | side << 31 | pair id) into x's
 // segment; k_sort_chains orders each segment by partner rank = the reference's visiting order for x,
-// and counts, per pair, on how many chains it is not yet at the head (pending).
+// links every pair to its successor on x's side (pair record: next_a / next_b) and counts, per pair, on how
+// many chains it is not yet at the head (pending).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_fill_chains(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
@@ -692,26 +707,36 @@ __global__ void __launch_bounds__(256)
     if (gate && *gate == 0) return;
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < np; pid += gridDim.x * blockDim.x) {
-        const uint4 r = pairs[pid];
+        const uint4 r = pairs[2 * (size_t)pid];
         const uint32_t ra = r.z & ~TOPBIT, rb = r.w & ~TOPBIT;
         if (!(r.x & TOPBIT)) {
             const uint32_t a = r.x;
             const uint32_t s = offs[a] + atomicSub(&chain_cnt[a], 1u) - 1u;
-            adj[s] = ((unsigned long long)rb << 32) | pid;
+            adj[s] = ((unsigned long long)rb << 32) | pid;  // side 0: this body is the pair's a
         }
         if (!(r.y & TOPBIT)) {
             const uint32_t b = r.y;
             const uint32_t s = offs[b] + atomicSub(&chain_cnt[b], 1u) - 1u;
-            adj[s] = ((unsigned long long)ra << 32) | pid;
+            adj[s] = ((unsigned long long)ra << 32) | TOPBIT | pid;  // side 1
         }
     }
 }
 
 constexpr uint32_t CHAIN_INLINE = 48;  // longer chains go to the block-wide sorter
 
+// entries [first, d) of a sorted chain, stride apart: entry i-1 gets entry i as its successor on this body's side
+__device__ __forceinline__ void link_chain(const unsigned long long* __restrict__ seg, uint32_t first, uint32_t d,
+                                           uint32_t stride, uint4* __restrict__ pairs) {
+    for (uint32_t i = first + 1; i < d; i += stride) {
+        const uint32_t prev = (uint32_t)seg[i - 1], cur = (uint32_t)seg[i] & ~TOPBIT;
+        pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
+        atomicAdd(&pair_link(pairs, cur)[2], 1u);
+    }
+}
+
 __global__ void __launch_bounds__(256)
     k_sort_chains(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj,
-                  uint32_t* __restrict__ pending, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl,
+                  uint4* __restrict__ pairs, uint32_t* __restrict__ heavy, uint32_t heavy_cap, Ctl* ctl,
                   const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -737,12 +762,12 @@ __global__ void __launch_bounds__(256)
         }
         adj[j] = v;
     }
-    for (uint32_t i = b + 1; i < e; ++i) atomicAdd(&pending[(uint32_t)adj[i]], 1u);
+    link_chain(adj + b, 0u, d, 1u, pairs);
 }
 
 // one CTA per heavy body: bitonic sort of its segment in global memory (any length)
 __global__ void __launch_bounds__(256)
-    k_sort_heavy(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending,
+    k_sort_heavy(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj, uint4* __restrict__ pairs,
                  const uint32_t* __restrict__ heavy, uint32_t heavy_cap, const Ctl* ctl,
                  const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;
@@ -771,7 +796,7 @@ __global__ void __launch_bounds__(256)
                 __syncthreads();
             }
         }
-        for (uint32_t i = threadIdx.x + 1; i < d; i += blockDim.x) atomicAdd(&pending[(uint32_t)adj[b + i]], 1u);
+        link_chain(adj + b, threadIdx.x, d, blockDim.x, pairs);
         __syncthreads();
     }
 }
@@ -896,11 +921,8 @@ __device__ __forceinline__ void track_escape(const BodyRW& x, uint32_t ix, float
 }
 
 __global__ void __launch_bounds__(256)
-    k_sweep(float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Lo, const float4* __restrict__ Hi,
-            const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
-            const uint32_t* __restrict__ offs, uint32_t* __restrict__ chain_cnt,
-            const unsigned long long* __restrict__ adj, uint32_t* __restrict__ pending, uint32_t* __restrict__ frontier0,
-            uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax, const float* __restrict__ reach,
+    k_sweep(const Bodies B, const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
+            uint32_t* __restrict__ frontier0, uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax, const float* __restrict__ reach,
             uint32_t* __restrict__ escapees, uint32_t esc_cap, const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;  // uniform across the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
@@ -912,7 +934,7 @@ __global__ void __launch_bounds__(256)
     // round 0 frontier: pairs at the head of all their chains
     for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gsz) {
         const uint32_t pid = p0 + threadIdx.x;
-        if (pid < np && __ldcg(&pending[pid]) == 0) stage_push(fs, pid);
+        if (pid < np && __ldcg(&pair_link(pairs, pid)[2]) == 0) stage_push(fs, pid);
         stage_flush(fs, frontier0, &ctl->frontier_n[0], blockDim.x);
     }
     stage_flush(fs, frontier0, &ctl->frontier_n[0], FB_CAP);
@@ -933,13 +955,14 @@ __global__ void __launch_bounds__(256)
             const uint32_t f = f0 + threadIdx.x;
             if (f < nf) {
                 const uint32_t pid = __ldcg(&fin[f]);
-                uint4 rec = pairs[pid];
+                const uint4 rec = __ldcg(&pairs[2 * (size_t)pid]);
+                const uint4 link = __ldcg(&pairs[2 * (size_t)pid + 1]);  // same 32 B sector
                 const uint32_t ia = rec.x & ~TOPBIT, ib = rec.y & ~TOPBIT;
                 BodyRW a, b;
                 a.is_static = (rec.x & TOPBIT) != 0;
                 b.is_static = (rec.y & TOPBIT) != 0;
-                const float4 pa = ldcg4(&P[ia]), pb = ldcg4(&P[ib]);
-                const float4 loa = Lo[ia], hia = Hi[ia], lob = Lo[ib], hib = Hi[ib];
+                const float4 pa = ldcg4(&B.P(ia)), pb = ldcg4(&B.P(ib));
+                const float4 loa = ldcg4(&B.Lo(ia)), hia = ldcg4(&B.Hi(ia)), lob = ldcg4(&B.Lo(ib)), hib = ldcg4(&B.Hi(ib));
                 a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
                 b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
                 const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
@@ -949,17 +972,17 @@ __global__ void __launch_bounds__(256)
                                  amin.z < bmax.z && amax.z > bmin.z;
                 if (hit) {
                     ++contacts;
-                    const float4 va = ldcg4(&V[ia]), vb = ldcg4(&V[ib]);
+                    const float4 va = ldcg4(&B.V(ia)), vb = ldcg4(&B.V(ib));
                     a.vel = xyz(va), a.rest = va.w;
                     b.vel = xyz(vb), b.rest = vb.w;
                     const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
                     if (!a.is_static) {
-                        __stcg(&P[ia], make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass));
-                        __stcg(&V[ia], make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest));
+                        __stcg(&B.P(ia), make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass));
+                        __stcg(&B.V(ia), make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest));
                     }
                     if (!b.is_static) {
-                        __stcg(&P[ib], make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass));
-                        __stcg(&V[ib], make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
+                        __stcg(&B.P(ib), make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass));
+                        __stcg(&B.V(ib), make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest));
                     }
                     if (moved) {
                         if (!a.is_static)
@@ -969,22 +992,12 @@ __global__ void __launch_bounds__(256)
                             track_escape(b, ib, box[2 * (size_t)ib], mverify, dmax, reach, escapees, esc_cap, ctl, maxd,
                                          maxabs);
                     }
-                    pairs[pid].w = rec.w | TOPBIT;  // S_sweep flag; also tells k_restore which bodies were written
+                    pairs[2 * (size_t)pid].w = rec.w | TOPBIT;  // S_sweep flag; k_restore: these bodies were written
                 }
-                // pop the chains; wake pairs that reached the head everywhere
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const bool st = s ? b.is_static : a.is_static;
-                    if (st) continue;
-                    const uint32_t x = s ? ib : ia;
-                    const uint32_t h = __ldcg(&chain_cnt[x]) + 1u;
-                    __stcg(&chain_cnt[x], h);
-                    const uint32_t o0 = offs[x], o1 = offs[x + 1];
-                    if (o0 + h < o1) {
-                        const uint32_t q = (uint32_t)adj[o0 + h];
-                        if (atomicSub(&pending[q], 1u) == 1u) stage_push(fs, q);
-                    }
-                }
+                // wake the successors on both chains once they are at the head everywhere (static endpoints have
+                // no chain: their link stays NONE)
+                if (link.x != NONE && atomicSub(&pair_link(pairs, link.x)[2], 1u) == 1u) stage_push(fs, link.x);
+                if (link.y != NONE && atomicSub(&pair_link(pairs, link.y)[2], 1u) == 1u) stage_push(fs, link.y);
             }
             stage_flush(fs, fout, &ctl->frontier_n[co], 2u * blockDim.x);
         }
@@ -1030,7 +1043,7 @@ __global__ void __launch_bounds__(256)
     k_requery(const float4* __restrict__ box, const float4* __restrict__ sbox,
               const uint32_t* __restrict__ LB, const float* __restrict__ dmax, const float* __restrict__ reach,
               const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint4* __restrict__ pairs,
-              uint32_t* __restrict__ pending, uint32_t pair_cap, Ctl* ctl) {
+              uint32_t pair_cap, Ctl* ctl) {
     const uint32_t ne = min(ctl->n_escapees, esc_cap);
     if (ne == 0) return;
     const GridParams g = ctl->grid;
@@ -1082,8 +1095,8 @@ __global__ void __launch_bounds__(256)
             base = cgp.shfl(base, 0);
             const uint32_t slot = base + cgp.thread_rank();
             if (slot < pair_cap) {
-                pairs[slot] = rec;
-                pending[slot] = 0;
+                pairs[2 * (size_t)slot] = rec;
+                pairs[2 * (size_t)slot + 1] = link_init();
             } else {
                 atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
             }
@@ -1101,17 +1114,16 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ sval,
-              const float4* __restrict__ P0, const float4* __restrict__ V0,
-              const float4* __restrict__ A0, float4* __restrict__ P1, float4* __restrict__ V1,
-              uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ pending, float* __restrict__ dmax,
+              const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
+              uint32_t* __restrict__ chain_cnt, float* __restrict__ dmax,
               float* __restrict__ reach, const uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl, float dt,
               float d16, float d18, float d35) {
     if (ctl->repair_needed == 0) return;
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     for (uint32_t pid = gtid; pid < np; pid += gsz) {
-        uint4 r = pairs[pid];
-        pending[pid] = 0;
+        uint4 r = pairs[2 * (size_t)pid];
+        pairs[2 * (size_t)pid + 1] = link_init();
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const uint32_t t = s ? r.y : r.x;
@@ -1119,14 +1131,14 @@ __global__ void __launch_bounds__(256)
             chain_cnt[t] = 0;
             if (r.w & TOPBIT) {  // the sweep wrote this body: recompute its post-integration state (idempotent)
                 const uint32_t s0 = sval[t];  // its slot in the untouched input set
-                float4 p = P0[s0], v = V0[s0];
+                float4 p = B0.P(s0), v = B0.V(s0);
                 const float4 a = A0[s0];
                 if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
-                P1[t] = p;
-                V1[t] = v;
+                B1.P(t) = p;
+                B1.V(t) = v;
             }
         }
-        if (r.w & TOPBIT) pairs[pid].w = r.w & ~TOPBIT;
+        if (r.w & TOPBIT) pairs[2 * (size_t)pid].w = r.w & ~TOPBIT;
     }
     // the pairs within the grown reaches are now candidates: commit the reaches, start a fresh sweep record
     const uint32_t ne = min(ctl->n_escapees, esc_cap);
@@ -1143,7 +1155,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     for (uint32_t pid = gtid; pid < np; pid += gsz) {
-        const uint4 r = pairs[pid];
+        const uint4 r = pairs[2 * (size_t)pid];
         if (!(r.x & TOPBIT)) atomicAdd(&chain_cnt[r.x], 1u);
         if (!(r.y & TOPBIT)) atomicAdd(&chain_cnt[r.y], 1u);
     }
@@ -1211,7 +1223,7 @@ __global__ void k_export_pairs(const uint4* __restrict__ pairs, uint32_t np, int
                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* counter) {
     const uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= np) return;
-    const uint4 r = pairs[pid];
+    const uint4 r = pairs[2 * (size_t)pid];
     const bool in = which == 0 ? (r.z & TOPBIT) != 0 : (r.w & TOPBIT) != 0;
     if (!in) return;
     cg::coalesced_group g = cg::coalesced_threads();
@@ -1224,12 +1236,12 @@ __global__ void k_export_pairs(const uint4* __restrict__ pairs, uint32_t np, int
 }
 
 __global__ void k_gather_pairs(const uint4* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t m,
-                               const float4* __restrict__ Lo, uint2* __restrict__ out) {
+                               const Bodies B, uint2* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const uint4 r = pairs[order[i]];
+    const uint4 r = pairs[2 * (size_t)order[i]];
     // pair records hold slots of the current (cell-sorted) set; report body ids
-    out[i] = make_uint2(__float_as_uint(Lo[r.x & ~TOPBIT].w), __float_as_uint(Lo[r.y & ~TOPBIT].w));
+    out[i] = make_uint2(__float_as_uint(B.Lo(r.x & ~TOPBIT).w), __float_as_uint(B.Lo(r.y & ~TOPBIT).w));
 }
 
 }  // namespace gp
