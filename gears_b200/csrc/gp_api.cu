@@ -59,8 +59,10 @@ struct gp_world {
     uint32_t* frontier[2] = {nullptr, nullptr};
     uint32_t* heavy = nullptr;
     uint32_t heavy_cap = 0;
-    float* dmax = nullptr;        // per body: largest displacement during the current sweep (escapees only, else 0)
+    float* dmax = nullptr;        // per body: largest displacement during the current sweep
     float* reach = nullptr;       // per body: largest displacement over the earlier sweeps of this step
+    uint32_t *moved_bits = nullptr, *esc_bits = nullptr;  // per body: moved at all / left the outer margin
+    uint2* watch = nullptr;       // lazy candidates: pairs between the inner and the outer margin
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
     // control
@@ -123,7 +125,7 @@ static void free_all(gp_world* w) {
     void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
                     w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
-                    w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->ctl, w->ctl_snap, w->d_small, w->stage};
+                    w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->moved_bits, w->esc_bits, w->watch, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
@@ -245,6 +247,8 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     CK(dmalloc(&w->reach, cap));
     CK(cudaMemset(w->reach, 0, sizeof(float) * (size_t)cap));
     CK(dmalloc(&w->escapees, cap));
+    CK(dmalloc(&w->moved_bits, (size_t)cap / 32 + 1));
+    CK(dmalloc(&w->esc_bits, (size_t)cap / 32 + 1));
     CK(cudaMemset(w->dmax, 0, sizeof(float) * (size_t)cap));
     w->cap = cap;
     return GP_OK;
@@ -254,6 +258,7 @@ static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
     if (pair_cap > 0x7fff0000ull) pair_cap = 0x7fff0000ull;
     CK(dmalloc(&w->pairs, 2 * pair_cap));  // 32 B records
     CK(dmalloc(&w->adj, 2 * pair_cap));
+    CK(dmalloc(&w->watch, pair_cap));
     CK(dmalloc(&w->frontier[0], pair_cap));
     CK(dmalloc(&w->frontier[1], pair_cap));
     w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);
@@ -353,6 +358,15 @@ static gp_status setup_grid(gp_world* w) {
     hc.margin = m_init;
     hc.margin_min = m_init;
     hc.margin_max = m_max;
+    {
+        // lazy candidates need repair sweeps; with GP_FLAG_NO_RETRY every candidate enters the sweep at once
+        const bool lazy = !(c.flags & GP_FLAG_NO_RETRY);
+        const char* e1 = getenv("GP_INNER_FRAC");
+        const char* e2 = getenv("GP_REPAIR_TOL");
+        hc.lazy = lazy ? 1u : 0u;
+        hc.margin_in = lazy ? m_init * (e1 ? (float)atof(e1) : 0.25f) : m_init;
+        hc.repair_tol = e2 ? (uint32_t)atoi(e2) : 1u;
+    }
     for (int k = 0; k < 3; ++k) hc.lo[k] = lo[k], hc.hi[k] = hi[k];
     hc.ext_max = ext_max;
     hc.cell_cfg = cell_min;
@@ -620,32 +634,43 @@ static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
     uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
     Ctl* ctl = w->ctl;
     float* dmax = w->dmax;
-    const float* reach = w->reach;
+    uint32_t *mvb = w->moved_bits, *esb = w->esc_bits;
     uint32_t* esc = w->escapees;
     uint32_t esc_cap = w->cap;
-    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &reach, &esc, &esc_cap, &gate};
+    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate};
     CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
     w->launches++;
     return GP_OK;
 }
 
-// One repair round (all kernels gated on ctl->repair_needed), ending with a fresh k_requery.
+// After a sweep: did it stay inside what the candidate set assumed?  k_requery looks for pairs beyond the outer
+// margin that escapees reached, k_verify_watch for watch pairs whose swept boxes touch; both append to the sweep set
+// and raise ctl->repair_needed.
+static void enqueue_verify(gp_world* w) {
+    cudaStream_t st = w->st;
+    k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->esc_bits, w->escapees,
+                                               w->cap, w->pairs, (uint32_t)w->pair_cap, w->ctl);
+    k_verify_watch<<<w->sm_count * 8, 256, 0, st>>>(w->watch, (uint32_t)w->pair_cap, w->sbox, w->dmax, w->reach,
+                                                    w->moved_bits, w->pairs, (uint32_t)w->pair_cap, w->ctl);
+    w->launches += 2;
+}
+
+// One repair round (all kernels gated on ctl->repair_needed), ending with a fresh verification.
 static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     cudaStream_t st = w->st;
     const int c = w->cur, o = c ^ 1;
     const uint32_t* gate = &w->ctl->repair_needed;
     k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->perm, Bodies{w->B[c]},
-                                               w->A[c], Bodies{w->B[o]}, w->chain_cnt, w->dmax, w->reach,
-                                               w->escapees, w->cap, w->ctl, dt, d[0], d[1], d[2]);
+                                               w->A[c], Bodies{w->B[o]}, w->chain_cnt, w->dmax, w->reach, w->ctl, dt, d[0], d[1],
+                                               d[2]);
     k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
     k_repair_reset<<<1, 1, 0, st>>>(w->ctl);
     w->launches += 3;
     gp_status s = enqueue_chains_and_sweep(w, gate);
     if (s != GP_OK) return s;
     k_repair_done<<<1, 1, 0, st>>>(w->ctl);
-    k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
-                                               w->pairs, (uint32_t)w->pair_cap, w->ctl);
-    w->launches += 2;
+    w->launches += 1;
+    enqueue_verify(w);
     return GP_OK;
 }
 
@@ -674,22 +699,18 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
         prof_mark(w, 2);
         k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
                                                        w->A[o], w->sbox,
-                                                       w->chain_cnt, w->perm, w->dmax, w->reach, w->LB, w->ctl, dt, d[0],
-                                                       d[1], d[2]);
+                                                       w->chain_cnt, w->perm, w->dmax, w->reach, w->moved_bits, w->esc_bits, w->LB,
+                                                       w->ctl, dt, d[0], d[1], d[2]);
         w->launches += 1;
         prof_mark(w, 3);
         k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
-            w->sbox, w->LB, w->pairs, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+            w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
         enqueue_chains_and_sweep(w, nullptr);
         // speculative broad phase: look for pairs the margin missed, repair, look again
-        k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->escapees, w->cap,
-                                                   w->pairs, (uint32_t)w->pair_cap, w->ctl);
-        w->launches++;
+        enqueue_verify(w);
         for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
-        k_clear_escapees<<<w->sm_count, 256, 0, st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, latch);
-        w->launches++;
     }
     prof_mark(w, 6);
     k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
@@ -703,7 +724,7 @@ static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
     gp_step_stats& s = w->last;
     s.n_bodies = w->n;
     s.n_big = w->n - std::min(c.n_small, w->n);
-    s.n_candidates = c.n_pairs;
+    s.n_candidates = (uint64_t)c.n_pairs + c.n_watch - c.n_activated;
     s.n_snapshot = c.n_snapshot;
     s.n_contacts = c.n_contacts;
     s.n_rounds = c.n_rounds;
@@ -753,9 +774,8 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
                 s = enqueue_repair_round(w, dt, d);
                 if (s != GP_OK) return s;
             }
-            k_clear_escapees<<<w->sm_count, 256, 0, w->st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, 0);
             k_finish_step<<<1, 1, 0, w->st>>>(w->ctl, w->ctl_snap, 0);
-            w->launches += 2;
+            w->launches += 1;
             s = read_ctl(w);
             if (s != GP_OK) return s;
             ++extra;
@@ -769,7 +789,8 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
             if (no_retry || retries >= 8)
                 return fail(w, GP_ERR_PAIR_OVERFLOW, "%u candidate pairs > max_pairs %llu", c.n_pairs,
                             (unsigned long long)w->pair_cap);
-            gp_status a = alloc_pairs(w, std::max<uint64_t>(2 * w->pair_cap, (uint64_t)c.n_pairs + c.n_pairs / 4));
+            const uint64_t need = std::max<uint64_t>(c.n_pairs, c.n_watch);
+            gp_status a = alloc_pairs(w, std::max<uint64_t>(2 * w->pair_cap, need + need / 4));
             if (a != GP_OK) return a;
             ++retries;
             result = GP_WARN_MARGIN_RETRIED;
@@ -780,16 +801,16 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
             if (stats) *stats = w->last;
             const uint32_t nrep = c.n_repairs;
             const float mrg = c.margin;
-            // give up on this step: drop the escapee marks and per-step counters (input buffers are untouched)
-            k_clear_escapees<<<w->sm_count, 256, 0, w->st>>>(w->dmax, w->reach, w->escapees, w->cap, w->ctl, 1);
+            // give up on this step: drop the per-step counters (the input set is untouched)
             k_finish_step<<<1, 1, 0, w->st>>>(w->ctl, w->ctl_snap, 2);
-            w->launches += 2;
+            w->launches += 1;
             CK(cudaStreamSynchronize(w->st));
             return fail(w, GP_ERR_MARGIN,
                         "the candidate pair set was still growing after %u repair sweeps (margin %.4g): step not applied",
                         nrep, mrg);
         }
-        if (c.n_repairs) result = GP_WARN_MARGIN_RETRIED;
+        // repair sweeps for activated watch pairs are routine; bodies out-running the OUTER margin are worth a note
+        if (c.n_requeried) result = GP_WARN_MARGIN_RETRIED;
         w->cur ^= 1;
         w->steps_total++;
         fill_stats(w, c, retries);

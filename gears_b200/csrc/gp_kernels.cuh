@@ -71,7 +71,14 @@ struct Ctl {
     float margin;             // relative margin mu of the current step: body x's AABB is inflated by
                               // mu * (largest extent of x) in K4, and K6 verifies it never moves further
     float margin_min, margin_max;
-    uint32_t n_pairs;         // candidate pairs emitted by K4 (may exceed capacity: then overflow)
+    float margin_in;          // relative INNER margin: pairs within it enter the sweep at once; pairs between the
+                              // inner and the outer margin only go on the watch list (lazy candidates)
+    uint32_t lazy;            // 0: margin_in == margin always (no watch list; GP_FLAG_NO_RETRY)
+    uint32_t repair_tol;      // margin policy: repair sweeps per step that are tolerated before the inner margin grows
+    uint32_t n_watch;         // watch-list entries written by K4
+    uint32_t n_activated;     // watch pairs that had to join the sweep (stats)
+    uint32_t n_requeried;     // pairs beyond the outer margin found by k_requery (stats; grows the outer margin)
+    uint32_t n_pairs;         // sweep pairs (K4 inner pairs + activated + requeried; may exceed capacity: overflow)
     uint32_t n_snapshot;
     uint32_t n_contacts;
     uint32_t n_rounds;
@@ -437,7 +444,8 @@ __global__ void __launch_bounds__(256)
     k_scatter_cells(const uint32_t* __restrict__ key, const uint32_t* __restrict__ lrank,
                     const Bodies B0, const float4* __restrict__ A0, const Bodies B1, float4* __restrict__ A1,
                     float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ perm,
-                    float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ LB, Ctl* ctl,
+                    float* __restrict__ dmax, float* __restrict__ reach, uint32_t* __restrict__ moved_bits,
+                    uint32_t* __restrict__ esc_bits, const uint32_t* __restrict__ LB, Ctl* ctl,
                     float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncells = ctl->grid.ncells;
@@ -466,6 +474,7 @@ __global__ void __launch_bounds__(256)
     chain_cnt[s] = 0;
     perm[s] = i;  // slot in the input set: k_restore re-integrates from there
     dmax[s] = 0.0f, reach[s] = 0.0f;
+    if ((s & 31u) == 0u) moved_bits[s >> 5] = 0u, esc_bits[s >> 5] = 0u;  // every word of [0, n) has one such slot
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,27 +497,34 @@ __device__ __forceinline__ bool inflated_overlap(const float4 alo, const float4 
            (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
 }
 
-// candidate test of one (a, b): returns true and fills rec if the pair must be emitted
-__device__ __forceinline__ bool test_candidate(const float4 alo, const float4 ahi, const float ma, const float4 blo,
-                                               const float4 bhi, float mu, uint4& rec) {
-    // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x)
-    if (!inflated_overlap(alo, ahi, blo, bhi, ma + mu * box_extent(blo, bhi))) return false;
+// candidate test of one (a, b): 0 = not a candidate, 1 = watch (between the inner and the outer margin),
+// 2 = sweep pair (within the inner margin; includes every pair that intersects on the snapshot); fills rec
+__device__ __forceinline__ int test_candidate(const float4 alo, const float4 ahi, const float ea, const float4 blo,
+                                              const float4 bhi, float mu, float mu_in, uint4& rec) {
+    // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x).  k_requery
+    // re-evaluates exactly this expression (fl(mu*ea) + fl(mu*eb)) to know what K4 has already found.
+    const float eb = box_extent(blo, bhi);
+    if (!inflated_overlap(alo, ahi, blo, bhi, mu * ea + mu * eb)) return 0;
     const uint32_t ta = __float_as_uint(alo.w), tb = __float_as_uint(blo.w);
-    if ((ta & tb) & TOPBIT) return false;  // static-static: no-op in the reference (physics.rs:225)
-    const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
+    if ((ta & tb) & TOPBIT) return 0;  // static-static: no-op in the reference (physics.rs:225)
     const uint32_t ra = __float_as_uint(ahi.w), rb = __float_as_uint(bhi.w);
+    if (!inflated_overlap(alo, ahi, blo, bhi, mu_in * ea + mu_in * eb)) {
+        rec = (ra < rb) ? make_uint4(ta, tb, 0u, 0u) : make_uint4(tb, ta, 0u, 0u);
+        return 1;
+    }
+    const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
     if (ra < rb)
         rec = make_uint4(ta, tb, ra | (snap ? TOPBIT : 0u), rb);
     else
         rec = make_uint4(tb, ta, rb | (snap ? TOPBIT : 0u), ra);
-    return true;
+    return 2;
 }
 
 constexpr int FP_THREADS = 256;   // bodies per tile = threads per CTA
 constexpr int FP_RANGES = 6;      // candidate slot ranges per body: 5 cell-row runs + the big list
 constexpr int FP_BATCH = 4;       // tests per thread per batch
 constexpr int FP_WARPS = FP_THREADS / 32;
-constexpr int FP_WSTAGE = 192;    // staged pair records per warp (flushed above 64: a batch adds <= 128)
+constexpr int FP_WSTAGE = 160;    // staged pair records per warp (flushed above 32: a batch adds <= 128)
 constexpr int FP_NR = FP_THREADS * FP_RANGES;
 
 // ---- TMA bulk copy (cp.async.bulk, 1-D) of a tile of AABBs into shared memory, completion on an mbarrier ----
@@ -542,9 +558,10 @@ struct FindPairsSmem {
     float4 abox[2 * FP_THREADS];  // AABBs of the tile's bodies (lo|tag, hi|rank), staged by TMA
     uint32_t rstart[FP_NR];       // first candidate slot of range id = r * FP_THREADS + j
     uint32_t roff[FP_NR + 1];     // exclusive scan of the range lengths: test t belongs to range id with roff[id] <= t
-    uint4 stage[FP_WARPS][FP_WSTAGE];  // per-warp pair records waiting for the next flush
+    uint4 stage[FP_WARPS][FP_WSTAGE];  // per-warp sweep-pair records waiting for the next flush
+    uint2 wstage[FP_WARPS][FP_WSTAGE]; // per-warp watch-list entries
     uint32_t scan[33];
-    uint32_t stage_cnt[FP_WARPS];
+    uint32_t stage_cnt[FP_WARPS], wstage_cnt[FP_WARPS];
     uint64_t bar;
 };
 
@@ -558,23 +575,25 @@ struct FindPairsSmem {
 //     of a CTA do not synchronise while they test.
 __global__ void __launch_bounds__(FP_THREADS)
     k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
-                 uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+                 uint2* __restrict__ watch, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
     extern __shared__ __align__(128) unsigned char fp_smem_raw[];
     FindPairsSmem& sm = *reinterpret_cast<FindPairsSmem*>(fp_smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t n = ctl->n;
     const GridParams g = ctl->grid;
-    const float mu = ctl->margin;
+    const float mu = ctl->margin, mu_in = ctl->margin_in;
     const uint32_t n_small = ctl->n_small;
     const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(&sm.bar, 1);
-    if (lane == 0) sm.stage_cnt[warp] = 0;
+    if (lane == 0) sm.stage_cnt[warp] = 0, sm.wstage_cnt[warp] = 0;
     __syncthreads();
     uint32_t parity = 0, nsnap = 0;
     const uint32_t ntiles = (n + FP_THREADS - 1) / FP_THREADS;
     uint4* const wstage = sm.stage[warp];
     uint32_t* const wcnt = &sm.stage_cnt[warp];
+    uint2* const wwatch = sm.wstage[warp];
+    uint32_t* const wwcnt = &sm.wstage_cnt[warp];
 
     auto flush = [&]() {  // warp-synchronous
         __syncwarp();
@@ -596,6 +615,19 @@ __global__ void __launch_bounds__(FP_THREADS)
         }
         __syncwarp();
         if (lane == 0) *wcnt = 0;
+        __syncwarp();
+    };
+    auto flush_watch = [&]() {  // warp-synchronous
+        __syncwarp();
+        const uint32_t c = *wwcnt;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->n_watch, c);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane == 0 && base + c > pair_cap) atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+        for (uint32_t i = lane; i < c; i += 32)
+            if (base + i < pair_cap) watch[base + i] = wwatch[i];
+        __syncwarp();
+        if (lane == 0) *wwcnt = 0;
         __syncwarp();
     };
 
@@ -667,7 +699,7 @@ __global__ void __launch_bounds__(FP_THREADS)
                 uint32_t q = sm.rstart[id] + (t0 - sm.roff[id]);
                 uint32_t j = id & (FP_THREADS - 1);
                 float4 alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
-                float ma = mu * box_extent(alo, ahi);
+                float ea = box_extent(alo, ahi);
                 const uint32_t t1 = min(t0 + FP_BATCH, T);
                 for (uint32_t t = t0; t < t1; ++t, ++q) {
                     if (t >= end_t) {
@@ -675,19 +707,25 @@ __global__ void __launch_bounds__(FP_THREADS)
                         q = sm.rstart[id];
                         j = id & (FP_THREADS - 1);
                         alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
-                        ma = mu * box_extent(alo, ahi);
+                        ea = box_extent(alo, ahi);
                     }
                     const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
                     uint4 rec;
-                    if (test_candidate(alo, ahi, ma, blo, bhi, mu, rec)) wstage[atomicAdd(wcnt, 1u)] = rec;
+                    const int kind = test_candidate(alo, ahi, ea, blo, bhi, mu, mu_in, rec);
+                    if (kind == 2)
+                        wstage[atomicAdd(wcnt, 1u)] = rec;
+                    else if (kind == 1)
+                        wwatch[atomicAdd(wwcnt, 1u)] = make_uint2(rec.x, rec.y);
                 }
             }
             __syncwarp();
-            if (*wcnt > 64u) flush();  // the next batch adds at most 32 * FP_BATCH = 128 records
+            if (*wcnt > 32u) flush();  // the next batch adds at most 32 * FP_BATCH = 128 records
+            if (*wwcnt > 32u) flush_watch();
         }
         __syncthreads();  // rstart/roff/abox are rewritten by the next tile
     }
     if (*wcnt) flush();
+    if (*wwcnt) flush_watch();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsnap += __shfl_xor_sync(0xffffffffu, nsnap, o);
     if ((tid & 31) == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
@@ -893,37 +931,43 @@ __device__ __forceinline__ void stage_flush(FrontierStage& fs, uint32_t* __restr
     __syncthreads();
 }
 
-// A body whose AABB leaves its K1 snapshot inflated by mu*extent is an ESCAPEE: the candidate set built
-// from the snapshot may miss pairs it reaches.  dmax[x] keeps the largest per-axis displacement it had at
-// any time in the current sweep (its swept AABB is inside snapshot (+) dmax); reach[x] is the largest dmax of
-// the earlier sweeps of this step.  k_requery looks for the pairs the candidate set missed.
-// Only one thread touches a dynamic body per round, so plain (L2) accesses suffice.
-__device__ __forceinline__ void track_escape(const BodyRW& x, uint32_t ix, float4 lo_snap, float mu_verify,
-                                             float* __restrict__ dmax, const float* __restrict__ reach,
-                                             uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl,
-                                             float& maxrel, float& maxabs) {
+// Displacement tracking.  dmax[x] = largest per-axis displacement body x had at any time in the current sweep (its
+// swept AABB lies inside snapshot (+) dmax); reach[x] = the same over the earlier sweeps of this step (committed by
+// k_restore).  moved_bits marks bodies with dmax or reach != 0 (k_verify_watch looks there first).
+// A body whose AABB leaves its snapshot inflated by mu*extent is an ESCAPEE (esc_bits, escapees[]): the candidate
+// set built from the snapshot may miss pairs it reaches; k_requery looks for them.
+// Only one thread touches a dynamic body per round, so plain (L2) accesses suffice for dmax.
+__device__ __forceinline__ void track_move(const BodyRW& x, uint32_t ix, float4 lo_snap, float mu_verify,
+                                           float* __restrict__ dmax, uint32_t* __restrict__ moved_bits,
+                                           uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
+                                           uint32_t esc_cap, Ctl* ctl, float& maxrel, float& maxabs) {
     const V3 lo_now = x.omin + x.pos;
     const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
+    if (d == 0.0f) return;
     const float e = fmaxf(x.omax.x - x.omin.x, fmaxf(x.omax.y - x.omin.y, x.omax.z - x.omin.z));
     maxrel = fmaxf(maxrel, d / e);
+    const float old = __ldcg(&dmax[ix]);
+    const uint32_t bit = 1u << (ix & 31u);
+    if (!(d <= old)) __stcg(&dmax[ix], d);
+    if (old == 0.0f) atomicOr(&moved_bits[ix >> 5], bit);
     if (!(d <= mu_verify * e)) {
-        const float old = __ldcg(&dmax[ix]);
-        if (old == 0.0f && reach[ix] == 0.0f) {  // first escape of this body in this step
+        const uint32_t prev = atomicOr(&esc_bits[ix >> 5], bit);
+        if (!(prev & bit)) {  // first escape of this body in this step
             const uint32_t s = atomicAdd(&ctl->n_escapees, 1u);
             if (s < esc_cap)
                 escapees[s] = ix;
             else
                 atomicOr(&ctl->step_flags, SF_ESCAPEE_OVERFLOW);
         }
-        if (d > old) __stcg(&dmax[ix], d);
         maxabs = fmaxf(maxabs, d);
     }
 }
 
 __global__ void __launch_bounds__(256)
     k_sweep(const Bodies B, const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
-            uint32_t* __restrict__ frontier0, uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax, const float* __restrict__ reach,
-            uint32_t* __restrict__ escapees, uint32_t esc_cap, const uint32_t* __restrict__ gate) {
+            uint32_t* __restrict__ frontier0, uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax,
+            uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
+            uint32_t esc_cap, const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;  // uniform across the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
     __shared__ FrontierStage fs;
@@ -986,11 +1030,11 @@ __global__ void __launch_bounds__(256)
                     }
                     if (moved) {
                         if (!a.is_static)
-                            track_escape(a, ia, box[2 * (size_t)ia], mverify, dmax, reach, escapees, esc_cap, ctl, maxd,
-                                         maxabs);
+                            track_move(a, ia, box[2 * (size_t)ia], mverify, dmax, moved_bits, esc_bits, escapees, esc_cap,
+                                       ctl, maxd, maxabs);
                         if (!b.is_static)
-                            track_escape(b, ib, box[2 * (size_t)ib], mverify, dmax, reach, escapees, esc_cap, ctl, maxd,
-                                         maxabs);
+                            track_move(b, ib, box[2 * (size_t)ib], mverify, dmax, moved_bits, esc_bits, escapees, esc_cap,
+                                       ctl, maxd, maxabs);
                     }
                     pairs[2 * (size_t)pid].w = rec.w | TOPBIT;  // S_sweep flag; k_restore: these bodies were written
                 }
@@ -1042,8 +1086,8 @@ constexpr float REACH_SLACK = 1.0001f;  // covers the rounding of the measured d
 __global__ void __launch_bounds__(256)
     k_requery(const float4* __restrict__ box, const float4* __restrict__ sbox,
               const uint32_t* __restrict__ LB, const float* __restrict__ dmax, const float* __restrict__ reach,
-              const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint4* __restrict__ pairs,
-              uint32_t pair_cap, Ctl* ctl) {
+              const uint32_t* __restrict__ esc_bits, const uint32_t* __restrict__ escapees, uint32_t esc_cap,
+              uint4* __restrict__ pairs, uint32_t pair_cap, Ctl* ctl) {
     const uint32_t ne = min(ctl->n_escapees, esc_cap);
     if (ne == 0) return;
     const GridParams g = ctl->grid;
@@ -1086,7 +1130,8 @@ __global__ void __launch_bounds__(256)
             const float rb_old = fmaxf(mb, ry_prev), rb_new = fmaxf(rb_old, ry_now);
             if (inflated_overlap(alo, ahi, blo, bhi, ra_old + rb_old)) return;   // found in an earlier round / by K4
             if (!inflated_overlap(alo, ahi, blo, bhi, ra_new + rb_new)) return;  // still out of reach
-            if (ry_now > ry_prev && y < x) return;  // y grew too: its own query reports the pair
+            // y is an escapee that grew too: its own query reports the pair (the lower slot wins)
+            if (y < x && ry_now > ry_prev && ((esc_bits[y >> 5] >> (y & 31u)) & 1u)) return;
             const uint32_t rb = __float_as_uint(bhi.w);
             uint4 rec = (ra < rb) ? make_uint4(ta, tb, ra, rb) : make_uint4(tb, ta, rb, ra);
             cg::coalesced_group cgp = cg::coalesced_threads();
@@ -1101,6 +1146,7 @@ __global__ void __launch_bounds__(256)
                 atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
             }
             ctl->repair_needed = 1u;
+            atomicAdd(&ctl->n_requeried, 1u);
         };
         for (int z = c0[2]; z <= c1[2]; ++z)
             for (int y = c0[1]; y <= c1[1]; ++y) {
@@ -1115,9 +1161,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ sval,
               const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
-              uint32_t* __restrict__ chain_cnt, float* __restrict__ dmax,
-              float* __restrict__ reach, const uint32_t* __restrict__ escapees, uint32_t esc_cap, Ctl* ctl, float dt,
-              float d16, float d18, float d35) {
+              uint32_t* __restrict__ chain_cnt, float* __restrict__ dmax, float* __restrict__ reach, Ctl* ctl,
+              float dt, float d16, float d18, float d35) {
     if (ctl->repair_needed == 0) return;
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -1136,16 +1181,16 @@ __global__ void __launch_bounds__(256)
                 if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
                 B1.P(t) = p;
                 B1.V(t) = v;
+                // the pairs within the grown reach are candidates now: commit it (several pairs may share t: the max
+                // is atomic, non-negative floats order like their bit patterns), start a fresh sweep record
+                const float dm = dmax[t];
+                if (dm != 0.0f) {
+                    atomicMax(reinterpret_cast<uint32_t*>(&reach[t]), __float_as_uint(dm * REACH_SLACK));
+                    dmax[t] = 0.0f;
+                }
             }
         }
         if (r.w & TOPBIT) pairs[2 * (size_t)pid].w = r.w & ~TOPBIT;
-    }
-    // the pairs within the grown reaches are now candidates: commit the reaches, start a fresh sweep record
-    const uint32_t ne = min(ctl->n_escapees, esc_cap);
-    for (uint32_t e = gtid; e < ne; e += gsz) {
-        const uint32_t x = escapees[e];
-        reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
-        dmax[x] = 0.0f;
     }
 }
 
@@ -1173,15 +1218,40 @@ __global__ void k_repair_reset(Ctl* ctl) {
 // after the repair sweep: the next k_requery decides again
 __global__ void k_repair_done(Ctl* ctl) { ctl->repair_needed = 0; }
 
-// escapee marks are only read by k_requery; clear them once the last one ran (k_restore does the same)
+// Lazy candidates: a watch pair (between the inner and the outer margin) can only intersect at its turn if one
+// of its bodies moved.  After a sweep, every watch pair whose SWEPT boxes (snapshot (+) reach) touch joins the sweep
+// set and a repair sweep runs; pairs that stay out provably never intersect (exactness argument).
 __global__ void __launch_bounds__(256)
-    k_clear_escapees(float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ escapees,
-                     uint32_t esc_cap, const Ctl* ctl, int force) {
-    if (!force && ctl->repair_needed) return;  // the repair loop goes on (sync mode): k_restore needs the marks
-    const uint32_t ne = min(ctl->n_escapees, esc_cap);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-        dmax[escapees[e]] = 0.0f;
-        reach[escapees[e]] = 0.0f;
+    k_verify_watch(uint2* __restrict__ watch, uint32_t watch_cap, const float4* __restrict__ sbox,
+                   const float* __restrict__ dmax, const float* __restrict__ reach,
+                   const uint32_t* __restrict__ moved_bits, uint4* __restrict__ pairs, uint32_t pair_cap, Ctl* ctl) {
+    const uint32_t nw = min(ctl->n_watch, watch_cap);
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nw; wi += gridDim.x * blockDim.x) {
+        const uint2 wp = watch[wi];
+        if (wp.x == NONE) continue;  // joined the sweep in an earlier round
+        const uint32_t a = wp.x & ~TOPBIT, b = wp.y & ~TOPBIT;
+        const bool ma = (moved_bits[a >> 5] >> (a & 31u)) & 1u, mb = (moved_bits[b >> 5] >> (b & 31u)) & 1u;
+        if (!(ma || mb)) continue;
+        const float ra = ma ? fmaxf(reach[a], dmax[a] * REACH_SLACK) : 0.0f;
+        const float rb = mb ? fmaxf(reach[b], dmax[b] * REACH_SLACK) : 0.0f;
+        const float4 alo = sbox[2 * (size_t)a], ahi = sbox[2 * (size_t)a + 1];
+        const float4 blo = sbox[2 * (size_t)b], bhi = sbox[2 * (size_t)b + 1];
+        if (!inflated_overlap(alo, ahi, blo, bhi, ra + rb)) continue;
+        watch[wi].x = NONE;
+        const uint4 rec = make_uint4(wp.x, wp.y, __float_as_uint(ahi.w), __float_as_uint(bhi.w));  // a = lower rank
+        cg::coalesced_group cgp = cg::coalesced_threads();
+        uint32_t base = 0;
+        if (cgp.thread_rank() == 0) base = atomicAdd(&ctl->n_pairs, cgp.size());
+        base = cgp.shfl(base, 0);
+        const uint32_t slot = base + cgp.thread_rank();
+        if (slot < pair_cap) {
+            pairs[2 * (size_t)slot] = rec;
+            pairs[2 * (size_t)slot + 1] = link_init();
+        } else {
+            atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
+        }
+        ctl->repair_needed = 1u;
+        atomicAdd(&ctl->n_activated, 1u);
     }
 }
 
@@ -1206,15 +1276,26 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     // a small margin keeps the candidate set (and every pair-proportional kernel) small; a repair sweep
     // costs about one more sweep.  Grow only when the pre-enqueued repair rounds were nearly used up.
     float m = c.margin;
-    if (c.n_repairs >= 2)
-        m *= 1.5f;
-    else if (c.n_repairs == 0)
-        m *= 0.9f;
+    // bodies that out-run the outer margin cost a neighbourhood query each and a repair sweep; a repair sweep
+    // is tolerated (watch-pair activations cause one anyway), a second one is not
+    if (c.n_requeried && c.n_repairs > c.repair_tol + (c.n_activated ? 0u : 1u))
+        m *= 1.25f;
+    else if (c.n_requeried == 0)
+        m *= 0.98f;
     c.margin = fminf(fmaxf(m, c.margin_min), c.margin_max);
+    float mi = c.margin_in;
+    if (c.n_repairs > c.repair_tol)
+        mi = fmaxf(mi * 1.5f, 0.004f);   // too many repair sweeps: let more pairs into the first sweep
+    else if (c.n_repairs < c.repair_tol)
+        mi *= 0.9f;
+    else if (c.repair_tol == 0)
+        mi *= 0.97f;  // no repairs wanted at all: relax slowly
+    c.margin_in = c.lazy ? fminf(mi, c.margin) : c.margin;
     c.grid = make_grid(c.lo, c.hi, c.ext_max, c.margin, c.cell_cfg, c.max_cells);
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.step_flags = 0;
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
+    c.n_watch = 0, c.n_activated = 0, c.n_requeried = 0;
     *ctl = c;
 }
 
