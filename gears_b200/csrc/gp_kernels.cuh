@@ -162,6 +162,10 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
 }
 __device__ __forceinline__ V3 xyz(float4 v) { return mk(v.x, v.y, v.z); }
 
+__device__ __forceinline__ float box_extent(const float4 lo, const float4 hi) {
+    return fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+}
+
 __device__ __forceinline__ uint32_t cell_key(const GridParams& g, float cx, float cy, float cz) {
     // __float2int_rd saturates and maps NaN to 0; the clamp keeps every body inside [1, dim-2]
     int ix = __float2int_rd((cx - g.ox) * g.inv_cell) + 1;
@@ -468,9 +472,13 @@ __global__ void __launch_bounds__(256)
     }
     B1.P(s) = p, B1.V(s) = v, A1[s] = a, B1.Lo(s) = lo, B1.Hi(s) = hi;
     // world AABB = offsets + position (physics.rs:117: corner + pos; min/max commute with the rounding)
-    const uint32_t tag = s | ((flags & F_STATIC) ? TOPBIT : 0u);
-    sbox[2 * (size_t)s] = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, __uint_as_float(tag));
-    sbox[2 * (size_t)s + 1] = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, hi.w /* rank */);
+    // AABB record: lo.w = the body's outer margin fl(mu * extent), sign bit = static; hi.w = rank
+    const float4 wlo = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, 0.0f);
+    const float4 whi = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, hi.w);
+    const float m = ctl->margin * box_extent(wlo, whi);
+    sbox[2 * (size_t)s] = make_float4(wlo.x, wlo.y, wlo.z,
+                                      __uint_as_float((__float_as_uint(m) & ~TOPBIT) | ((flags & F_STATIC) ? TOPBIT : 0u)));
+    sbox[2 * (size_t)s + 1] = whi;
     chain_cnt[s] = 0;
     perm[s] = i;  // slot in the input set: k_restore re-integrates from there
     dmax[s] = 0.0f, reach[s] = 0.0f;
@@ -487,37 +495,22 @@ __global__ void __launch_bounds__(256)
 // Pairs are appended with warp-aggregated atomics (one atomicAdd per warp-wide ballot).
 // Pair record: x = a | static<<31, y = b | static<<31, z = rank_a | snapshot<<31, w = rank_b (| hit<<31 in K6).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float box_extent(const float4 lo, const float4 hi) {
-    return fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
-}
+// AABB record of the step (sbox, 32 B per slot): lo = (min.xyz, +-m) where m = fl(mu * extent) is the body's
+// OUTER margin and the sign bit is the static flag; hi = (max.xyz, rank).  K3 writes it, so every kernel of the
+// step (K4, k_requery, k_verify_watch) sees the same margin bits.
+__device__ __forceinline__ float box_margin(const float4 lo) { return fabsf(lo.w); }
+__device__ __forceinline__ uint32_t box_static(const float4 lo) { return __float_as_uint(lo.w) & TOPBIT; }
 
 __device__ __forceinline__ bool inflated_overlap(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi,
                                                  float m2) {
     return (alo.x - bhi.x < m2) && (blo.x - ahi.x < m2) && (alo.y - bhi.y < m2) && (blo.y - ahi.y < m2) &&
            (alo.z - bhi.z < m2) && (blo.z - ahi.z < m2);
 }
-
-// candidate test of one (a, b): 0 = not a candidate, 1 = watch (between the inner and the outer margin),
-// 2 = sweep pair (within the inner margin; includes every pair that intersects on the snapshot); fills rec
-__device__ __forceinline__ int test_candidate(const float4 alo, const float4 ahi, const float ea, const float4 blo,
-                                              const float4 bhi, float mu, float mu_in, uint4& rec) {
-    // inflated test: (a.lo - b.hi) < m_a + m_b on every axis and direction, m_x = mu * extent(x).  k_requery
-    // re-evaluates exactly this expression (fl(mu*ea) + fl(mu*eb)) to know what K4 has already found.
-    const float eb = box_extent(blo, bhi);
-    if (!inflated_overlap(alo, ahi, blo, bhi, mu * ea + mu * eb)) return 0;
-    const uint32_t ta = __float_as_uint(alo.w), tb = __float_as_uint(blo.w);
-    if ((ta & tb) & TOPBIT) return 0;  // static-static: no-op in the reference (physics.rs:225)
-    const uint32_t ra = __float_as_uint(ahi.w), rb = __float_as_uint(bhi.w);
-    if (!inflated_overlap(alo, ahi, blo, bhi, mu_in * ea + mu_in * eb)) {
-        rec = (ra < rb) ? make_uint4(ta, tb, 0u, 0u) : make_uint4(tb, ta, 0u, 0u);
-        return 1;
-    }
-    const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z && ahi.z > blo.z;
-    if (ra < rb)
-        rec = make_uint4(ta, tb, ra | (snap ? TOPBIT : 0u), rb);
-    else
-        rec = make_uint4(tb, ta, rb | (snap ? TOPBIT : 0u), ra);
-    return 2;
+// the largest of the six separations: every comparison above is `separation < m2` (equivalent for non-NaN boxes;
+// a NaN box may only ADD a candidate, and candidates are re-tested exactly in the sweep)
+__device__ __forceinline__ float max_separation(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+    return fmaxf(fmaxf(fmaxf(alo.x - bhi.x, blo.x - ahi.x), fmaxf(alo.y - bhi.y, blo.y - ahi.y)),
+                 fmaxf(alo.z - bhi.z, blo.z - ahi.z));
 }
 
 constexpr int FP_THREADS = 256;   // bodies per tile = threads per CTA
@@ -555,9 +548,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 struct FindPairsSmem {
-    float4 abox[2 * FP_THREADS];  // AABBs of the tile's bodies (lo|tag, hi|rank), staged by TMA
-    uint32_t rstart[FP_NR];       // first candidate slot of range id = r * FP_THREADS + j
-    uint32_t roff[FP_NR + 1];     // exclusive scan of the range lengths: test t belongs to range id with roff[id] <= t
+    float4 abox[2 * FP_THREADS];  // AABB records of the tile's bodies, staged by TMA
+    uint32_t rstart[FP_NR];       // NON-EMPTY candidate ranges of the tile, compacted: first candidate slot,
+    uint32_t roff[FP_NR + 1];     //   exclusive scan of their lengths (test t belongs to range id, roff[id] <= t),
+    uint8_t rbody[FP_NR];         //   and the tile-local body the range belongs to
     uint4 stage[FP_WARPS][FP_WSTAGE];  // per-warp sweep-pair records waiting for the next flush
     uint2 wstage[FP_WARPS][FP_WSTAGE]; // per-warp watch-list entries
     uint32_t scan[33];
@@ -565,14 +559,19 @@ struct FindPairsSmem {
     uint64_t bar;
 };
 
-// Persistent CTAs; a tile is 256 consecutive slots (= bodies in cell order).  Per tile:
-//  1. one thread issues a TMA bulk copy of the tile's 8 KB of AABBs into shared memory; meanwhile every thread
-//     fetches the 10 cell-table entries of its body (independent loads) and publishes its 6 candidate ranges;
-//  2. a block scan over the 1536 range lengths flattens the tile's tests into [0, T);
-//  3. the tests are dealt out evenly, FP_BATCH consecutive tests per thread per batch (a thread finds its place
-//     with one binary search per batch and then walks): every lane is busy whatever the cell populations are;
+// K4.  Persistent CTAs; a tile is 256 consecutive slots (= bodies in cell order).  Per tile:
+//  1. one thread issues a TMA bulk copy of the tile's 8 KB of AABB records into shared memory; meanwhile every
+//     thread fetches the 10 cell-table entries of its body (independent loads) and derives its 6 candidate ranges:
+//     the rest of its own cell + the 13 forward neighbour cells are 5 contiguous runs of slots, + the big list;
+//  2. two block scans compact the non-empty ranges and flatten the tile's tests into [0, T);
+//  3. the tests are dealt out evenly, FP_BATCH consecutive tests per thread per batch (one binary search per
+//     batch, then a walk): every lane is busy whatever the cell populations are; the candidates' records of a
+//     batch are fetched back to back before any is tested;
 //  4. hits are staged per warp in shared memory and leave in bursts with ONE global atomic per flush; the warps
 //     of a CTA do not synchronise while they test.
+// A candidate (separation < m_a + m_b) within the inner margin becomes a sweep pair
+//   (a | static<<31, b | static<<31, rank_a | snapshot<<31, rank_b), a = earlier in iteration order,
+// the others go to the watch list.  S_snapshot flag: the exact test physics.rs:159-164 on the snapshot.
 __global__ void __launch_bounds__(FP_THREADS)
     k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
                  uint2* __restrict__ watch, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(FP_THREADS)
     const uint32_t tid = threadIdx.x;
     const uint32_t n = ctl->n;
     const GridParams g = ctl->grid;
-    const float mu = ctl->margin, mu_in = ctl->margin_in;
+    const float in_ratio = ctl->margin > 0.0f ? ctl->margin_in / ctl->margin : 1.0f;
     const uint32_t n_small = ctl->n_small;
     const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
     const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -630,6 +629,26 @@ __global__ void __launch_bounds__(FP_THREADS)
         if (lane == 0) *wwcnt = 0;
         __syncwarp();
     };
+    // one candidate: a = tile body (record from shared memory, slot pa), b = slot q
+    auto test = [&](const float4 alo, const float4 ahi, uint32_t pa, const float4 blo, const float4 bhi, uint32_t q) {
+        const float sep = max_separation(alo, ahi, blo, bhi);
+        const float m2 = box_margin(alo) + box_margin(blo);
+        if (!(sep < m2)) return;
+        const uint32_t sa = box_static(alo), sb = box_static(blo);
+        if (sa & sb) return;  // static-static: no-op in the reference (physics.rs:225)
+        const uint32_t ra = __float_as_uint(ahi.w), rb = __float_as_uint(bhi.w);
+        const bool a_first = ra < rb;  // pair order = the reference's iteration order
+        const uint32_t x = a_first ? (pa | sa) : (q | sb), y = a_first ? (q | sb) : (pa | sa);
+        if (sep < m2 * in_ratio) {
+            // physics.rs:159-164 on the snapshot (strict): the S_snapshot flag
+            const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z &&
+                              ahi.z > blo.z;
+            wstage[atomicAdd(wcnt, 1u)] =
+                make_uint4(x, y, (a_first ? ra : rb) | (snap ? TOPBIT : 0u), a_first ? rb : ra);
+        } else {
+            wwatch[atomicAdd(wwcnt, 1u)] = make_uint2(x, y);
+        }
+    };
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t p0 = tile * FP_THREADS;
@@ -637,17 +656,15 @@ __global__ void __launch_bounds__(FP_THREADS)
         if (tid == 0) tma_load_1d(sm.abox, sbox + 2 * (size_t)p0, valid * 32u, &sm.bar);
         const uint32_t p = p0 + tid;
         const bool live = tid < valid;
-        // the cell of body p: the AABB is needed for the key, read it straight from global (the TMA copy of the
-        // same lines is in flight; both are served by one L2 fill)
         uint32_t q0[FP_RANGES], len[FP_RANGES];
 #pragma unroll
         for (int r = 0; r < FP_RANGES; ++r) q0[r] = 0, len[r] = 0;
         if (live) {
             if (p < n_small) {
+                // the AABB is needed for the cell: read it straight from global (the TMA copy of the same lines is
+                // in flight; one L2 fill serves both).  Same expression as body_key() in K1: bit-identical cell.
                 const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
-                // same expression as body_key() in K1: bit-identical cell
                 const uint32_t k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
-                // forward half of the 27-neighbourhood = 5 contiguous runs of slots
                 const uint32_t e0 = LB[k + 2];
                 const uint32_t b1 = LB[k + row - 1], e1 = LB[k + row + 2];
                 const uint32_t b2 = LB[k + slab - row - 1], e2 = LB[k + slab - row + 2];
@@ -662,24 +679,52 @@ __global__ void __launch_bounds__(FP_THREADS)
             const uint32_t qb = max(p + 1, n_small);  // big list: every body tests the big bodies after it
             q0[5] = qb, len[5] = n > qb ? n - qb : 0u;
         }
+        // compact the non-empty ranges (thread-major order) and scan their lengths
+        uint32_t nne = 0;
+        unsigned long long sum64 = 0;
 #pragma unroll
-        for (int r = 0; r < FP_RANGES; ++r) {
-            sm.rstart[r * FP_THREADS + tid] = q0[r];
-            sm.roff[r * FP_THREADS + tid] = len[r];
+        for (int r = 0; r < FP_RANGES; ++r) nne += len[r] ? 1u : 0u, sum64 += len[r];
+        const bool dense = __syncthreads_or(sum64 > 0x400000ull);  // a degenerate tile (thousands of bodies per cell)
+        if (dense) {
+            // the flattened index would overflow: every thread walks its own ranges
+            const bool tma_ok = mbar_wait(&sm.bar, parity);
+            parity ^= 1u;
+            if (!tma_ok && tid == 0) atomicOr(&ctl->step_flags, SF_INTERNAL);
+            // warp-cooperative: the 32 lanes share the ranges of one body at a time
+#pragma unroll
+            for (int r = 0; r < FP_RANGES; ++r)
+                for (int L = 0; L < 32; ++L) {
+                    const uint32_t bq0 = __shfl_sync(0xffffffffu, q0[r], L), bln = __shfl_sync(0xffffffffu, len[r], L);
+                    if (bln == 0) continue;  // uniform across the warp
+                    const uint32_t j = warp * 32 + L;
+                    const float4 alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
+                    for (uint32_t o = 0; o < bln; o += 32) {
+                        const uint32_t q = bq0 + o + lane;
+                        if (o + lane < bln) test(alo, ahi, p0 + j, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
+                        __syncwarp();
+                        if (*wcnt > 32u) flush();
+                        if (*wwcnt > 32u) flush_watch();
+                    }
+                }
+            __syncthreads();
+            continue;
         }
-        __syncthreads();
-        // exclusive scan of the 1536 lengths: thread t owns ids [6t, 6t+6)
-        uint32_t l6[FP_RANGES], s6 = 0;
+        uint32_t Rn, T;
+        const uint32_t rbase = block_exclusive_scan_256(nne, &Rn, sm.scan);
+        uint32_t run = block_exclusive_scan_256((uint32_t)sum64, &T, sm.scan);
+        {
+            uint32_t w = rbase;
 #pragma unroll
-        for (int i = 0; i < FP_RANGES; ++i) l6[i] = sm.roff[FP_RANGES * tid + i], s6 += l6[i];
-        uint32_t T;
-        uint32_t run = block_exclusive_scan_256(s6, &T, sm.scan);  // (contains the barriers that order the rewrite)
-#pragma unroll
-        for (int i = 0; i < FP_RANGES; ++i) {
-            sm.roff[FP_RANGES * tid + i] = run;
-            run += l6[i];
+            for (int r = 0; r < FP_RANGES; ++r)
+                if (len[r]) {
+                    sm.rstart[w] = q0[r];
+                    sm.roff[w] = run;
+                    sm.rbody[w] = (uint8_t)tid;
+                    run += len[r];
+                    ++w;
+                }
+            if (tid == FP_THREADS - 1) sm.roff[Rn] = run;  // = T
         }
-        if (tid == FP_THREADS - 1) sm.roff[FP_NR] = run;
         const bool tma_ok = mbar_wait(&sm.bar, parity);
         parity ^= 1u;
         if (!tma_ok && tid == 0) atomicOr(&ctl->step_flags, SF_INTERNAL);
@@ -688,8 +733,9 @@ __global__ void __launch_bounds__(FP_THREADS)
         for (uint32_t tb = warp * 32 * FP_BATCH; tb < T; tb += FP_THREADS * FP_BATCH) {
             const uint32_t t0 = tb + lane * FP_BATCH;
             if (t0 < T) {
-                // range that holds test t0: largest id with roff[id] <= t0
-                uint32_t lo_i = 0, hi_i = FP_NR;
+                // range that holds test t0: largest id with roff[id] <= t0 (ranges are non-empty: roff is strictly
+                // increasing)
+                uint32_t lo_i = 0, hi_i = Rn;
                 while (hi_i - lo_i > 1) {
                     const uint32_t mid = (lo_i + hi_i) >> 1;
                     if (sm.roff[mid] <= t0) lo_i = mid; else hi_i = mid;
@@ -697,26 +743,30 @@ __global__ void __launch_bounds__(FP_THREADS)
                 uint32_t id = lo_i;
                 uint32_t end_t = sm.roff[id + 1];
                 uint32_t q = sm.rstart[id] + (t0 - sm.roff[id]);
-                uint32_t j = id & (FP_THREADS - 1);
-                float4 alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
-                float ea = box_extent(alo, ahi);
-                const uint32_t t1 = min(t0 + FP_BATCH, T);
-                for (uint32_t t = t0; t < t1; ++t, ++q) {
-                    if (t >= end_t) {
-                        do { ++id; end_t = sm.roff[id + 1]; } while (t >= end_t);  // skip empty ranges
-                        q = sm.rstart[id];
-                        j = id & (FP_THREADS - 1);
-                        alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
-                        ea = box_extent(alo, ahi);
+                const uint32_t nt = min((uint32_t)FP_BATCH, T - t0);
+                // where the tests of this batch live, then all their loads, then the tests
+                uint32_t qs[FP_BATCH], js[FP_BATCH];
+#pragma unroll
+                for (int u = 0; u < FP_BATCH; ++u) {
+                    if ((uint32_t)u < nt) {
+                        if (t0 + u >= end_t) {
+                            ++id;
+                            end_t = sm.roff[id + 1];
+                            q = sm.rstart[id];
+                        }
+                        qs[u] = q++;
+                        js[u] = sm.rbody[id];
+                    } else {
+                        qs[u] = qs[0], js[u] = js[0];
                     }
-                    const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-                    uint4 rec;
-                    const int kind = test_candidate(alo, ahi, ea, blo, bhi, mu, mu_in, rec);
-                    if (kind == 2)
-                        wstage[atomicAdd(wcnt, 1u)] = rec;
-                    else if (kind == 1)
-                        wwatch[atomicAdd(wwcnt, 1u)] = make_uint2(rec.x, rec.y);
                 }
+                float4 bl[FP_BATCH], bh[FP_BATCH];
+#pragma unroll
+                for (int u = 0; u < FP_BATCH; ++u) bl[u] = sbox[2 * (size_t)qs[u]], bh[u] = sbox[2 * (size_t)qs[u] + 1];
+#pragma unroll
+                for (int u = 0; u < FP_BATCH; ++u)
+                    if ((uint32_t)u < nt)
+                        test(sm.abox[2 * js[u]], sm.abox[2 * js[u] + 1], p0 + js[u], bl[u], bh[u], qs[u]);
             }
             __syncwarp();
             if (*wcnt > 32u) flush();  // the next batch adds at most 32 * FP_BATCH = 128 records
@@ -1103,9 +1153,9 @@ __global__ void __launch_bounds__(256)
         const float rx_now = dmax[x] * REACH_SLACK;
         if (!(rx_now > rx_prev)) continue;  // did not move further than in an earlier sweep
         const float4 alo = box[2 * (size_t)x], ahi = box[2 * (size_t)x + 1];
-        const float ma = mu * box_extent(alo, ahi);
+        const float ma = box_margin(alo);  // the very bits K4 used
         const float ra_old = fmaxf(ma, rx_prev), ra_new = fmaxf(ma, rx_now);
-        const uint32_t ta = __float_as_uint(alo.w), ra = __float_as_uint(ahi.w);
+        const uint32_t ta = x | box_static(alo), ra = __float_as_uint(ahi.w);
         // partner centres lie within the query box grown by the partner's own reach and half extent
         const float grow = (ra_new + partner_reach) * 1.001f + 0.5f * ext_max * 1.001f;
         int c0[3], c1[3];
@@ -1122,10 +1172,11 @@ __global__ void __launch_bounds__(256)
         }
         auto test = [&](uint32_t q) {
             const float4 blo = sbox[2 * (size_t)q], bhi = sbox[2 * (size_t)q + 1];
-            const uint32_t tb = __float_as_uint(blo.w);
-            const uint32_t y = tb & ~TOPBIT;
+            const uint32_t y = q;
+            const uint32_t tb = y | box_static(blo);
             if (y == x) return;
-            const float mb = mu * box_extent(blo, bhi);
+            if (ta & tb & TOPBIT) return;  // static-static (an escapee is dynamic; kept for symmetry)
+            const float mb = box_margin(blo);
             const float ry_prev = reach[y], ry_now = dmax[y] * REACH_SLACK;
             const float rb_old = fmaxf(mb, ry_prev), rb_new = fmaxf(rb_old, ry_now);
             if (inflated_overlap(alo, ahi, blo, bhi, ra_old + rb_old)) return;   // found in an earlier round / by K4

@@ -1,28 +1,23 @@
 #!/usr/bin/env python
-"""Top source lines by warp-stall samples: python tools/ncu_source.py rep.ncu-rep <kernel-substr> [launch-index]"""
-import csv, subprocess, sys, io, collections, re
+"""Per-source-line instruction / stall-sample shares of one kernel: python tools/ncu_source.py rep.ncu-rep <kernel-regex> [topN]"""
+import csv, subprocess, sys, io, collections
 rep, kname = sys.argv[1], sys.argv[2]
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kname] +
-                     (["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else ["--launch-count", "1"]),
-                     capture_output=True, text=True).stdout
-lines = out.splitlines()
-# find header row
-start = next(i for i, l in enumerate(lines) if l.startswith('"') and 'Source' in l)
-rows = list(csv.reader(io.StringIO("\n".join(lines[start:]))))
-hdr = rows[0]
-print(hdr[:12])
-def col(name):
-    for i, h in enumerate(hdr):
-        if h.strip() == name: return i
-    return None
-ci_src = col('Source'); ci_samp = col('# Samples') or col('Warp Stall Sampling (All Samples)') or col('Samples')
-print('cols', ci_src, ci_samp)
-agg = collections.Counter(); cur = None
-tot = 0
-for r in rows[1:]:
-    if len(r) <= max(ci_src, ci_samp or 0): continue
-    try: v = float(r[ci_samp].replace(',', '') or 0)
-    except: v = 0
-    agg[r[ci_src][:110]] += v; tot += v
-for k, v in agg.most_common(40):
-    print(f"{v:8.0f} {100*v/max(1,tot):5.1f}%  {k}")
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kname,
+                      "--launch-count", "1"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hi = next(i for i, r in enumerate(rows) if '# Samples' in r)
+hdr = rows[hi]
+ln, src = hdr.index('Line No'), hdr.index('Source')
+sa, ie = hdr.index('# Samples'), hdr.index('Instructions Executed')
+agg = collections.OrderedDict(); ts = ti = 0.0
+cur = ('?', '')
+for r in rows[hi + 1:]:
+    if len(r) <= max(sa, ie): continue
+    if r[ln].strip(): cur = (r[ln], r[src])
+    try: s = float(r[sa] or 0); i = float(r[ie] or 0)
+    except ValueError: continue
+    a = agg.setdefault(cur, [0.0, 0.0]); a[0] += i; a[1] += s; ts += s; ti += i
+print(f"total warp-instructions {ti:.0f}, stall samples {ts:.0f}")
+for (l, sline), (i, s) in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
+    print(f"{100*i/max(ti,1):5.1f}% inst {100*s/max(ts,1):5.1f}% stall  L{l}: {sline.strip()[:110]}")
