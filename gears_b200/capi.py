@@ -18,7 +18,7 @@ GP_FLAG_RECORD_PAIRS = 0x1
 GP_FLAG_NO_RETRY = 0x2
 GP_FLAG_PROFILE = 0x4
 GP_NUM_KERNEL_GROUPS = 8
-KERNEL_GROUPS = ["integrate", "radix_sort", "cells_gather", "find_pairs", "chains", "sweep", "finish", "exchange"]
+KERNEL_GROUPS = ["keys", "cell_scan", "scatter", "find_pairs", "chains", "sweep", "finish", "exchange"]
 GP_UNIQUE_ID_BYTES = 128
 
 f32p = C.POINTER(C.c_float)
@@ -40,7 +40,9 @@ class GpStepStats(C.Structure):
                 ("n_retries", C.c_uint32), ("margin", C.c_float), ("max_displacement", C.c_float),
                 ("cell_size", C.c_float), ("grid_dim", C.c_uint32 * 3), ("n_heavy", C.c_uint32),
                 ("n_migrated_out", C.c_uint32), ("n_migrated_in", C.c_uint32), ("n_halo_out", C.c_uint32),
-                ("n_halo_in", C.c_uint32), ("steps_total", C.c_uint64), ("steps_inexact", C.c_uint64)]
+                ("n_halo_in", C.c_uint32), ("steps_total", C.c_uint64), ("steps_inexact", C.c_uint64),
+                ("n_unverified", C.c_uint32), ("unverified_total", C.c_uint64), ("n_watch", C.c_uint32),
+                ("n_activated", C.c_uint32)]
 
     def as_dict(self):
         d = {}
@@ -48,6 +50,14 @@ class GpStepStats(C.Structure):
             v = getattr(self, name)
             d[name] = list(v) if hasattr(v, "__len__") else v
         return d
+
+
+class GpSlabConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_int32), ("nranks", C.c_int32), ("x_lo", C.c_float),
+                ("x_hi", C.c_float), ("halo", C.c_float), ("max_exchange", C.c_uint32), ("flags", C.c_uint32)]
+
+
+GP_SLAB_NO_VERIFY = 0x1
 
 
 class GpKernelTimes(C.Structure):
@@ -59,7 +69,7 @@ SYMBOLS = [
     "gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_upload", "gp_set_state", "gp_update_dirty",
     "gp_update_shape", "gp_step", "gp_step_async", "gp_sync", "gp_download", "gp_pairs", "gp_damping_factors",
     "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_kernel_times_read", "gp_comm_unique_id", "gp_comm_init",
-    "gp_owned_count", "gp_download_owned", "gp_test_radix_sort", "gp_test_radix_sort64", "gp_test_exclusive_scan",
+    "gp_comm_init_local", "gp_step_group", "gp_owned_count", "gp_download_owned", "gp_test_radix_sort", "gp_test_radix_sort64", "gp_test_exclusive_scan",
 ]
 
 _lib = None
@@ -113,11 +123,15 @@ def lib():
     L.gp_kernel_times_read.restype = C.c_int32
     L.gp_comm_unique_id.argtypes = [C.c_void_p]
     L.gp_comm_unique_id.restype = C.c_int32
-    L.gp_comm_init.argtypes = [vp, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float]
+    L.gp_comm_init.argtypes = [vp, C.c_void_p, C.POINTER(GpSlabConfig)]
     L.gp_comm_init.restype = C.c_int32
+    L.gp_comm_init_local.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(GpSlabConfig)]
+    L.gp_comm_init_local.restype = C.c_int32
+    L.gp_step_group.argtypes = [C.POINTER(vp), C.c_int32, C.c_float, C.c_void_p, C.c_uint32]
+    L.gp_step_group.restype = C.c_int32
     L.gp_owned_count.argtypes = [vp, u32p]
     L.gp_owned_count.restype = C.c_int32
-    L.gp_download_owned.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gp_download_owned.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_download_owned.restype = C.c_int32
     L.gp_test_radix_sort.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     L.gp_test_radix_sort.restype = C.c_int32

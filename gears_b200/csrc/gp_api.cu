@@ -41,6 +41,8 @@ struct gp_world {
     int cur = 0;
     float* ext = nullptr;
     uint32_t* slot_of = nullptr;  // body id -> current slot (rebuilt on demand: slots change every step)
+    uint32_t* entity_dev = nullptr;  // caller's entity ids as uploaded (become the body ids of a slab world)
+    bool have_entity = false;
     bool slot_valid = false;
     // broad phase
     float4* sbox = nullptr;       // world AABBs of the current step in cell order (lo|tag, hi|rank)
@@ -122,7 +124,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 static void free_all(gp_world* w) {
-    void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of,
+    void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of, w->entity_dev,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
                     w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
                     w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->moved_bits, w->esc_bits, w->watch, w->ctl, w->ctl_snap, w->d_small, w->stage};
@@ -236,6 +238,7 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     }
     CK(dmalloc(&w->ext, cap));
     CK(dmalloc(&w->slot_of, cap));
+    CK(dmalloc(&w->entity_dev, cap));
     CK(dmalloc(&w->sbox, 2 * (size_t)cap));
     CK(dmalloc(&w->key, cap));
     CK(dmalloc(&w->lrank, cap));
@@ -401,6 +404,10 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
         gp_status s = alloc_pairs(w, want_pairs);
         if (s != GP_OK) return s;
     }
+    if (w->multi) {  // a fresh upload starts a fresh (single-GPU) world; call gp_comm_init again for slabs
+        gp_multi_destroy(w->multi);
+        w->multi = nullptr;
+    }
     w->n = n;
     w->cur = 0;
     // stage host-layout arrays on the device, then pack
@@ -443,6 +450,8 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
             Bodies{w->B[0]}, w->A[0], w->ext, 0, nullptr);
         w->launches++;
         CK(cudaGetLastError());
+        w->have_entity = entity != nullptr;
+        if (entity) CK(cudaMemcpyAsync(w->entity_dev, sg + o_ent, 4 * (size_t)n, cudaMemcpyDeviceToDevice, w->st));
     }
     CK(cudaMemsetAsync(w->dmax, 0, sizeof(float) * (size_t)w->cap, w->st));
     CK(cudaMemsetAsync(w->reach, 0, sizeof(float) * (size_t)w->cap, w->st));
@@ -674,15 +683,21 @@ static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     return GP_OK;
 }
 
-// Enqueue the kernels of one step.  Reads set `cur`, leaves the result (in cell order) in set `cur^1`.
-static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch, int repair_rounds) {
-    cudaStream_t st = w->st;
-    float d[3];
+// One step = phase A (cell keys + histogram; on a slab also the packing of what the neighbours need), the slab
+// exchange (multi-GPU only, gp_multi_impl.cuh), phase B (everything else).  Reads set `cur`, leaves the result (in
+// cell order) in set `cur^1`.
+static void step_damping(float dt, const float* damp3, float* d) {
     if (damp3)
         d[0] = damp3[0], d[1] = damp3[1], d[2] = damp3[2];
     else
         gp_damping_factors(dt, d);
-    const int c = w->cur, o = c ^ 1;
+}
+
+static gp_status enqueue_phase_a(gp_world* w, float dt, const float* damp3) {
+    cudaStream_t st = w->st;
+    float d[3];
+    step_damping(dt, damp3, d);
+    const int c = w->cur;
     const uint32_t nb = n_bound(w);  // grids are sized for this; kernels stop at the device-resident counts
     prof_begin_step(w);
     w->slot_valid = false;
@@ -691,16 +706,41 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
         // K1 + K2: one-pass radix (bucket) sort by cell key: histogram with the keys, scan, scatter
         const uint32_t ncnt = w->max_cells + 2;  // counters: every cell of the finest grid + big list + dead
         CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
-        k_keys<<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB,
-                                              w->ctl, dt, d[0], d[1], d[2]);
-        w->launches++;
+        if (w->multi) {
+            k_keys<true><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
+                                                        gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), dt, d[0],
+                                                        d[1], d[2]);
+            k_seal_sends<<<1, 1, 0, st>>>(gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), w->ctl);
+            w->launches += 2;
+        } else {
+            k_keys<false><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
+                                                         nullptr, nullptr, dt, d[0], d[1], d[2]);
+            w->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return GP_OK;
+}
+
+static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int latch, int repair_rounds) {
+    cudaStream_t st = w->st;
+    float d[3];
+    step_damping(dt, damp3, d);
+    const int c = w->cur, o = c ^ 1;
+    const uint32_t nb = n_bound(w);
+    if (nb) {
+        if (w->multi) {
+            k_append<<<w->sm_count * 2, 256, 0, st>>>(gp_multi_recv(w->multi, 0), gp_multi_recv(w->multi, 1),
+                                                      Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl);
+            w->launches++;
+        }
         prof_mark(w, 1);
+        const uint32_t ncnt = w->max_cells + 2;
         exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
         prof_mark(w, 2);
         k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
-                                                       w->A[o], w->sbox,
-                                                       w->chain_cnt, w->perm, w->dmax, w->reach, w->moved_bits, w->esc_bits, w->LB,
-                                                       w->ctl, dt, d[0], d[1], d[2]);
+                                                       w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
+                                                       w->moved_bits, w->esc_bits, w->LB, w->ctl, dt, d[0], d[1], d[2]);
         w->launches += 1;
         prof_mark(w, 3);
         k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
@@ -708,9 +748,10 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
         w->launches += 1;
         prof_mark(w, 4);
         enqueue_chains_and_sweep(w, nullptr);
-        // speculative broad phase: look for pairs the margin missed, repair, look again
+        // speculative broad phase: look for pairs the candidate set missed, repair, look again
         enqueue_verify(w);
         for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
+        if (w->multi) gp_multi_enqueue_verification(w->multi);
     }
     prof_mark(w, 6);
     k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
@@ -720,10 +761,20 @@ static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int lat
     return GP_OK;
 }
 
+static gp_status enqueue_step(gp_world* w, float dt, const float* damp3, int latch, int repair_rounds) {
+    gp_status s = enqueue_phase_a(w, dt, damp3);
+    if (s != GP_OK) return s;
+    if (w->multi) {
+        s = gp_multi_enqueue_exchange(w->multi);
+        if (s != GP_OK) return s;
+    }
+    return enqueue_phase_b(w, dt, damp3, latch, repair_rounds);
+}
+
 static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
     gp_step_stats& s = w->last;
-    s.n_bodies = w->n;
-    s.n_big = w->n - std::min(c.n_small, w->n);
+    s.n_bodies = c.n;  // live bodies of the step (device-resident count; on a slab: owned + halo copies)
+    s.n_big = c.n - std::min(c.n_small, c.n);
     s.n_candidates = (uint64_t)c.n_pairs + c.n_watch - c.n_activated;
     s.n_snapshot = c.n_snapshot;
     s.n_contacts = c.n_contacts;
@@ -737,6 +788,13 @@ static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
     s.n_heavy = c.n_heavy;
     s.steps_total = w->steps_total;
     s.steps_inexact = c.steps_inexact;
+    s.n_migrated_out = c.n_migrated_out, s.n_migrated_in = c.n_migrated_in;
+    s.n_halo_out = c.n_sent[0] + c.n_sent[1] - c.n_migrated_out;
+    s.n_halo_in = c.n_recv - c.n_migrated_in;
+    s.n_unverified = c.n_unverified;
+    s.unverified_total = c.unverified_total;
+    s.n_watch = c.n_watch;
+    s.n_activated = c.n_activated;
     w->last_np = (uint32_t)std::min<uint64_t>(c.n_pairs, w->pair_cap);
 }
 
@@ -752,7 +810,11 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
     if (!w) return GP_ERR_BAD_ARG;
     if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_step before gp_upload");
     CK(cudaSetDevice(w->device));
-    if (w->multi) return gp_multi_step(w->multi, dt, damp3, stats);
+    if (w->multi) {  // slab worlds step asynchronously (the exchange is collective); failures latch
+        gp_status a = gp_step_async(w, dt, damp3, 1);
+        if (a != GP_OK) return a;
+        return gp_sync(w, stats);
+    }
     gp_status result = GP_OK;
     uint32_t retries = 0;
     float d[3];
@@ -826,7 +888,8 @@ extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, ui
     if (!w) return GP_ERR_BAD_ARG;
     if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_step_async before gp_upload");
     CK(cudaSetDevice(w->device));
-    if (w->multi) return gp_multi_step_async(w->multi, dt, damp3, nsteps);
+    if (w->multi && gp_multi_is_local(w->multi))
+        return fail(w, GP_ERR_STATE, "in-process slabs advance together: use gp_step_group");
     CK(cudaEventRecord(w->ev0, w->st));
     for (uint32_t s = 0; s < nsteps; ++s) {
         gp_status r = enqueue_step(w, dt, damp3, 1, REPAIR_ROUNDS_ENQUEUED);
@@ -842,7 +905,6 @@ extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, ui
 extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
     if (!w) return GP_ERR_BAD_ARG;
     CK(cudaSetDevice(w->device));
-    if (w->multi) return gp_multi_sync(w->multi, stats);
     if (!w->uploaded) {
         CK(cudaStreamSynchronize(w->st));
         return GP_OK;
@@ -858,6 +920,9 @@ extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
         Ctl* dc = w->ctl;
         CK(cudaMemsetAsync(&dc->sticky_flags, 0, sizeof(uint32_t), w->st));
         CK(cudaStreamSynchronize(w->st));
+        if (f & SF_EXCHANGE_OVERFLOW)
+            return fail(w, GP_ERR_CAPACITY, "%u async step(s) were inexact: a slab exchange buffer (max_exchange) or "
+                        "max_bodies was too small", c.steps_inexact);
         if (f & SF_PAIR_OVERFLOW)
             return fail(w, GP_ERR_PAIR_OVERFLOW, "%u async step(s) were inexact: candidate pairs exceeded max_pairs",
                         c.steps_inexact);
@@ -881,6 +946,7 @@ extern "C" gp_status gp_last_step_ms(gp_world* w, float* ms) {
 
 extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
     if (!w || !w->uploaded) return w ? fail(w, GP_ERR_STATE, "no bodies uploaded") : GP_ERR_BAD_ARG;
+    if (w->multi) return fail(w, GP_ERR_STATE, "gp_download addresses bodies by upload index; on a slab world use gp_download_owned");
     CK(cudaSetDevice(w->device));
     const uint32_t n = w->n;
     if (n == 0) return gp_sync(w, nullptr);

@@ -66,7 +66,19 @@ struct GridParams {
 struct Ctl {
     // device-resident body counts: kernels never take n from the host, so a step needs no host round trip even
     // when bodies arrive / leave between steps (multi-GPU slabs)
-    uint32_t n_in;            // bodies entering the step (live bodies of the last step + received ones)
+    uint32_t n_in;            // bodies entering the step = live bodies of the last step
+    uint32_t n_recv;          // + records received from the slab neighbours this step (appended behind n_in)
+    // multi-GPU slab along x: this rank owns the bodies whose AABB centre x lies in [x_lo, x_hi)
+    float x_lo, x_hi;
+    float halo;               // coverage H: the neighbour sends every body whose inflated AABB comes within H of the face
+    uint32_t has_left, has_right;
+    uint32_t xcap;            // records per exchange buffer
+    uint32_t cap;             // body capacity of the arrays
+    uint32_t n_sent[2];       // records packed for the left / right neighbour this step
+    uint32_t n_migrated_out, n_migrated_in;  // stats of the step
+    uint32_t n_unverified;    // owned bodies whose result could depend on a body this rank does not know (this step)
+    uint32_t unverified_total;  // summed over the async steps since the last sync
+    uint32_t taint_changed;
     uint32_t n;               // live bodies of the current step (set by K3 after the sort dropped dead keys)
     float margin;             // relative margin mu of the current step: body x's AABB is inflated by
                               // mu * (largest extent of x) in K4, and K6 verifies it never moves further
@@ -133,6 +145,7 @@ constexpr uint32_t SF_MARGIN = 2u;       // the candidate set was still growing 
 constexpr uint32_t SF_MARGIN_MAX = 4u;   // (unused)
 constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
 constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
+constexpr uint32_t SF_EXCHANGE_OVERFLOW = 128u;  // a slab exchange buffer or the body arrays were too small
 constexpr uint32_t SF_INTERNAL = 64u;     // a bounded wait expired (TMA copy never landed): result invalid
 
 // Body record (array of structures, 64 B = one DRAM burst): P = pos|mass, V = vel|restitution, Lo = min offset|id,
@@ -418,10 +431,34 @@ __device__ __forceinline__ uint32_t body_key(const GridParams& g, const float4 p
     return cell_key(g, (lx + hx) * 0.5f, (ly + hy) * 0.5f, (lz + hz) * 0.5f);
 }
 
+// Exchange buffer of a slab face: 16 B header {count, -, -, -} + records of five float4 (P, V, A, Lo, Hi) holding
+// the POST-integration state, flagged F_INTEGRATED (+ F_GHOST for halo copies; without it the record transfers
+// ownership = migration).
+constexpr uint32_t XREC = 5;  // float4 per record
+__device__ __forceinline__ void pack_record(float4* __restrict__ buf, uint32_t xcap, uint32_t* counter, Ctl* ctl,
+                                            const float4 p, const float4 v, float4 a, const float4 lo, const float4 hi,
+                                            uint32_t flags_out) {
+    cg::coalesced_group cgp = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (cgp.thread_rank() == 0) base = atomicAdd(counter, cgp.size());
+    base = cgp.shfl(base, 0);
+    const uint32_t slot = base + cgp.thread_rank();
+    if (slot >= xcap) {
+        atomicOr(&ctl->step_flags, SF_EXCHANGE_OVERFLOW);
+        return;
+    }
+    a.w = __uint_as_float(flags_out);
+    float4* r = buf + 1 + (size_t)slot * XREC;
+    r[0] = p, r[1] = v, r[2] = a, r[3] = lo, r[4] = hi;
+}
+
+// SLAB = true adds the multi-GPU duties: drop last step's ghosts, hand bodies whose centre left the slab to the
+// neighbour (they stay here as ghosts for this step) and copy bodies near a face into the neighbour's halo.
+template <bool SLAB>
 __global__ void __launch_bounds__(256)
-    k_keys(const Bodies B0, const float4* __restrict__ A, uint32_t* __restrict__ key,
-           uint32_t* __restrict__ lrank, uint32_t* __restrict__ cell_cnt, const Ctl* __restrict__ ctl, float dt,
-           float d16, float d18, float d35) {
+    k_keys(const Bodies B0, float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
+           uint32_t* __restrict__ cell_cnt, Ctl* __restrict__ ctl, float4* __restrict__ send_l,
+           float4* __restrict__ send_r, float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ctl->n_in) return;
     const GridParams g = ctl->grid;
@@ -429,11 +466,68 @@ __global__ void __launch_bounds__(256)
     const float4 a = A[i], lo = B0.Lo(i), hi = B0.Hi(i);
     const uint32_t flags = __float_as_uint(a.w);
     if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
-    const uint32_t k = body_key(g, p, lo, hi, flags);
+    uint32_t k = body_key(g, p, lo, hi, flags);
+    if (SLAB) {
+        if (flags & F_GHOST) {
+            k = g.ncells + 1u;  // last step's halo copy: its owner sends a fresh one if it is still near
+        } else if (!(flags & F_BIG)) {  // big (static) bodies are replicated on every rank and never travel
+            const float4 wlo = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, 0.f);
+            const float4 whi = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, 0.f);
+            const float cx = (wlo.x + whi.x) * 0.5f;
+            const float m = ctl->margin * box_extent(wlo, whi);  // the margin K3 will store for this body
+            const bool own_l = ctl->has_left && cx < ctl->x_lo, own_r = ctl->has_right && !(cx < ctl->x_hi);
+            const bool halo_l = ctl->has_left && wlo.x - m < ctl->x_lo + ctl->halo;
+            const bool halo_r = ctl->has_right && whi.x + m > ctl->x_hi - ctl->halo;
+            const uint32_t fl = (flags | F_INTEGRATED) & ~F_GHOST;
+            if (own_l || halo_l)
+                pack_record(send_l, ctl->xcap, &ctl->n_sent[0], ctl, p, v, a, lo, hi, own_l ? fl : (fl | F_GHOST));
+            if (own_r || halo_r)
+                pack_record(send_r, ctl->xcap, &ctl->n_sent[1], ctl, p, v, a, lo, hi, own_r ? fl : (fl | F_GHOST));
+            if (own_l || own_r) {
+                A[i].w = __uint_as_float(flags | F_GHOST);  // ownership moved: here it is a halo copy from now on
+                atomicAdd(&ctl->n_migrated_out, 1u);
+            }
+        }
+    }
     key[i] = k;
     // K2 is a one-pass radix sort whose single digit is the whole cell key: this is its histogram.  The bodies
     // arrive in last step's cell order, so the atomics of a warp fall on a few neighbouring L2 lines.
     lrank[i] = atomicAdd(&cell_cnt[k], 1u);
+}
+
+// the counts travel in the buffer header
+__global__ void k_seal_sends(float4* send_l, float4* send_r, const Ctl* ctl) {
+    if (send_l) send_l[0] = make_float4(__uint_as_float(min(ctl->n_sent[0], ctl->xcap)), 0.f, 0.f, 0.f);
+    if (send_r) send_r[0] = make_float4(__uint_as_float(min(ctl->n_sent[1], ctl->xcap)), 0.f, 0.f, 0.f);
+}
+
+// received records join the input set behind the bodies that were already here; their cell keys enter the
+// histogram before the scan
+__global__ void __launch_bounds__(256)
+    k_append(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, const Bodies B0,
+             float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
+             uint32_t* __restrict__ cell_cnt, Ctl* ctl) {
+    const uint32_t cl = recv_l ? min(__float_as_uint(recv_l[0].x), ctl->xcap) : 0u;
+    const uint32_t cr = recv_r ? min(__float_as_uint(recv_r[0].x), ctl->xcap) : 0u;
+    const uint32_t n_in = ctl->n_in;
+    uint32_t total = cl + cr;
+    if (n_in + total > ctl->cap) {
+        total = ctl->cap - n_in;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->step_flags, SF_EXCHANGE_OVERFLOW);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_recv = total;
+    const GridParams g = ctl->grid;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const float4* r = (t < cl) ? recv_l + 1 + (size_t)t * XREC : recv_r + 1 + (size_t)(t - cl) * XREC;
+        const float4 p = r[0], v = r[1], a = r[2], lo = r[3], hi = r[4];
+        const uint32_t s = n_in + t;
+        B0.P(s) = p, B0.V(s) = v, A[s] = a, B0.Lo(s) = lo, B0.Hi(s) = hi;
+        const uint32_t flags = __float_as_uint(a.w);
+        if (!(flags & F_GHOST)) atomicAdd(&ctl->n_migrated_in, 1u);
+        const uint32_t k = body_key(g, p, lo, hi, flags);  // the record is already integrated
+        key[s] = k;
+        lrank[s] = atomicAdd(&cell_cnt[k], 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -457,7 +551,7 @@ __global__ void __launch_bounds__(256)
         ctl->n_small = LB[ncells];
         ctl->n = LB[ncells + 1u];
     }
-    if (i >= ctl->n_in) return;
+    if (i >= ctl->n_in + ctl->n_recv) return;
     const uint32_t k = key[i];
     if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here
     const uint32_t s = LB[k] + lrank[i];
@@ -1312,7 +1406,8 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     Ctl c = *ctl;
     if (c.repair_needed) c.step_flags |= SF_MARGIN;
     if (latch == 1) {  // async stepping: failures are latched, the host looks later
-        if (c.step_flags & (SF_PAIR_OVERFLOW | SF_MARGIN | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW | SF_INTERNAL)) {
+        if (c.step_flags &
+            (SF_PAIR_OVERFLOW | SF_MARGIN | SF_HEAVY_OVERFLOW | SF_ESCAPEE_OVERFLOW | SF_INTERNAL | SF_EXCHANGE_OVERFLOW)) {
             c.steps_inexact += 1;
             c.sticky_flags |= c.step_flags;
         }
@@ -1320,6 +1415,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     }
     // the live set of an accepted step is the input of the next one (ghosts and departed bodies were dropped)
     if (latch == 1 || (latch == 0 && c.step_flags == 0)) c.n_in = c.n;
+    c.unverified_total += c.n_unverified;
     *snapshot_out = c;  // what the host reads (stats of THIS step)
     if (latch == 0 && c.step_flags == SF_MARGIN) return;  // sync mode: the host continues the repair loop
     // (latch == 2: the host gave up on this step; just reset)
@@ -1347,7 +1443,117 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.step_flags = 0;
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
     c.n_watch = 0, c.n_activated = 0, c.n_requeried = 0;
+    c.n_recv = 0, c.n_sent[0] = 0, c.n_sent[1] = 0, c.n_migrated_out = 0, c.n_migrated_in = 0, c.n_unverified = 0;
+    c.taint_changed = 0;
     *ctl = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab verification (multi-GPU).  A rank knows its own bodies and, per the halo rule, every neighbour body whose
+// inflated AABB comes within H of the shared face.  A body whose own reach (margin, or swept displacement if
+// larger) pokes beyond that coverage may have a partner this rank has never seen: it is TAINTED.  The result of a
+// body can only depend on bodies of its connected component of the candidate graph (sweep pairs + watch pairs), so
+// taint spreads over components; every owned body that stays clean is bit-identical to the single-GPU result
+// (multi-GPU exactness).  n_unverified counts the owned bodies that do not stay clean.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_taint_init(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
+                 const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits, const Ctl* ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->n) return;
+    const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
+    if (box_static(lo)) return;  // static bodies never change: nothing to get wrong
+    float r = box_margin(lo);
+    if ((moved_bits[i >> 5] >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(reach[i], dmax[i] * REACH_SLACK));
+    const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
+    const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
+    if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
+}
+
+__device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __restrict__ taint_bits, Ctl* ctl) {
+    if ((x | y) & TOPBIT) return;  // an edge through a static body carries nothing
+    const bool tx = (taint_bits[x >> 5] >> (x & 31u)) & 1u, ty = (taint_bits[y >> 5] >> (y & 31u)) & 1u;
+    if (tx == ty) return;
+    const uint32_t z = tx ? y : x;
+    atomicOr(&taint_bits[z >> 5], 1u << (z & 31u));
+    ctl->taint_changed = 1u;
+}
+
+__global__ void __launch_bounds__(256)
+    k_taint_propagate(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,
+                      uint32_t* __restrict__ taint_bits, Ctl* ctl, const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // the previous launch changed nothing: the fixed point is reached
+    const uint32_t np = min(ctl->n_pairs, pair_cap), nw = min(ctl->n_watch, pair_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t i = gtid; i < np; i += gsz) {
+        const uint4 r = pairs[2 * (size_t)i];
+        taint_edge(r.x, r.y, taint_bits, ctl);
+    }
+    for (uint32_t i = gtid; i < nw; i += gsz) {
+        const uint2 r = watch[i];
+        if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, ctl);  // (activated entries are among the pairs)
+    }
+}
+// between two propagation launches: remember whether the last one changed anything, arm the next
+__global__ void k_taint_roll(Ctl* ctl, uint32_t* scratch) {
+    scratch[0] = ctl->taint_changed;
+    ctl->taint_changed = 0;
+}
+
+__global__ void __launch_bounds__(256)
+    k_taint_count(const float4* __restrict__ A, const uint32_t* __restrict__ taint_bits, Ctl* ctl, int still_open) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    if (i < ctl->n) {
+        const uint32_t f = __float_as_uint(A[i].w);
+        const bool owned_dyn = !(f & (F_GHOST | F_STATIC));
+        // propagation did not reach its fixed point within the launches provided: nothing is verified
+        if (owned_dyn && (((taint_bits[i >> 5] >> (i & 31u)) & 1u) || (still_open && ctl->taint_changed))) c = 1;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->n_unverified, c);
+}
+
+// owned bodies (no halo copies; replicated big statics only on the rank that has no left neighbour) -> host layout
+__global__ void __launch_bounds__(256)
+    k_compact_owned(const Ctl* ctl, const Bodies B, const float4* __restrict__ A, int is_first_rank, uint32_t* counter,
+                    uint32_t* __restrict__ ids, float* __restrict__ pos3, float* __restrict__ vel3,
+                    const uint32_t* __restrict__ taint_bits, uint8_t* __restrict__ unverified) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->n_in) return;  // between steps n_in = the live bodies of the last step
+    const uint32_t f = __float_as_uint(A[i].w);
+    if (f & F_GHOST) return;
+    if ((f & F_BIG) && !is_first_rank) return;
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    const uint32_t s = base + g.thread_rank();
+    if (!ids) return;  // counting pass
+    const float4 p = B.P(i), v = B.V(i);
+    ids[s] = __float_as_uint(B.Lo(i).w);
+    pos3[3 * (size_t)s] = p.x, pos3[3 * (size_t)s + 1] = p.y, pos3[3 * (size_t)s + 2] = p.z;
+    vel3[3 * (size_t)s] = v.x, vel3[3 * (size_t)s + 1] = v.y, vel3[3 * (size_t)s + 2] = v.z;
+    if (taint_bits && unverified) unverified[s] = (taint_bits[i >> 5] >> (i & 31u)) & 1u;  // of the LAST step
+}
+
+// gp_comm_init: body ids become the caller's global entity ids; count what the faces would send right now
+__global__ void k_slab_prepare(uint32_t n, const Bodies B, const float4* __restrict__ A,
+                               const uint32_t* __restrict__ entity, uint32_t* __restrict__ counts /*[3]: L, R, dyn big*/,
+                               const Ctl* ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (entity) B.Lo(i).w = __uint_as_float(entity[i]);  // at upload slot == caller index
+    const uint32_t f = __float_as_uint(A[i].w);
+    if (f & F_BIG) {
+        if (!(f & F_STATIC)) atomicAdd(&counts[2], 1u);
+        return;
+    }
+    const float4 p = B.P(i), lo = B.Lo(i), hi = B.Hi(i);
+    const float wlo = lo.x + p.x, whi = hi.x + p.x;
+    const float m = whi - wlo;  // generous: a margin of one extent
+    if (ctl->has_left && wlo - m < ctl->x_lo + 2.0f * ctl->halo) atomicAdd(&counts[0], 1u);
+    if (ctl->has_right && whi + m > ctl->x_hi - 2.0f * ctl->halo) atomicAdd(&counts[1], 1u);
 }
 
 // ---- pair-set export (gp_pairs): compact flagged pairs into (key = rank_a<<32|rank_b, value = pair id) ----

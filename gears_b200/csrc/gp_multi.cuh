@@ -1,9 +1,13 @@
-// gp_multi.cuh — multi-GPU (spatial slab) extension: forward declarations used by gp_api.cu.
+// gp_multi.cuh — multi-GPU (spatial slab) extension: what gp_api.cu needs to know about it.
 #pragma once
+#include <cuda_runtime.h>
+
 #include "../../include/gears_physics_cuda.h"
 
 struct gp_multi;
 static void gp_multi_destroy(gp_multi* m);
-static gp_status gp_multi_step(gp_multi* m, float dt, const float* damp3, gp_step_stats* stats);
-static gp_status gp_multi_step_async(gp_multi* m, float dt, const float* damp3, uint32_t nsteps);
-static gp_status gp_multi_sync(gp_multi* m, gp_step_stats* stats);
+static float4* gp_multi_send(gp_multi* m, int side);  // side 0 = left neighbour, 1 = right; nullptr if none
+static float4* gp_multi_recv(gp_multi* m, int side);
+static gp_status gp_multi_enqueue_exchange(gp_multi* m);     // NCCL transport: send/recv on the step stream
+static void gp_multi_enqueue_verification(gp_multi* m);     // taint kernels (which owned bodies are provably exact)
+static bool gp_multi_is_local(gp_multi* m);

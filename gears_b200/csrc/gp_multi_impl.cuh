@@ -1,32 +1,384 @@
-// gp_multi_impl.cuh — multi-GPU slabs over NCCL send/recv (included at the end of gp_api.cu).
+// gp_multi_impl.cuh — multi-GPU slabs along x (included at the end of gp_api.cu; sees gp_world).
+//
+// One gp_world per GPU.  A rank owns the bodies whose AABB centre x lies in its slab [x_lo, x_hi).  Per step, on the
+// step stream and without any host synchronisation:
+//   K1 (k_keys<true>)  integrates, packs (a) bodies whose centre left the slab -> ownership moves to the neighbour,
+//                      (b) bodies whose inflated AABB comes within H of a face -> halo copies, into one fixed-size
+//                      buffer per face (count in the header);
+//   exchange           ncclSend/ncclRecv of the two buffers inside one ncclGroup (NVLink 5 / NVSwitch: both
+//                      neighbours at full bandwidth), or peer copies when all slabs live in one process;
+//   k_append           received records join the input set; the normal step follows (sort, pairs, sweep, repair);
+//   verification       taint kernels decide which owned bodies are provably identical to the single-GPU result.
+// The reference has no distributed runtime at all; this decomposition is new.
 #pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+// NCCL is bound at run time so that single-GPU users of the library do not need it installed.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static bool nccl_load(std::string* why) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return true;
+    // prefer a copy that is already in the process (e.g. the one torch.distributed loaded)
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        if (why) *why = std::string("libnccl.so.2 not found: ") + dlerror();
+        return false;
+    }
+    NcclApi a;
+    a.handle = h;
+#define GP_SYM(field, name)                                                      \
+    *(void**)(&a.field) = dlsym(h, name);                                        \
+    if (!a.field) {                                                              \
+        if (why) *why = std::string("NCCL symbol missing: ") + name;             \
+        return false;                                                            \
+    }
+    GP_SYM(GetUniqueId, "ncclGetUniqueId")
+    GP_SYM(CommInitRank, "ncclCommInitRank")
+    GP_SYM(CommDestroy, "ncclCommDestroy")
+    GP_SYM(GroupStart, "ncclGroupStart")
+    GP_SYM(GroupEnd, "ncclGroupEnd")
+    GP_SYM(Send, "ncclSend")
+    GP_SYM(Recv, "ncclRecv")
+    GP_SYM(GetErrorString, "ncclGetErrorString")
+#undef GP_SYM
+    g_nccl = a;
+    return true;
+}
 
 struct gp_multi {
-    gp_world* w;
+    gp_world* w = nullptr;
+    gp_slab_config cfg{};
+    bool local = false;            // all slabs in this process: peer copies instead of NCCL
+    ncclComm_t comm = nullptr;
+    gp_world* peer[2] = {nullptr, nullptr};  // local transport: left / right neighbour world
+    float4* send[2] = {nullptr, nullptr};
+    float4* recv[2] = {nullptr, nullptr};
+    size_t buf_bytes = 0;
+    uint32_t* taint_bits = nullptr;
+    uint32_t* scratch = nullptr;   // [0] taint gate, [1..3] prepare counts, [4] compact counter
+    cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
+    cudaEvent_t ev_copied = nullptr;   // local transport: this world has copied what it needs from its neighbours
+    bool verify = true;
 };
-static void gp_multi_destroy(gp_multi* m) { delete m; }
-static gp_status gp_multi_step(gp_multi* m, float, const float*, gp_step_stats*) {
-    return fail(m->w, GP_ERR_STATE, "multi-GPU stepping is not available in this build");
+
+static void gp_multi_destroy(gp_multi* m) {
+    if (!m) return;
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    for (int s = 0; s < 2; ++s) {
+        if (m->send[s]) cudaFree(m->send[s]);
+        if (m->recv[s]) cudaFree(m->recv[s]);
+    }
+    if (m->taint_bits) cudaFree(m->taint_bits);
+    if (m->scratch) cudaFree(m->scratch);
+    if (m->ev_packed) cudaEventDestroy(m->ev_packed);
+    if (m->ev_copied) cudaEventDestroy(m->ev_copied);
+    delete m;
 }
-static gp_status gp_multi_step_async(gp_multi* m, float, const float*, uint32_t) {
-    return fail(m->w, GP_ERR_STATE, "multi-GPU stepping is not available in this build");
+static bool gp_multi_is_local(gp_multi* m) { return m->local; }
+static float4* gp_multi_send(gp_multi* m, int side) { return m->send[side]; }
+static float4* gp_multi_recv(gp_multi* m, int side) { return m->recv[side]; }
+
+#define CKN(call)                                                                                             \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return fail(w, GP_ERR_NCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
+    gp_world* w = m->w;
+    if (m->local) return GP_OK;  // gp_step_group drives the copies of all worlds
+    const int rank = m->cfg.rank;
+    CKN(g_nccl.GroupStart());
+    // fixed-size messages (the count travels in the header): no host round trip to size them
+    if (m->send[0]) CKN(g_nccl.Send(m->send[0], m->buf_bytes, ncclChar, rank - 1, m->comm, w->st));
+    if (m->send[1]) CKN(g_nccl.Send(m->send[1], m->buf_bytes, ncclChar, rank + 1, m->comm, w->st));
+    if (m->recv[0]) CKN(g_nccl.Recv(m->recv[0], m->buf_bytes, ncclChar, rank - 1, m->comm, w->st));
+    if (m->recv[1]) CKN(g_nccl.Recv(m->recv[1], m->buf_bytes, ncclChar, rank + 1, m->comm, w->st));
+    CKN(g_nccl.GroupEnd());
+    return GP_OK;
 }
-static gp_status gp_multi_sync(gp_multi* m, gp_step_stats*) {
-    return fail(m->w, GP_ERR_STATE, "multi-GPU stepping is not available in this build");
+
+static const int TAINT_ROUNDS = 24;  // launches after the fixed point return at once
+static void gp_multi_enqueue_verification(gp_multi* m) {
+    gp_world* w = m->w;
+    if (!m->verify) return;
+    cudaStream_t st = w->st;
+    const uint32_t nb = w->cap;
+    cudaMemsetAsync(m->taint_bits, 0, sizeof(uint32_t) * ((size_t)nb / 32 + 1), st);
+    k_taint_init<<<cdiv(nb, 256), 256, 0, st>>>(w->sbox, w->dmax, w->reach, w->moved_bits, m->taint_bits, w->ctl);
+    for (int r = 0; r < TAINT_ROUNDS; ++r) {
+        k_taint_propagate<<<w->sm_count * 4, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->watch, m->taint_bits,
+                                                           w->ctl, r == 0 ? nullptr : m->scratch);
+        if (r + 1 < TAINT_ROUNDS) k_taint_roll<<<1, 1, 0, st>>>(w->ctl, m->scratch);
+    }
+    k_taint_count<<<cdiv(nb, 256), 256, 0, st>>>(w->A[w->cur ^ 1], m->taint_bits, w->ctl, 1);
+    w->launches += 2 * TAINT_ROUNDS + 1;
+}
+
+// common part of gp_comm_init / gp_comm_init_local
+static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) {
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_comm_init before gp_upload");
+    if (w->multi) return fail(w, GP_ERR_STATE, "this world already belongs to a slab decomposition");
+    if (!cfg || cfg->struct_size == 0 || cfg->struct_size > sizeof(gp_slab_config))
+        return fail(w, GP_ERR_BAD_ARG, "bad gp_slab_config");
+    gp_slab_config c{};
+    memcpy(&c, cfg, cfg->struct_size);
+    if (c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks) return fail(w, GP_ERR_BAD_ARG, "bad rank %d of %d", c.rank, c.nranks);
+    if (!(c.x_lo < c.x_hi)) return fail(w, GP_ERR_BAD_ARG, "empty slab [%g, %g)", c.x_lo, c.x_hi);
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->st));
+    CK(cudaMemcpy(w->h_ctl, w->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    Ctl hc = *w->h_ctl;
+    // coverage: three (largest grid-class extents) unless the caller says otherwise: about 2.5 layers of contact
+    // neighbours at the usual margins.  Too small a halo is not silent: the verification counts what it cannot prove.
+    if (!(c.halo > 0)) c.halo = 3.0f * hc.ext_max;
+    if (c.nranks > 1 && c.x_hi - c.x_lo < 2.0f * c.halo && c.rank > 0 && c.rank + 1 < c.nranks)
+        return fail(w, GP_ERR_BAD_ARG, "slab width %g is below twice the halo %g: a body could reach a rank two slabs away",
+                    c.x_hi - c.x_lo, c.halo);
+    gp_multi* m = new gp_multi();
+    m->w = w;
+    m->cfg = c;
+    m->local = local;
+    m->verify = !(c.flags & GP_SLAB_NO_VERIFY);
+    hc.x_lo = c.x_lo, hc.x_hi = c.x_hi, hc.halo = c.halo;
+    hc.has_left = c.rank > 0, hc.has_right = c.rank + 1 < c.nranks;
+    hc.cap = w->cap;
+    gp_status rs = GP_OK;
+    do {
+        if (dmalloc(&m->scratch, 16) || dmalloc(&m->taint_bits, (size_t)w->cap / 32 + 1) ||
+            cudaEventCreateWithFlags(&m->ev_packed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
+            rs = fail(w, GP_ERR_CUDA, "slab setup: out of device memory");
+            break;
+        }
+        cudaMemsetAsync(m->scratch, 0, 16 * sizeof(uint32_t), w->st);
+        cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st);
+        // body ids -> global entity ids; how many records would the faces send today?
+        const uint32_t* d_ent = w->have_entity ? (const uint32_t*)w->entity_dev : nullptr;
+        if (w->n) k_slab_prepare<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, Bodies{w->B[w->cur]}, w->A[w->cur], d_ent, m->scratch + 1, w->ctl);
+        w->launches++;
+        uint32_t counts[3] = {0, 0, 0};
+        if (cudaMemcpyAsync(counts, m->scratch + 1, sizeof counts, cudaMemcpyDeviceToHost, w->st) != cudaSuccess ||
+            cudaStreamSynchronize(w->st) != cudaSuccess) {
+            rs = fail(w, GP_ERR_CUDA, "slab setup: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (counts[2]) {
+            rs = fail(w, GP_ERR_BAD_ARG, "%u dynamic bodies are larger than the grid cell: big bodies must be static "
+                      "(they are replicated on every rank)", counts[2]);
+            break;
+        }
+        uint32_t xcap = c.max_exchange;
+        if (xcap == 0) xcap = 2u * std::max(counts[0], counts[1]) + 8192u;
+        m->cfg.max_exchange = xcap;
+        hc.xcap = xcap;
+        cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st);
+        m->buf_bytes = sizeof(float4) * (1 + (size_t)xcap * XREC);
+        for (int s = 0; s < 2; ++s) {
+            const bool has = s == 0 ? hc.has_left : hc.has_right;
+            if (!has) continue;
+            if (dmalloc(&m->send[s], m->buf_bytes / sizeof(float4)) || dmalloc(&m->recv[s], m->buf_bytes / sizeof(float4))) {
+                rs = fail(w, GP_ERR_CUDA, "slab setup: out of device memory for the exchange buffers");
+                break;
+            }
+            cudaMemsetAsync(m->send[s], 0, sizeof(float4), w->st);
+            cudaMemsetAsync(m->recv[s], 0, sizeof(float4), w->st);
+        }
+        if (rs != GP_OK) break;
+        if (cudaStreamSynchronize(w->st) != cudaSuccess) rs = fail(w, GP_ERR_CUDA, "slab setup failed");
+    } while (0);
+    if (rs != GP_OK) {
+        gp_multi_destroy(m);
+        return rs;
+    }
+    w->multi = m;
+    return GP_OK;
 }
 
 extern "C" gp_status gp_comm_unique_id(uint8_t id[GP_UNIQUE_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= GP_UNIQUE_ID_BYTES, "unique id does not fit");
     memset(id, 0, GP_UNIQUE_ID_BYTES);
-    return GP_ERR_NCCL;
-}
-extern "C" gp_status gp_comm_init(gp_world* w, const uint8_t*, int32_t, int32_t, float, float) {
-    return fail(w, GP_ERR_NCCL, "multi-GPU slabs are not available in this build");
-}
-extern "C" gp_status gp_owned_count(gp_world* w, uint32_t* n) {
-    if (!w || !n) return GP_ERR_BAD_ARG;
-    *n = w->n;
+    std::string why;
+    if (!nccl_load(&why)) {
+        fail(nullptr, GP_ERR_NCCL, "%s", why.c_str());
+        return GP_ERR_NCCL;
+    }
+    ncclUniqueId uid;
+    if (g_nccl.GetUniqueId(&uid) != ncclSuccess) return GP_ERR_NCCL;
+    memcpy(id, &uid, sizeof uid);
     return GP_OK;
 }
-extern "C" gp_status gp_download_owned(gp_world* w, uint32_t*, float*, float*) {
-    return fail(w, GP_ERR_STATE, "multi-GPU slabs are not available in this build");
+
+extern "C" gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYTES], const gp_slab_config* cfg) {
+    if (!w || !id) return GP_ERR_BAD_ARG;
+    std::string why;
+    if (!nccl_load(&why)) return fail(w, GP_ERR_NCCL, "%s", why.c_str());
+    gp_status s = slab_setup(w, cfg, false);
+    if (s != GP_OK) return s;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    CK(cudaSetDevice(w->device));
+    ncclResult_t r = g_nccl.CommInitRank(&w->multi->comm, w->multi->cfg.nranks, uid, w->multi->cfg.rank);
+    if (r != ncclSuccess) {
+        gp_multi_destroy(w->multi);
+        w->multi = nullptr;
+        return fail(w, GP_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    return GP_OK;
+}
+
+extern "C" gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, const gp_slab_config* cfgs) {
+    if (!worlds || !cfgs || n < 1) return GP_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i) {
+        if (!worlds[i]) return GP_ERR_BAD_ARG;
+        if (cfgs[i].rank != i || cfgs[i].nranks != n)
+            return fail(worlds[i], GP_ERR_BAD_ARG, "gp_comm_init_local: cfgs[%d] must have rank %d of %d", i, i, n);
+    }
+    for (int i = 0; i < n; ++i) {
+        gp_status s = slab_setup(worlds[i], &cfgs[i], true);
+        if (s != GP_OK) {
+            for (int j = 0; j < i; ++j) gp_multi_destroy(worlds[j]->multi), worlds[j]->multi = nullptr;
+            return s;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        gp_multi* m = worlds[i]->multi;
+        m->peer[0] = i > 0 ? worlds[i - 1] : nullptr;
+        m->peer[1] = i + 1 < n ? worlds[i + 1] : nullptr;
+        if ((m->peer[0] && m->peer[0]->multi->buf_bytes < 16) || (m->peer[1] && m->peer[1]->multi->buf_bytes < 16))
+            return fail(worlds[i], GP_ERR_STATE, "neighbour without exchange buffers");
+    }
+    // both sides of a face must agree on the message size
+    for (int i = 0; i + 1 < n; ++i) {
+        gp_multi *a = worlds[i]->multi, *b = worlds[i + 1]->multi;
+        if (a->cfg.max_exchange != b->cfg.max_exchange)
+            return fail(worlds[i], GP_ERR_BAD_ARG, "max_exchange differs across a face (%u vs %u): pass the same value to all ranks",
+                        a->cfg.max_exchange, b->cfg.max_exchange);
+    }
+    return GP_OK;
+}
+
+// In-process slabs: all worlds advance in lock step; the exchange is a peer copy ordered by events.
+extern "C" gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt, const float* damp3, uint32_t nsteps) {
+    if (!worlds || n < 1) return GP_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i)
+        if (!worlds[i] || !worlds[i]->multi || !worlds[i]->multi->local)
+            return worlds[i] ? fail(worlds[i], GP_ERR_STATE, "gp_step_group needs worlds set up by gp_comm_init_local") : GP_ERR_BAD_ARG;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        for (int i = 0; i < n; ++i) {
+            gp_world* w = worlds[i];
+            gp_multi* m = w->multi;
+            CK(cudaSetDevice(w->device));
+            if (s == 0) CK(cudaEventRecord(w->ev0, w->st));
+            // the neighbours must have finished copying out of my send buffers (previous step) before I refill them
+            for (int side = 0; side < 2; ++side)
+                if (m->peer[side]) CK(cudaStreamWaitEvent(w->st, m->peer[side]->multi->ev_copied, 0));
+            gp_status r = enqueue_phase_a(w, dt, damp3);
+            if (r != GP_OK) return r;
+            CK(cudaEventRecord(m->ev_packed, w->st));
+        }
+        for (int i = 0; i < n; ++i) {
+            gp_world* w = worlds[i];
+            gp_multi* m = w->multi;
+            CK(cudaSetDevice(w->device));
+            for (int side = 0; side < 2; ++side) {
+                gp_world* p = m->peer[side];
+                if (!p) continue;
+                CK(cudaStreamWaitEvent(w->st, p->multi->ev_packed, 0));
+                // my left neighbour's RIGHT send buffer is my left receive buffer, and vice versa
+                CK(cudaMemcpyPeerAsync(m->recv[side], w->device, p->multi->send[side ^ 1], p->device, m->buf_bytes, w->st));
+            }
+            CK(cudaEventRecord(m->ev_copied, w->st));
+        }
+        for (int i = 0; i < n; ++i) {
+            gp_world* w = worlds[i];
+            CK(cudaSetDevice(w->device));
+            gp_status r = enqueue_phase_b(w, dt, damp3, 1, REPAIR_ROUNDS_ENQUEUED);
+            if (r != GP_OK) return r;
+            w->cur ^= 1;
+            w->steps_total++;
+            if (s + 1 == nsteps) {
+                CK(cudaEventRecord(w->ev1, w->st));
+                w->timed = true;
+            }
+        }
+    }
+    return GP_OK;
+}
+
+static gp_status count_owned(gp_world* w, uint32_t* n) {
+    gp_multi* m = w->multi;
+    CK(cudaMemsetAsync(m->scratch + 4, 0, sizeof(uint32_t), w->st));
+    k_compact_owned<<<cdiv(w->cap, 256), 256, 0, w->st>>>(w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur], m->cfg.rank == 0,
+                                                           m->scratch + 4, nullptr, nullptr, nullptr, nullptr, nullptr);
+    w->launches++;
+    CK(cudaMemcpyAsync(n, m->scratch + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_owned_count(gp_world* w, uint32_t* n) {
+    if (!w || !n) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "no bodies uploaded");
+    if (!w->multi) {
+        *n = w->n;
+        return GP_OK;
+    }
+    CK(cudaSetDevice(w->device));
+    return count_owned(w, n);
+}
+
+// entity ids + state of the bodies this rank owns now (after migration), in no particular order
+extern "C" gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified) {
+    if (!w || !entity || !pos3 || !vel3) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "no bodies uploaded");
+    CK(cudaSetDevice(w->device));
+    uint32_t n = 0;
+    if (w->multi) {
+        gp_status s = count_owned(w, &n);
+        if (s != GP_OK) return s;
+    } else {
+        n = w->n;
+    }
+    if (n == 0) return gp_sync(w, nullptr);
+    const size_t b3 = 3 * sizeof(float) * (size_t)n, a3 = (b3 + 255) & ~(size_t)255, bi = ((size_t)n * 4 + 255) & ~(size_t)255;
+    gp_status s = ensure_stage(w, 2 * a3 + 2 * bi + 256);
+    if (s != GP_OK) return s;
+    float* dp = (float*)w->stage;
+    float* dv = (float*)(w->stage + a3);
+    uint32_t* di = (uint32_t*)(w->stage + 2 * a3);
+    uint8_t* du = (uint8_t*)(w->stage + 2 * a3 + bi);
+    CK(cudaMemsetAsync(du, 0, n, w->st));
+    if (w->multi) {
+        CK(cudaMemsetAsync(w->multi->scratch + 4, 0, sizeof(uint32_t), w->st));
+        k_compact_owned<<<cdiv(w->cap, 256), 256, 0, w->st>>>(w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur],
+                                                               w->multi->cfg.rank == 0, w->multi->scratch + 4, di, dp, dv,
+                                                               w->multi->verify && w->steps_total ? w->multi->taint_bits : nullptr, du);
+    } else {
+        k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, dp, dv, di, 0);
+    }
+    w->launches++;
+    CK(cudaMemcpyAsync(pos3, dp, b3, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaMemcpyAsync(vel3, dv, b3, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaMemcpyAsync(entity, di, (size_t)n * 4, cudaMemcpyDeviceToHost, w->st));
+    if (unverified) CK(cudaMemcpyAsync(unverified, du, n, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return gp_sync(w, nullptr);
 }

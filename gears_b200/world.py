@@ -153,6 +153,17 @@ class PhysicsWorld:
         self._check(self._lib.gp_download(self._h, _ptr(pos), _ptr(vel)))
         return pos, vel
 
+    def download_owned(self):
+        """(entity, pos, vel) of the bodies this world owns now (slab worlds: after migration; no halo copies)."""
+        n = C.c_uint32()
+        self._check(self._lib.gp_owned_count(self._h, C.byref(n)))
+        k = max(1, n.value)
+        ent, pos, vel = np.zeros(k, np.uint32), np.zeros((k, 3), np.float32), np.zeros((k, 3), np.float32)
+        unv = np.zeros(k, np.uint8)
+        self._check(self._lib.gp_download_owned(self._h, _ptr(ent), _ptr(pos), _ptr(vel), _ptr(unv)))
+        self.last_unverified = unv[: n.value]
+        return ent[: n.value], pos[: n.value], vel[: n.value]
+
     def pairs(self, which: int) -> np.ndarray:
         n = C.c_uint64()
         self._check(self._lib.gp_pairs(self._h, which, None, 0, C.byref(n)))

@@ -88,6 +88,12 @@ typedef struct gp_step_stats {
     uint32_t n_migrated_out, n_migrated_in, n_halo_out, n_halo_in; /* multi-GPU only               */
     uint64_t steps_total;    /* steps since upload                                                    */
     uint64_t steps_inexact;  /* async steps (gp_step_async) that hit GP_ERR_MARGIN/PAIR_OVERFLOW      */
+    uint32_t n_unverified;   /* multi-GPU: owned bodies of this step whose result could depend on a   */
+                             /* body this rank has not seen (0 = the step is provably identical to    */
+                             /* the single-GPU result)                                                */
+    uint64_t unverified_total; /* the same, summed over the steps since the last gp_sync             */
+    uint32_t n_watch;        /* candidates that only went on the watch list (lazy candidates)         */
+    uint32_t n_activated;    /* watch pairs that had to join the sweep                                */
 } gp_step_stats;
 
 /* ---- lifetime ---- */
@@ -156,22 +162,47 @@ uint64_t gp_kernel_launches(const gp_world* w);
 #define GP_NUM_KERNEL_GROUPS 8
 typedef struct gp_kernel_times {
     uint32_t steps;                       /* steps covered by the sums                                */
-    float ms[GP_NUM_KERNEL_GROUPS];       /* 0 integrate (K1), 1 radix sort (K2), 2 cell table+gather  */
-                                          /* (K3), 3 pair find (K4), 4 chain build (K5: scan, fill,    */
-                                          /* sort), 5 contact sweep (K6), 6 finish, 7 exchange (multi) */
+    float ms[GP_NUM_KERNEL_GROUPS];       /* 0 cell keys + histogram (K1; on a slab also packing),     */
+                                          /* 1 cell scan (K2; on a slab also append), 2 scatter into    */
+                                          /* cell order + integrate + AABBs (K3), 3 pair find (K4),     */
+                                          /* 4 chain build (K5: scan, fill, sort+link), 5 contact sweep */
+                                          /* + verification + repair rounds (K6), 6 finish, 7 unused    */
     uint32_t launches[GP_NUM_KERNEL_GROUPS]; /* kernel launches per group over those steps            */
 } gp_kernel_times;
 gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
 
-/* ---- multi-GPU: spatial slabs along x, one handle per GPU / process, NCCL point-to-point ---- */
+/* ---- multi-GPU: spatial slabs along x, one gp_world per GPU ----
+ * The reference is a single process (no collectives of any kind); this decomposition is new.
+ * A rank owns the bodies whose AABB centre x lies in [x_lo, x_hi) (use -INFINITY / +INFINITY at the two ends).
+ * Upload each rank's bodies with gp_upload (entity = GLOBAL ids, rank = GLOBAL iteration ranks; big static bodies
+ * such as a floor are uploaded on EVERY rank), then attach the worlds:
+ *   - one process per GPU:   gp_comm_unique_id on rank 0, broadcast it, gp_comm_init on every rank (collective);
+ *                            then gp_step_async / gp_sync as usual: every step exchanges migrating bodies and halo
+ *                            copies with the two neighbours by ncclSend/ncclRecv on the step stream;
+ *   - one process, n worlds: gp_comm_init_local, then gp_step_group (peer copies instead of NCCL; the worlds may
+ *                            even share a device, which is how the slab logic is tested on one GPU).
+ * Per-index calls (gp_set_state, gp_update_dirty, gp_update_shape, gp_download) are not available on a slab world;
+ * read results with gp_owned_count / gp_download_owned. */
 #define GP_UNIQUE_ID_BYTES 128
+#define GP_SLAB_NO_VERIFY 0x1u /* skip the per-step proof that owned bodies cannot depend on unseen bodies */
+typedef struct gp_slab_config {
+    uint32_t struct_size;  /* = sizeof(gp_slab_config)                                                      */
+    int32_t rank, nranks;  /* slab index along x, number of slabs                                           */
+    float x_lo, x_hi;      /* this rank's slab                                                              */
+    float halo;            /* coverage H beyond a face that the neighbour mirrors; <=0 = 3 x the largest    */
+                           /* grid-class extent.  Inner slabs must be >= 2 H wide                            */
+    uint32_t max_exchange; /* records per face buffer; 0 = 2 x (bodies within 2 H of a face today) + 8192.   */
+                           /* Both sides of a face must use the same value (messages have a fixed size)     */
+    uint32_t flags;        /* GP_SLAB_*                                                                     */
+} gp_slab_config;
 gp_status gp_comm_unique_id(uint8_t id[GP_UNIQUE_ID_BYTES]);
-/* Collective over all ranks.  slab = [x_lo, x_hi): this rank owns bodies whose AABB centre x lies in it. */
-gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks,
-                       float x_lo, float x_hi);
-/* global ids of the bodies currently owned by this rank, in device order (after migration) */
+gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYTES], const gp_slab_config* cfg);
+gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, const gp_slab_config* cfgs);
+gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt, const float* damp3, uint32_t nsteps);
+/* bodies owned by this rank now (after migration); arrays of gp_owned_count elements, in no particular order.
+ * unverified (nullable): 1 for a body the LAST step could not prove independent of unseen bodies. */
 gp_status gp_owned_count(gp_world* w, uint32_t* n);
-gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3);
+gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified);
 
 /* ---- test hooks (used by tests/ only; stable but not part of the drop-in surface) ---- */
 gp_status gp_test_radix_sort(int32_t device, uint32_t n, uint32_t key_bits, uint32_t* keys_inout,

@@ -1,0 +1,131 @@
+"""Multi-GPU slab decomposition, exercised on ONE GPU: n slab worlds in one process (gp_comm_init_local +
+gp_step_group, peer copies instead of NCCL).  The acceptance bar: every owned body the verification does not flag is
+bit-identical to the single-world result, and on these scenes nothing is flagged."""
+import numpy as np
+import pytest
+
+from gears_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+DT = np.float32(1.0) / np.float32(60.0)
+
+
+def single_world_result(scene, steps, **kw):
+    from gears_b200.world import PhysicsWorld
+    with PhysicsWorld(**kw) as w:
+        w.upload(scene)
+        w.step_async(DT, steps)
+        st = w.sync()
+        assert st["steps_inexact"] == 0
+        pos, vel = w.download()
+    return pos, vel
+
+
+def assert_same_bits(a, b, what):
+    a = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, np.float32).view(np.uint32)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} words differ, first at {bad[0]}")
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_local_slabs_bit_exact_vs_single_world(nranks):
+    """BASELINE config 4 in miniature (same number density 0.05): slabs + halo + migration, checked every step."""
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import PhysicsWorld
+    s = scenes.uniform(60_000, L=106.0, seed=101, rank_seed=102)
+    n = s["pos"].shape[0]
+    steps = 12
+    with PhysicsWorld() as w, LocalSlabs(s, nranks, halo=6.0) as g:
+        w.upload(s)
+        mig = halo = unverified = 0
+        for k in range(steps):
+            w.step(DT)
+            ref_pos, ref_vel = w.download()
+            g.step(DT, 1)
+            for st in g.sync():
+                mig += st["n_migrated_out"]
+                halo += st["n_halo_in"]
+                unverified += st["n_unverified"]
+                assert st["steps_inexact"] == 0
+            ent, pos, vel = g.download()
+            assert len(ent) == n and np.array_equal(ent, np.arange(n, dtype=np.uint32)), "every body owned exactly once"
+            assert_same_bits(pos, ref_pos, f"pos after step {k + 1}")
+            assert_same_bits(vel, ref_vel, f"vel after step {k + 1}")
+    assert mig > 0 and halo > 0, "the scene must exercise migration and the halo"
+    assert unverified == 0, "with a 6-extent halo every owned body is provably independent of unseen bodies"
+
+
+def test_unflagged_bodies_are_exact_in_a_dense_scene():
+    """Denser scene, default halo: a few bodies cannot be proven independent; every body that differs from the
+    single-world result (if any) must be among the flagged ones."""
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import PhysicsWorld
+    s = scenes.uniform(60_000, L=90.0, seed=101, rank_seed=102)
+    with PhysicsWorld() as w, LocalSlabs(s, 3) as g:
+        w.upload(s)
+        flagged_total = 0
+        for k in range(8):
+            w.step(DT)
+            ref_pos, ref_vel = w.download()
+            g.step(DT, 1)
+            g.sync()
+            ent, pos, vel = g.download()
+            u = g.last_unverified
+            bad = (pos.view(np.uint32) != ref_pos.view(np.uint32)).any(axis=1) | \
+                  (vel.view(np.uint32) != ref_vel.view(np.uint32)).any(axis=1)
+            assert not (bad & (u == 0)).any(), f"step {k + 1}: an unflagged body differs from the single-world result"
+            flagged_total += int(u.sum())
+            if bad.any():
+                break  # from here on the inputs of the two runs differ
+        assert flagged_total < 8 * 600  # a small minority of the 60k bodies
+
+
+def test_local_slabs_async_batches_and_equal_width_faces():
+    from gears_b200.slabs import LocalSlabs
+    s = scenes.uniform(30_000, L=84.0, seed=111, rank_seed=None)  # identity ranks, number density 0.05
+    n = s["pos"].shape[0]
+    ref_pos, ref_vel = single_world_result(s, 20)
+    with LocalSlabs(s, 3, mode="width", halo=6.0) as g:
+        g.step(DT, 20)  # twenty steps enqueued without any host synchronisation
+        sts = g.sync()
+        assert sum(st["unverified_total"] for st in sts) == 0
+        assert all(st["steps_inexact"] == 0 for st in sts)
+        ent, pos, vel = g.download()
+    assert np.array_equal(ent, np.arange(n, dtype=np.uint32))
+    assert_same_bits(pos, ref_pos, "pos")
+    assert_same_bits(vel, ref_vel, "vel")
+
+
+def test_too_small_halo_is_reported_not_hidden():
+    from gears_b200.slabs import LocalSlabs
+    s = scenes.uniform(40_000, L=60.0, seed=121, rank_seed=122)  # denser: contact chains cross the faces
+    with LocalSlabs(s, 2, halo=0.05) as g:  # far less than one body extent
+        g.step(DT, 5)
+        sts = g.sync()
+        assert sum(st["unverified_total"] for st in sts) > 0
+
+
+def test_pile_across_a_face_counts_what_it_cannot_prove():
+    # a settling pile is one big contact component: the slabs cannot prove independence, and must say so
+    from gears_b200.slabs import LocalSlabs
+    s = scenes.pile(16, 8, 8)
+    with LocalSlabs(s, 2) as g:
+        g.step(DT, 3)
+        sts = g.sync()
+        assert sum(st["unverified_total"] for st in sts) > 0
+        ent, pos, vel = g.download()
+        assert len(np.unique(ent)) == s["pos"].shape[0]
+
+
+def test_slab_world_rejects_per_index_calls():
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import GpError
+    s = scenes.uniform(5_000, L=40.0, seed=131)
+    with LocalSlabs(s, 2) as g:
+        with pytest.raises(GpError):
+            g.worlds[0].download()
+        with pytest.raises(GpError):
+            g.worlds[0].step_async(DT, 1)  # in-process slabs advance together
