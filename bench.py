@@ -29,6 +29,10 @@ if ROOT not in sys.path:
 from gears_b200 import scenes  # noqa: E402
 
 DT = np.float32(1.0) / np.float32(60.0)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's main kernel, from the ncu --set full capture
+# under profiles/ (uniform_16M, 1 GPU); None = not captured for that group
+NCU_TRAFFIC = {"find_pairs": 942e6, "scatter": 3.78e9, "keys": 1.73e9}
+
 WORKLOADS = {
     # name: (generator kwargs, world kwargs)
     "uniform_16M": (dict(kind="uniform", n=16_777_216, L=695.0, seed=1003, rank_seed=2003),
@@ -103,17 +107,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(n: int, passes: int, st: dict) -> dict:
-    """Useful bytes per launch group for ONE step (SURVEY §8d contract, our layout)."""
-    cand, contacts = st["n_candidates"], st["n_contacts"]
+def algorithmic_bytes(n: int, st: dict) -> dict:
+    """Useful bytes per launch group for ONE step (every array counted once per kernel that
+    needs it, cache re-reads not counted)."""
     ncells = st["grid_dim"][0] * st["grid_dim"][1] * st["grid_dim"][2]
+    nw = st["n_watch"]
+    npairs = max(0, st["n_candidates"] - nw + st["n_activated"])   # pairs that entered the sweep
+    c, r = st["n_contacts"], st["n_retries"]
     return {
-        "integrate": 152 * n,                       # R 80 (P,V,A,Lo,Hi) + W 32 (P',V') + W 32 (box) + W 4 key + W 4 chain counter
-        "radix_sort": (20 * passes - 4) * n,        # per pass: upsweep R 4, downsweep R 8 + W 8 (first pass reads no values)
-        "cells_gather": 72 * n + 4 * (ncells + 2),  # R 8 (key,val) + R 32 (box gather) + W 32 (sbox) + cell table
-        "find_pairs": 36 * n + 20 * cand,           # R 4 key + R 32 own box; W 16 pair + 4 pending per candidate
-        "chains": 12 * n + 40 * cand,               # scan R 8 + W 4 per body; fill R 16 + W 16, sort R/W ~8 per pair
-        "sweep": 52 * cand + 208 * contacts,        # per candidate: pair 16, pos/offs 2x(16+...) ; per contact: SURVEY K6 208
+        "keys": 96 * n + 4 * ncells,        # R 64 body + 16 acc|flags, W key 4 + arrival rank 4, histogram RMW 8; table memset
+        "cell_scan": 8 * ncells,            # in-place exclusive scan of the cell histogram
+        "scatter": 220 * n,                 # R 8 + 80 + 4 (cell start), W 80 body + 32 AABB + 4 + 4 + 8 per-body scratch
+        "find_pairs": 32 * n + 4 * ncells + 40 * npairs + 8 * nw,  # AABBs + cell table once; W 32 pair (+8 degree atomics), 8 watch
+        "chains": 8 * n + 72 * npairs,      # degree scan; fill R 16 + W 16 + 8; sort+link R/W 16 + W 8 + 8
+        "sweep": (1 + r) * (144 * npairs + 150 * c + 8 * nw) + r * (64 * npairs + 224 * c),  # sweeps, verification, restore
         "finish": 0,
     }
 
@@ -142,15 +149,25 @@ def run_ours(args) -> dict:
     n_total = int(scene["pos"].shape[0])
     lib = capi.lib()
 
-    w = PhysicsWorld(device=local_rank, profile=True, **wkw)
     if world_size > 1:
+        # strong scaling: the SAME scene, cut into x-slabs of equal body count; the floor is replicated
         from gears_b200 import slabs
-        scene, slab = slabs.partition(scene, rank, world_size, axis_lo=0.0, axis_hi=float(gen.get("L", 0.0)))
+        ext = (scene["box_max"] - scene["box_min"]).max(axis=1)
+        rep = slabs.big_static_mask(scene, 4.0 * float(ext[scene["is_static"] == 0].max()))
+        faces = slabs.bounds(scene, world_size, "count", replicate=rep)
+        part = slabs.partition(scene, faces, rep)[rank]
+        del scene
+        scene = part
+        n_local = int(scene["pos"].shape[0])
+        wkw = dict(wkw)
+        wkw["max_pairs"] = max(1 << 20, wkw.get("max_pairs", 16 * n_total) // world_size * 2)
+        w = PhysicsWorld(device=local_rank, profile=True, max_bodies=int(n_local * 1.25) + 262144, **wkw)
         w.upload(scene)
-        slabs.comm_init(w, dist, rank, world_size, slab)
+        slabs.comm_init(w, dist, rank, world_size, faces, halo=args.halo, device=torch.device("cuda", local_rank))
     else:
+        w = PhysicsWorld(device=local_rank, profile=True, **wkw)
         w.upload(scene)
-    n_local = int(scene["pos"].shape[0])
+        n_local = n_total
 
     def barrier():
         torch.cuda.synchronize()
@@ -166,27 +183,34 @@ def run_ours(args) -> dict:
     l0 = w.kernel_launches()
     barrier()
     sampler.start()
+    t_wall0 = time.perf_counter()
     w.step_async(DT, args.steps)
     st = w.sync()
     barrier()
+    t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     ms_total = w.last_step_ms()  # CUDA events on the step stream around the K steps
     launches = w.kernel_launches() - l0
     kt = w.kernel_times()
+    slab_stats = None
     if world_size > 1:
-        t = torch.tensor([ms_total], device="cuda")
+        t = torch.tensor([ms_total, t_wall * 1e3], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        inexact = torch.tensor([float(st["steps_inexact"])], device="cuda")
-        dist.all_reduce(inexact, op=dist.ReduceOp.SUM)
-        st["steps_inexact"] = int(inexact.item())
+        ms_total = float(t[0].item())
+        agg = torch.tensor([float(st["steps_inexact"]), float(st["unverified_total"]), float(st["n_halo_in"]),
+                            float(st["n_migrated_out"]), float(st["n_bodies"]), float(launches)], device="cuda")
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        st["steps_inexact"] = int(agg[0].item())
+        slab_stats = {"unverified_body_steps": int(agg[1].item()), "halo_copies_last_step": int(agg[2].item()),
+                      "migrations_last_step": int(agg[3].item()), "bodies_incl_halo_last_step": int(agg[4].item()),
+                      "halo": args.halo, "transport": "ncclSend/ncclRecv, one group per step, fixed-size messages"}
+        launches = int(agg[5].item())
     ms_per_step = ms_total / args.steps
     value = n_total * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel group ----
+    # ---- roofline of the dominant kernel group (rank 0's share of the work) ----
     peak, peak_src = peaks()
-    passes = (max(1, int(np.ceil(np.log2(max(2, st["grid_dim"][0] * st["grid_dim"][1] * st["grid_dim"][2] + 1))))) + 7) // 8
-    alg = algorithmic_bytes(n_local, passes, st)
+    alg = algorithmic_bytes(st["n_bodies"], st)
     groups = {}
     for g, ms in kt["ms"].items():
         if kt["steps"] and ms > 0:
@@ -197,8 +221,9 @@ def run_ours(args) -> dict:
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": groups[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": round(groups[dom]["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
-                    "share_of_step": round(groups[dom]["ms"] / sum(x["ms"] for x in groups.values()), 3)}
+                    "frac": round(groups[dom]["gbs"] / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                    "share_of_step": round(groups[dom]["ms"] / sum(x["ms"] for x in groups.values()), 3),
+                    "per_kernel_frac": {g: round(x["gbs"] / peak, 3) for g, x in groups.items() if x["alg_bytes"]}}
 
     # ---- end to end through the C ABI with pinned HOST buffers: H2D state + step + D2H result every step ----
     e2e = None
@@ -227,6 +252,25 @@ def run_ours(args) -> dict:
                "path": "gp_set_state + gp_step + gp_download on pinned host buffers"}
         for p in (pp, pv, pa):
             lib.gp_host_free(p)
+    else:
+        # slab worlds keep their state on the device between steps; the host-visible result is gp_download_owned
+        nown = 0
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            w.step_async(DT, 1)
+            ent, hp, hv = w.download_owned()               # D2H: ids, pos, vel of the owned bodies (sync)
+            nown = len(ent)
+        barrier()
+        t1 = time.perf_counter()
+        tt = torch.tensor([t1 - t0], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total * e2e_steps / float(tt.item()), "unit": "body-steps/s", "steps": e2e_steps,
+               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 28 * nown,
+               "path": "gp_step_async + gp_download_owned per step (slab worlds have no per-index H2D path; "
+                       "inputs are device-resident)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference algorithm on a bounded sample ----
     cpu = cpu_baseline(args, gen) if (rank == 0 and world_size == 1 and not args.no_cpu) else None
@@ -234,16 +278,18 @@ def run_ours(args) -> dict:
     out = {
         "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world_size, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if world_size > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "bodies": n_total, "dt": float(DT), "box": gen.get("L"),
                    "l2": "state arrays (80 B/body) exceed the 126 MB L2 by >10x; no flush needed"
-                   if n_total * 80 > 4 * 126e6 else "working set fits L2: numbers are L2-resident",
+                   if n_total * 80 > 4 * 126e6 * world_size else "working set fits L2: numbers are L2-resident",
                    "parallelism": f"x-slabs{world_size}" if world_size > 1 else "single"},
         "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "kernels": groups,
-        "step_stats": {k: st[k] for k in ("n_candidates", "n_contacts", "n_rounds", "n_retries", "margin",
-                                          "max_displacement", "cell_size", "grid_dim", "n_big", "steps_inexact")},
-        "exact": st["steps_inexact"] == 0,
+        "kernels": groups, "wall_ms_per_step": t_wall * 1e3 / args.steps,
+        "step_stats": {k: st[k] for k in ("n_bodies", "n_candidates", "n_watch", "n_activated", "n_contacts", "n_rounds",
+                                          "n_retries", "margin", "max_displacement", "cell_size", "grid_dim", "n_big",
+                                          "steps_inexact")},
+        "slabs": slab_stats,
+        "exact": st["steps_inexact"] == 0 and (slab_stats is None or slab_stats["unverified_body_steps"] == 0),
     }
     w.close()
     if world_size > 1:
@@ -321,6 +367,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768, help="bodies in the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--halo", type=float, default=4.0, help="slab coverage H beyond a face (multi-GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -72,13 +72,13 @@ struct Ctl {
     float x_lo, x_hi;
     float halo;               // coverage H: the neighbour sends every body whose inflated AABB comes within H of the face
     uint32_t has_left, has_right;
-    uint32_t xcap;            // records per exchange buffer
+    uint32_t xcap[2];         // records per exchange buffer (left / right face; both sides of a face agree)
     uint32_t cap;             // body capacity of the arrays
     uint32_t n_sent[2];       // records packed for the left / right neighbour this step
     uint32_t n_migrated_out, n_migrated_in;  // stats of the step
     uint32_t n_unverified;    // owned bodies whose result could depend on a body this rank does not know (this step)
     uint32_t unverified_total;  // summed over the async steps since the last sync
-    uint32_t taint_changed;
+    uint32_t taint_flag[3];
     uint32_t n;               // live bodies of the current step (set by K3 after the sort dropped dead keys)
     float margin;             // relative margin mu of the current step: body x's AABB is inflated by
                               // mu * (largest extent of x) in K4, and K6 verifies it never moves further
@@ -480,9 +480,9 @@ __global__ void __launch_bounds__(256)
             const bool halo_r = ctl->has_right && whi.x + m > ctl->x_hi - ctl->halo;
             const uint32_t fl = (flags | F_INTEGRATED) & ~F_GHOST;
             if (own_l || halo_l)
-                pack_record(send_l, ctl->xcap, &ctl->n_sent[0], ctl, p, v, a, lo, hi, own_l ? fl : (fl | F_GHOST));
+                pack_record(send_l, ctl->xcap[0], &ctl->n_sent[0], ctl, p, v, a, lo, hi, own_l ? fl : (fl | F_GHOST));
             if (own_r || halo_r)
-                pack_record(send_r, ctl->xcap, &ctl->n_sent[1], ctl, p, v, a, lo, hi, own_r ? fl : (fl | F_GHOST));
+                pack_record(send_r, ctl->xcap[1], &ctl->n_sent[1], ctl, p, v, a, lo, hi, own_r ? fl : (fl | F_GHOST));
             if (own_l || own_r) {
                 A[i].w = __uint_as_float(flags | F_GHOST);  // ownership moved: here it is a halo copy from now on
                 atomicAdd(&ctl->n_migrated_out, 1u);
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(256)
 
 // the counts travel in the buffer header
 __global__ void k_seal_sends(float4* send_l, float4* send_r, const Ctl* ctl) {
-    if (send_l) send_l[0] = make_float4(__uint_as_float(min(ctl->n_sent[0], ctl->xcap)), 0.f, 0.f, 0.f);
-    if (send_r) send_r[0] = make_float4(__uint_as_float(min(ctl->n_sent[1], ctl->xcap)), 0.f, 0.f, 0.f);
+    if (send_l) send_l[0] = make_float4(__uint_as_float(min(ctl->n_sent[0], ctl->xcap[0])), 0.f, 0.f, 0.f);
+    if (send_r) send_r[0] = make_float4(__uint_as_float(min(ctl->n_sent[1], ctl->xcap[1])), 0.f, 0.f, 0.f);
 }
 
 // received records join the input set behind the bodies that were already here; their cell keys enter the
@@ -507,8 +507,8 @@ __global__ void __launch_bounds__(256)
     k_append(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, const Bodies B0,
              float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
              uint32_t* __restrict__ cell_cnt, Ctl* ctl) {
-    const uint32_t cl = recv_l ? min(__float_as_uint(recv_l[0].x), ctl->xcap) : 0u;
-    const uint32_t cr = recv_r ? min(__float_as_uint(recv_r[0].x), ctl->xcap) : 0u;
+    const uint32_t cl = recv_l ? min(__float_as_uint(recv_l[0].x), ctl->xcap[0]) : 0u;
+    const uint32_t cr = recv_r ? min(__float_as_uint(recv_r[0].x), ctl->xcap[1]) : 0u;
     const uint32_t n_in = ctl->n_in;
     uint32_t total = cl + cr;
     if (n_in + total > ctl->cap) {
@@ -1444,7 +1444,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
     c.n_watch = 0, c.n_activated = 0, c.n_requeried = 0;
     c.n_recv = 0, c.n_sent[0] = 0, c.n_sent[1] = 0, c.n_migrated_out = 0, c.n_migrated_in = 0, c.n_unverified = 0;
-    c.taint_changed = 0;
+    c.taint_flag[0] = 0, c.taint_flag[1] = 0, c.taint_flag[2] = 0;
     *ctl = c;
 }
 
@@ -1456,59 +1456,65 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
 // taint spreads over components; every owned body that stays clean is bit-identical to the single-GPU result
 // (multi-GPU exactness).  n_unverified counts the owned bodies that do not stay clean.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    k_taint_init(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
-                 const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits, const Ctl* ctl) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n) return;
-    const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
-    if (box_static(lo)) return;  // static bodies never change: nothing to get wrong
-    float r = box_margin(lo);
-    if ((moved_bits[i >> 5] >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(reach[i], dmax[i] * REACH_SLACK));
-    const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
-    const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
-    if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
-}
-
-__device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __restrict__ taint_bits, Ctl* ctl) {
+__device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __restrict__ taint_bits, uint32_t* flag) {
     if ((x | y) & TOPBIT) return;  // an edge through a static body carries nothing
-    const bool tx = (taint_bits[x >> 5] >> (x & 31u)) & 1u, ty = (taint_bits[y >> 5] >> (y & 31u)) & 1u;
+    const bool tx = (__ldcg(&taint_bits[x >> 5]) >> (x & 31u)) & 1u, ty = (__ldcg(&taint_bits[y >> 5]) >> (y & 31u)) & 1u;
     if (tx == ty) return;
     const uint32_t z = tx ? y : x;
     atomicOr(&taint_bits[z >> 5], 1u << (z & 31u));
-    ctl->taint_changed = 1u;
+    *flag = 1u;
 }
 
+// ONE cooperative launch: clear, seed, propagate to the fixed point (a grid barrier per round), count.
+constexpr uint32_t TAINT_MAX_ROUNDS = 64;
 __global__ void __launch_bounds__(256)
-    k_taint_propagate(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,
-                      uint32_t* __restrict__ taint_bits, Ctl* ctl, const uint32_t* __restrict__ gate) {
-    if (gate && *gate == 0) return;  // the previous launch changed nothing: the fixed point is reached
-    const uint32_t np = min(ctl->n_pairs, pair_cap), nw = min(ctl->n_watch, pair_cap);
+    k_taint_closure(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
+                    const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits,
+                    const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,
+                    const float4* __restrict__ A, Ctl* ctl) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t n = ctl->n;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (uint32_t i = gtid; i < np; i += gsz) {
-        const uint4 r = pairs[2 * (size_t)i];
-        taint_edge(r.x, r.y, taint_bits, ctl);
+    for (uint32_t wd = gtid; wd < (n + 31u) / 32u; wd += gsz) taint_bits[wd] = 0u;
+    if (gtid == 0) ctl->taint_flag[0] = 0u, ctl->taint_flag[1] = 0u, ctl->taint_flag[2] = 0u;
+    grid.sync();
+    // seeds: bodies whose reach pokes beyond what the neighbours mirror
+    for (uint32_t i = gtid; i < n; i += gsz) {
+        const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
+        if (box_static(lo)) continue;  // static bodies never change: nothing to get wrong
+        float r = box_margin(lo);
+        if ((moved_bits[i >> 5] >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(reach[i], dmax[i] * REACH_SLACK));
+        const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
+        const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
+        if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
     }
-    for (uint32_t i = gtid; i < nw; i += gsz) {
-        const uint2 r = watch[i];
-        if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, ctl);  // (activated entries are among the pairs)
+    grid.sync();
+    const uint32_t np = min(ctl->n_pairs, pair_cap), nw = min(ctl->n_watch, pair_cap);
+    uint32_t it = 0;
+    bool open = true;
+    while (open && it < TAINT_MAX_ROUNDS) {
+        // three rotating flags: round `it` raises flag it%3 and clears flag (it+1)%3, which was last READ at the end
+        // of round it-2, i.e. behind the barrier of round it-1 (with two flags a fast thread would clear the flag a
+        // slow thread is still about to read, and the grid would disagree about leaving the loop)
+        uint32_t* flag = &ctl->taint_flag[it % 3u];
+        if (gtid == 0) ctl->taint_flag[(it + 1u) % 3u] = 0u;
+        for (uint32_t i = gtid; i < np; i += gsz) {
+            const uint4 r = pairs[2 * (size_t)i];
+            taint_edge(r.x, r.y, taint_bits, flag);
+        }
+        for (uint32_t i = gtid; i < nw; i += gsz) {
+            const uint2 r = watch[i];
+            if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, flag);  // (activated entries are among the pairs)
+        }
+        grid.sync();
+        open = __ldcg(flag) != 0u;
+        ++it;
     }
-}
-// between two propagation launches: remember whether the last one changed anything, arm the next
-__global__ void k_taint_roll(Ctl* ctl, uint32_t* scratch) {
-    scratch[0] = ctl->taint_changed;
-    ctl->taint_changed = 0;
-}
-
-__global__ void __launch_bounds__(256)
-    k_taint_count(const float4* __restrict__ A, const uint32_t* __restrict__ taint_bits, Ctl* ctl, int still_open) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // owned dynamic bodies that are not provably independent of unseen bodies
     uint32_t c = 0;
-    if (i < ctl->n) {
+    for (uint32_t i = gtid; i < n; i += gsz) {
         const uint32_t f = __float_as_uint(A[i].w);
-        const bool owned_dyn = !(f & (F_GHOST | F_STATIC));
-        // propagation did not reach its fixed point within the launches provided: nothing is verified
-        if (owned_dyn && (((taint_bits[i >> 5] >> (i & 31u)) & 1u) || (still_open && ctl->taint_changed))) c = 1;
+        if (!(f & (F_GHOST | F_STATIC)) && (open || ((__ldcg(&taint_bits[i >> 5]) >> (i & 31u)) & 1u))) ++c;
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->n_unverified, c);

@@ -69,7 +69,9 @@ struct gp_multi {
     gp_world* peer[2] = {nullptr, nullptr};  // local transport: left / right neighbour world
     float4* send[2] = {nullptr, nullptr};
     float4* recv[2] = {nullptr, nullptr};
-    size_t buf_bytes = 0;
+    size_t buf_bytes[2] = {0, 0};  // per face: 16 B header + xcap[side] records (both sides of a face agree)
+    uint32_t proposal = 0;         // records per face buffer this rank asks for
+    int taint_grid = 0;
     uint32_t* taint_bits = nullptr;
     uint32_t* scratch = nullptr;   // [0] taint gate, [1..3] prepare counts, [4] compact counter
     cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
@@ -107,29 +109,29 @@ static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
     const int rank = m->cfg.rank;
     CKN(g_nccl.GroupStart());
     // fixed-size messages (the count travels in the header): no host round trip to size them
-    if (m->send[0]) CKN(g_nccl.Send(m->send[0], m->buf_bytes, ncclChar, rank - 1, m->comm, w->st));
-    if (m->send[1]) CKN(g_nccl.Send(m->send[1], m->buf_bytes, ncclChar, rank + 1, m->comm, w->st));
-    if (m->recv[0]) CKN(g_nccl.Recv(m->recv[0], m->buf_bytes, ncclChar, rank - 1, m->comm, w->st));
-    if (m->recv[1]) CKN(g_nccl.Recv(m->recv[1], m->buf_bytes, ncclChar, rank + 1, m->comm, w->st));
+    if (m->send[0]) CKN(g_nccl.Send(m->send[0], m->buf_bytes[0], ncclChar, rank - 1, m->comm, w->st));
+    if (m->send[1]) CKN(g_nccl.Send(m->send[1], m->buf_bytes[1], ncclChar, rank + 1, m->comm, w->st));
+    if (m->recv[0]) CKN(g_nccl.Recv(m->recv[0], m->buf_bytes[0], ncclChar, rank - 1, m->comm, w->st));
+    if (m->recv[1]) CKN(g_nccl.Recv(m->recv[1], m->buf_bytes[1], ncclChar, rank + 1, m->comm, w->st));
     CKN(g_nccl.GroupEnd());
     return GP_OK;
 }
 
-static const int TAINT_ROUNDS = 24;  // launches after the fixed point return at once
 static void gp_multi_enqueue_verification(gp_multi* m) {
     gp_world* w = m->w;
     if (!m->verify) return;
-    cudaStream_t st = w->st;
-    const uint32_t nb = w->cap;
-    cudaMemsetAsync(m->taint_bits, 0, sizeof(uint32_t) * ((size_t)nb / 32 + 1), st);
-    k_taint_init<<<cdiv(nb, 256), 256, 0, st>>>(w->sbox, w->dmax, w->reach, w->moved_bits, m->taint_bits, w->ctl);
-    for (int r = 0; r < TAINT_ROUNDS; ++r) {
-        k_taint_propagate<<<w->sm_count * 4, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->watch, m->taint_bits,
-                                                           w->ctl, r == 0 ? nullptr : m->scratch);
-        if (r + 1 < TAINT_ROUNDS) k_taint_roll<<<1, 1, 0, st>>>(w->ctl, m->scratch);
-    }
-    k_taint_count<<<cdiv(nb, 256), 256, 0, st>>>(w->A[w->cur ^ 1], m->taint_bits, w->ctl, 1);
-    w->launches += 2 * TAINT_ROUNDS + 1;
+    const float4* sbox = w->sbox;
+    const float *dmax = w->dmax, *reach = w->reach;
+    const uint32_t* mvb = w->moved_bits;
+    uint32_t* tb = m->taint_bits;
+    const uint4* pairs = w->pairs;
+    uint32_t pair_cap = (uint32_t)w->pair_cap;
+    const uint2* watch = w->watch;
+    const float4* A = w->A[w->cur ^ 1];
+    Ctl* ctl = w->ctl;
+    void* args[] = {&sbox, &dmax, &reach, &mvb, &tb, &pairs, &pair_cap, &watch, &A, &ctl};
+    cudaLaunchCooperativeKernel((void*)k_taint_closure, dim3(m->taint_grid), dim3(256), args, 0, w->st);
+    w->launches += 1;
 }
 
 // common part of gp_comm_init / gp_comm_init_local
@@ -160,6 +162,7 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
     hc.x_lo = c.x_lo, hc.x_hi = c.x_hi, hc.halo = c.halo;
     hc.has_left = c.rank > 0, hc.has_right = c.rank + 1 < c.nranks;
     hc.cap = w->cap;
+    hc.xcap[0] = hc.xcap[1] = 0;
     gp_status rs = GP_OK;
     do {
         if (dmalloc(&m->scratch, 16) || dmalloc(&m->taint_bits, (size_t)w->cap / 32 + 1) ||
@@ -185,23 +188,13 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
                       "(they are replicated on every rank)", counts[2]);
             break;
         }
-        uint32_t xcap = c.max_exchange;
-        if (xcap == 0) xcap = 2u * std::max(counts[0], counts[1]) + 8192u;
-        m->cfg.max_exchange = xcap;
-        hc.xcap = xcap;
-        cudaMemcpyAsync(w->ctl, &hc, sizeof hc, cudaMemcpyHostToDevice, w->st);
-        m->buf_bytes = sizeof(float4) * (1 + (size_t)xcap * XREC);
-        for (int s = 0; s < 2; ++s) {
-            const bool has = s == 0 ? hc.has_left : hc.has_right;
-            if (!has) continue;
-            if (dmalloc(&m->send[s], m->buf_bytes / sizeof(float4)) || dmalloc(&m->recv[s], m->buf_bytes / sizeof(float4))) {
-                rs = fail(w, GP_ERR_CUDA, "slab setup: out of device memory for the exchange buffers");
-                break;
-            }
-            cudaMemsetAsync(m->send[s], 0, sizeof(float4), w->st);
-            cudaMemsetAsync(m->recv[s], 0, sizeof(float4), w->st);
+        m->proposal = c.max_exchange ? c.max_exchange : 2u * std::max(counts[0], counts[1]) + 8192u;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_taint_closure, 256, 0) != cudaSuccess || occ < 1) {
+            rs = fail(w, GP_ERR_CUDA, "slab setup: no occupancy for the verification kernel");
+            break;
         }
-        if (rs != GP_OK) break;
+        m->taint_grid = std::min(occ, 4) * w->sm_count;
         if (cudaStreamSynchronize(w->st) != cudaSuccess) rs = fail(w, GP_ERR_CUDA, "slab setup failed");
     } while (0);
     if (rs != GP_OK) {
@@ -209,6 +202,27 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
         return rs;
     }
     w->multi = m;
+    return GP_OK;
+}
+
+// both sides of a face have agreed on cap[side] records: allocate the buffers, publish the capacities
+static gp_status slab_alloc_buffers(gp_world* w, const uint32_t cap[2]) {
+    gp_multi* m = w->multi;
+    CK(cudaSetDevice(w->device));
+    const bool has[2] = {m->cfg.rank > 0, m->cfg.rank + 1 < m->cfg.nranks};
+    uint32_t xc[2] = {0, 0};
+    for (int s = 0; s < 2; ++s) {
+        if (!has[s]) continue;
+        xc[s] = cap[s];
+        m->buf_bytes[s] = sizeof(float4) * (1 + (size_t)cap[s] * XREC);
+        CK(dmalloc(&m->send[s], m->buf_bytes[s] / sizeof(float4)));
+        CK(dmalloc(&m->recv[s], m->buf_bytes[s] / sizeof(float4)));
+        CK(cudaMemsetAsync(m->send[s], 0, sizeof(float4), w->st));
+        CK(cudaMemsetAsync(m->recv[s], 0, sizeof(float4), w->st));
+    }
+    Ctl* dc = w->ctl;
+    CK(cudaMemcpyAsync(&dc->xcap[0], xc, sizeof xc, cudaMemcpyHostToDevice, w->st));
+    CK(cudaStreamSynchronize(w->st));
     return GP_OK;
 }
 
@@ -241,7 +255,23 @@ extern "C" gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYT
         w->multi = nullptr;
         return fail(w, GP_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
     }
-    return GP_OK;
+    // agree with each neighbour on the message size of the shared face: the larger of the two proposals
+    gp_multi* m = w->multi;
+    const int rank = m->cfg.rank, nr = m->cfg.nranks;
+    uint32_t* sc = m->scratch;  // [8] mine, [9] left's, [10] right's
+    uint32_t mine[3] = {m->proposal, 0, 0};
+    CK(cudaMemcpyAsync(sc + 8, mine, sizeof mine, cudaMemcpyHostToDevice, w->st));
+    CKN(g_nccl.GroupStart());
+    if (rank > 0) CKN(g_nccl.Send(sc + 8, 4, ncclChar, rank - 1, m->comm, w->st));
+    if (rank + 1 < nr) CKN(g_nccl.Send(sc + 8, 4, ncclChar, rank + 1, m->comm, w->st));
+    if (rank > 0) CKN(g_nccl.Recv(sc + 9, 4, ncclChar, rank - 1, m->comm, w->st));
+    if (rank + 1 < nr) CKN(g_nccl.Recv(sc + 10, 4, ncclChar, rank + 1, m->comm, w->st));
+    CKN(g_nccl.GroupEnd());
+    uint32_t got[3];
+    CK(cudaMemcpyAsync(got, sc + 8, sizeof got, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    const uint32_t cap[2] = {std::max(got[0], got[1]), std::max(got[0], got[2])};
+    return slab_alloc_buffers(w, cap);
 }
 
 extern "C" gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, const gp_slab_config* cfgs) {
@@ -262,15 +292,11 @@ extern "C" gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, cons
         gp_multi* m = worlds[i]->multi;
         m->peer[0] = i > 0 ? worlds[i - 1] : nullptr;
         m->peer[1] = i + 1 < n ? worlds[i + 1] : nullptr;
-        if ((m->peer[0] && m->peer[0]->multi->buf_bytes < 16) || (m->peer[1] && m->peer[1]->multi->buf_bytes < 16))
-            return fail(worlds[i], GP_ERR_STATE, "neighbour without exchange buffers");
-    }
-    // both sides of a face must agree on the message size
-    for (int i = 0; i + 1 < n; ++i) {
-        gp_multi *a = worlds[i]->multi, *b = worlds[i + 1]->multi;
-        if (a->cfg.max_exchange != b->cfg.max_exchange)
-            return fail(worlds[i], GP_ERR_BAD_ARG, "max_exchange differs across a face (%u vs %u): pass the same value to all ranks",
-                        a->cfg.max_exchange, b->cfg.max_exchange);
+        // message size of a face = the larger of the two sides' proposals
+        const uint32_t cap[2] = {m->peer[0] ? std::max(m->proposal, m->peer[0]->multi->proposal) : 0u,
+                                 m->peer[1] ? std::max(m->proposal, m->peer[1]->multi->proposal) : 0u};
+        gp_status s = slab_alloc_buffers(worlds[i], cap);
+        if (s != GP_OK) return s;
     }
     return GP_OK;
 }
@@ -303,7 +329,7 @@ extern "C" gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt,
                 if (!p) continue;
                 CK(cudaStreamWaitEvent(w->st, p->multi->ev_packed, 0));
                 // my left neighbour's RIGHT send buffer is my left receive buffer, and vice versa
-                CK(cudaMemcpyPeerAsync(m->recv[side], w->device, p->multi->send[side ^ 1], p->device, m->buf_bytes, w->st));
+                CK(cudaMemcpyPeerAsync(m->recv[side], w->device, p->multi->send[side ^ 1], p->device, m->buf_bytes[side], w->st));
             }
             CK(cudaEventRecord(m->ev_copied, w->st));
         }

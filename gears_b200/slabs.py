@@ -112,8 +112,6 @@ class LocalSlabs:
             w = PhysicsWorld(device=devices[r], **kw)
             w.upload(part)
             self.worlds.append(w)
-        if max_exchange == 0:
-            max_exchange = max(8192, n_total // max(2, nranks))  # generous: both sides of a face must agree
         cfgs = (capi.GpSlabConfig * nranks)(*[slab_config(r, nranks, self.faces, halo, max_exchange, verify)
                                                for r in range(nranks)])
         hs = (C.c_void_p * nranks)(*[w._h for w in self.worlds])
