@@ -154,7 +154,7 @@ def run_ours(args) -> dict:
         from gears_b200 import slabs
         ext = (scene["box_max"] - scene["box_min"]).max(axis=1)
         rep = slabs.big_static_mask(scene, 4.0 * float(ext[scene["is_static"] == 0].max()))
-        faces = slabs.bounds(scene, world_size, "count", replicate=rep)
+        faces = slabs.bounds(scene, world_size, "balanced", replicate=rep, halo=args.halo)
         part = slabs.partition(scene, faces, rep)[rank]
         del scene
         scene = part
@@ -163,7 +163,8 @@ def run_ours(args) -> dict:
         wkw["max_pairs"] = max(1 << 20, wkw.get("max_pairs", 16 * n_total) // world_size * 2)
         w = PhysicsWorld(device=local_rank, profile=True, max_bodies=int(n_local * 1.25) + 262144, **wkw)
         w.upload(scene)
-        slabs.comm_init(w, dist, rank, world_size, faces, halo=args.halo, device=torch.device("cuda", local_rank))
+        slabs.comm_init(w, dist, rank, world_size, faces, halo=args.halo, max_exchange=args.max_exchange,
+                        device=torch.device("cuda", local_rank))
     else:
         w = PhysicsWorld(device=local_rank, profile=True, **wkw)
         w.upload(scene)
@@ -205,6 +206,11 @@ def run_ours(args) -> dict:
                       "migrations_last_step": int(agg[3].item()), "bodies_incl_halo_last_step": int(agg[4].item()),
                       "halo": args.halo, "transport": "ncclSend/ncclRecv, one group per step, fixed-size messages"}
         launches = int(agg[5].item())
+        # per-rank view of the step (ms per kernel group): who waits for whom at the exchange
+        mine = torch.tensor([kt["ms"][g] / max(1, kt["steps"]) for g in capi.KERNEL_GROUPS], device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world_size)]
+        dist.all_gather(allr, mine)
+        slab_stats["per_rank_group_ms"] = [[round(float(x), 4) for x in t.tolist()] for t in allr]
     ms_per_step = ms_total / args.steps
     value = n_total * args.steps / (ms_total * 1e-3)
 
@@ -368,6 +374,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo", type=float, default=4.0, help="slab coverage H beyond a face (multi-GPU)")
+    ap.add_argument("--max-exchange", type=int, default=0, help="records per slab face buffer (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -435,14 +435,33 @@ __device__ __forceinline__ uint32_t body_key(const GridParams& g, const float4 p
 // the POST-integration state, flagged F_INTEGRATED (+ F_GHOST for halo copies; without it the record transfers
 // ownership = migration).
 constexpr uint32_t XREC = 5;  // float4 per record
-__device__ __forceinline__ void pack_record(float4* __restrict__ buf, uint32_t xcap, uint32_t* counter, Ctl* ctl,
-                                            const float4 p, const float4 v, float4 a, const float4 lo, const float4 hi,
-                                            uint32_t flags_out) {
-    cg::coalesced_group cgp = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (cgp.thread_rank() == 0) base = atomicAdd(counter, cgp.size());
-    base = cgp.shfl(base, 0);
-    const uint32_t slot = base + cgp.thread_rank();
+
+// CTA-wide slot reservation: ONE global atomic per CTA and face (the send counter is a single address, and the
+// bodies near a face are spread over almost every warp of the grid).  Called by all 256 threads.
+__device__ __forceinline__ uint32_t block_reserve(bool want, uint32_t* counter, uint32_t* sm /*[10]*/) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, want);
+    if (lane == 0) sm[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = sm[w];
+            sm[w] = tot;
+            tot += c;
+        }
+        sm[8] = tot ? atomicAdd(counter, tot) : 0u;
+    }
+    __syncthreads();
+    const uint32_t slot = sm[8] + sm[warp] + __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();  // sm is reused by the next reservation
+    return slot;
+}
+
+__device__ __forceinline__ void write_record(float4* __restrict__ buf, uint32_t xcap, uint32_t slot, Ctl* ctl,
+                                             const float4 p, const float4 v, float4 a, const float4 lo, const float4 hi,
+                                             uint32_t flags_out) {
     if (slot >= xcap) {
         atomicOr(&ctl->step_flags, SF_EXCHANGE_OVERFLOW);
         return;
@@ -459,36 +478,51 @@ __global__ void __launch_bounds__(256)
     k_keys(const Bodies B0, float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
            uint32_t* __restrict__ cell_cnt, Ctl* __restrict__ ctl, float4* __restrict__ send_l,
            float4* __restrict__ send_r, float dt, float d16, float d18, float d35) {
+    __shared__ uint32_t sm_res[10];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n_in) return;
+    const uint32_t n_in = ctl->n_in;
+    if (blockIdx.x * blockDim.x >= n_in) return;  // whole CTA beyond the bodies (grids are sized for capacity)
+    const bool live = i < n_in;
     const GridParams g = ctl->grid;
-    float4 p = B0.P(i), v = B0.V(i);
-    const float4 a = A[i], lo = B0.Lo(i), hi = B0.Hi(i);
-    const uint32_t flags = __float_as_uint(a.w);
-    if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
-    uint32_t k = body_key(g, p, lo, hi, flags);
+    float4 p = make_float4(0, 0, 0, 0), v = p, a = p, lo = p, hi = p;
+    uint32_t flags = 0, k = 0;
+    if (live) {
+        p = B0.P(i), v = B0.V(i), a = A[i], lo = B0.Lo(i), hi = B0.Hi(i);
+        flags = __float_as_uint(a.w);
+        if (!(flags & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
+        k = body_key(g, p, lo, hi, flags);
+    }
     if (SLAB) {
-        if (flags & F_GHOST) {
-            k = g.ncells + 1u;  // last step's halo copy: its owner sends a fresh one if it is still near
-        } else if (!(flags & F_BIG)) {  // big (static) bodies are replicated on every rank and never travel
-            const float4 wlo = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, 0.f);
-            const float4 whi = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, 0.f);
-            const float cx = (wlo.x + whi.x) * 0.5f;
-            const float m = ctl->margin * box_extent(wlo, whi);  // the margin K3 will store for this body
-            const bool own_l = ctl->has_left && cx < ctl->x_lo, own_r = ctl->has_right && !(cx < ctl->x_hi);
-            const bool halo_l = ctl->has_left && wlo.x - m < ctl->x_lo + ctl->halo;
-            const bool halo_r = ctl->has_right && whi.x + m > ctl->x_hi - ctl->halo;
-            const uint32_t fl = (flags | F_INTEGRATED) & ~F_GHOST;
-            if (own_l || halo_l)
-                pack_record(send_l, ctl->xcap[0], &ctl->n_sent[0], ctl, p, v, a, lo, hi, own_l ? fl : (fl | F_GHOST));
-            if (own_r || halo_r)
-                pack_record(send_r, ctl->xcap[1], &ctl->n_sent[1], ctl, p, v, a, lo, hi, own_r ? fl : (fl | F_GHOST));
-            if (own_l || own_r) {
-                A[i].w = __uint_as_float(flags | F_GHOST);  // ownership moved: here it is a halo copy from now on
-                atomicAdd(&ctl->n_migrated_out, 1u);
+        bool to_l = false, to_r = false, own_l = false, own_r = false;
+        if (live) {
+            if (flags & F_GHOST) {
+                k = g.ncells + 1u;  // last step's halo copy: its owner sends a fresh one if it is still near
+            } else if (!(flags & F_BIG)) {  // big (static) bodies are replicated on every rank and never travel
+                const float4 wlo = make_float4(lo.x + p.x, lo.y + p.y, lo.z + p.z, 0.f);
+                const float4 whi = make_float4(hi.x + p.x, hi.y + p.y, hi.z + p.z, 0.f);
+                const float cx = (wlo.x + whi.x) * 0.5f;
+                const float m = ctl->margin * box_extent(wlo, whi);  // the margin K3 will store for this body
+                own_l = ctl->has_left && cx < ctl->x_lo;
+                own_r = ctl->has_right && !(cx < ctl->x_hi);
+                to_l = own_l || (ctl->has_left && wlo.x - m < ctl->x_lo + ctl->halo);
+                to_r = own_r || (ctl->has_right && whi.x + m > ctl->x_hi - ctl->halo);
             }
         }
+        const uint32_t fl = (flags | F_INTEGRATED) & ~F_GHOST;
+        if (send_l) {
+            const uint32_t slot = block_reserve(to_l, &ctl->n_sent[0], sm_res);
+            if (to_l) write_record(send_l, ctl->xcap[0], slot, ctl, p, v, a, lo, hi, own_l ? fl : (fl | F_GHOST));
+        }
+        if (send_r) {
+            const uint32_t slot = block_reserve(to_r, &ctl->n_sent[1], sm_res);
+            if (to_r) write_record(send_r, ctl->xcap[1], slot, ctl, p, v, a, lo, hi, own_r ? fl : (fl | F_GHOST));
+        }
+        if (own_l || own_r) {
+            A[i].w = __uint_as_float(flags | F_GHOST);  // ownership moved: here it is a halo copy from now on
+            atomicAdd(&ctl->n_migrated_out, 1u);
+        }
     }
+    if (!live) return;
     key[i] = k;
     // K2 is a one-pass radix sort whose single digit is the whole cell key: this is its histogram.  The bodies
     // arrive in last step's cell order, so the atomics of a warp fall on a few neighbouring L2 lines.

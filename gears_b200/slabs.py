@@ -29,9 +29,11 @@ def centres_x(scene: dict) -> np.ndarray:
     return ((lo + hi) * np.float32(0.5)).astype(np.float32)
 
 
-def bounds(scene: dict, nranks: int, mode: str = "count", lo: float | None = None, hi: float | None = None,
-           replicate: np.ndarray | None = None) -> np.ndarray:
-    """nranks+1 faces; the outer two are -inf / +inf.  mode 'count': equal body counts, 'width': equal widths."""
+def bounds(scene: dict, nranks: int, mode: str = "balanced", lo: float | None = None, hi: float | None = None,
+           replicate: np.ndarray | None = None, halo: float = 4.0) -> np.ndarray:
+    """nranks+1 faces; the outer two are -inf / +inf.
+    mode 'count': equal owned-body counts; 'balanced': equal owned + halo-copy counts (inner slabs mirror two faces,
+    the end slabs one, so inner slabs get a little less to own); 'width': equal widths."""
     cx = centres_x(scene)
     if replicate is not None:
         cx = cx[~replicate]
@@ -42,7 +44,18 @@ def bounds(scene: dict, nranks: int, mode: str = "count", lo: float | None = Non
         b = float(cx.max()) if hi is None else hi
         inner = a + (b - a) * np.arange(1, nranks) / nranks
     else:
-        inner = np.quantile(cx.astype(np.float64), np.arange(1, nranks) / nranks)
+        n = len(cx)
+        faces_per_rank = np.array([1.0] + [2.0] * (nranks - 2) + [1.0]) if nranks > 1 else np.array([0.0])
+        g = 0.0
+        if mode == "balanced" and n:
+            ext = float((scene["box_max"] - scene["box_min"])[:, 0].max()) if replicate is None else \
+                float((scene["box_max"] - scene["box_min"])[~replicate, 0].max())
+            span = max(1e-6, float(cx.max() - cx.min()))
+            g = n * min(0.25, (halo + 1.5 * ext) / span)  # halo copies per face at the average density
+        total = (n + faces_per_rank.sum() * g) / nranks   # owned + mirrored per rank
+        own = np.maximum(total - faces_per_rank * g, 0.05 * n / nranks)
+        q = np.cumsum(own)[:-1] / own.sum()
+        inner = np.quantile(cx.astype(np.float64), q)
     return np.concatenate([[-INF], inner, [INF]]).astype(np.float32)
 
 
@@ -94,7 +107,7 @@ class LocalSlabs:
     """n slab worlds in one process (devices[i] may repeat)."""
 
     def __init__(self, scene: dict, nranks: int, devices=None, halo: float = 0.0, max_exchange: int = 0,
-                 big_threshold: float | None = None, mode: str = "count", verify: bool = True, **world_kw):
+                 big_threshold: float | None = None, mode: str = "balanced", verify: bool = True, **world_kw):
         self.lib = capi.lib()
         devices = devices or [0] * nranks
         ext = (scene["box_max"] - scene["box_min"]).max(axis=1)
