@@ -1,15 +1,20 @@
 // gp_kernels.cuh — the physics step as sm_100a CUDA kernels.
 //
 // Reference behaviour reproduced (paths relative to /root/reference):
-//   K1  k_integrate       RigidBody::update_pos            crates/gears-ecs/src/components/physics.rs:405-462
-//                         + world AABB (get_rotated_aabb)  physics.rs:84-135 (via per-body min/max offsets)
-//   K3  k_gather_cells    (new) cell-range table + AABB tiles in cell order
-//   K4  k_find_pairs      CollisionBox::intersects         physics.rs:148-165  (margin-inflated superset + exact snapshot test)
-//   K5  k_fill_chains / k_sort_chains   (new) per-body contact chains in the reference's pair order
-//   K6  k_sweep           check_and_resolve_collision      physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
+//   K1  k_keys            RigidBody::update_pos (in registers)   crates/gears-ecs/src/components/physics.rs:405-462
+//                         + world AABB centre -> cell key + cell histogram; slabs: migration / halo packing
+//   K2  (scan.cuh)        (new) in-place scan of the histogram = cell start table (one-pass bucket sort by cell)
+//   K3  k_scatter_cells   update_pos again on the fly + world AABB (get_rotated_aabb, physics.rs:84-135, via per-body
+//                         min/max offsets); bodies are physically re-sorted into cell order
+//   K4  k_find_pairs      CollisionBox::intersects                physics.rs:148-165  (margin-inflated superset, TMA-staged
+//                         tiles, flattened tests, per-warp staged bursts; exact snapshot test for S_snapshot)
+//   K5  k_fill_chains / k_sort_chains / k_sort_heavy   (new) per-body contact chains in the reference's pair order
+//   K6  k_sweep           check_and_resolve_collision             physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
 //                         in the order of update_systems.rs:408-487
+//       k_requery / k_verify_watch / k_restore / k_recount        (new) verification + repair of the speculative pair set
+//       k_taint_closure   (new) multi-GPU: which owned bodies are provably independent of unseen bodies
 //
-// Ordering argument (DESIGN.md §4): the reference visits pairs (i,j), i<j in iteration order,
+// Ordering argument (DESIGN.md section 1.1): the reference visits pairs (i,j), i<j in iteration order,
 // lexicographically.  Only pairs that share a DYNAMIC body interact (static bodies are never written,
 // physics.rs:245-270).  For a body x the pairs involving x, in reference order, are exactly its
 // partners sorted by partner rank.  So executing a pair when it is at the head of both of its
