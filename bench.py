@@ -204,7 +204,10 @@ def run_ours(args) -> dict:
         st["steps_inexact"] = int(agg[0].item())
         slab_stats = {"unverified_body_steps": int(agg[1].item()), "halo_copies_last_step": int(agg[2].item()),
                       "migrations_last_step": int(agg[3].item()), "bodies_incl_halo_last_step": int(agg[4].item()),
-                      "halo": args.halo, "transport": "ncclSend/ncclRecv, one group per step, fixed-size messages"}
+                      "halo": args.halo,
+                      "transport": "ncclSend/ncclRecv, one group per step" if os.environ.get("GP_SLAB_TRANSPORT") == "nccl"
+                      else "K1 writes records into the neighbour's buffer over NVLink (CUDA IPC peer memory), "
+                           "release/acquire step flags; NCCL only at set-up"}
         launches = int(agg[5].item())
         # per-rank view of the step (ms per kernel group): who waits for whom at the exchange
         mine = torch.tensor([kt["ms"][g] / max(1, kt["steps"]) for g in capi.KERNEL_GROUPS], device="cuda")

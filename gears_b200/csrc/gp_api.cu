@@ -707,11 +707,12 @@ static gp_status enqueue_phase_a(gp_world* w, float dt, const float* damp3) {
         const uint32_t ncnt = w->max_cells + 2;  // counters: every cell of the finest grid + big list + dead
         CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
         if (w->multi) {
+            gp_multi_begin_step(w->multi);  // (peer-to-peer transport: wait for buffer credit)
             k_keys<true><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
                                                         gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), dt, d[0],
                                                         d[1], d[2]);
-            k_seal_sends<<<1, 1, 0, st>>>(gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), w->ctl);
-            w->launches += 2;
+            w->launches += 1;
+            gp_multi_seal(w->multi);        // counts into the headers (+ ready flags on the peer-to-peer transport)
         } else {
             k_keys<false><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
                                                          nullptr, nullptr, dt, d[0], d[1], d[2]);
@@ -730,9 +731,11 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
     const uint32_t nb = n_bound(w);
     if (nb) {
         if (w->multi) {
+            gp_multi_before_append(w->multi);  // (peer-to-peer transport: wait for the neighbours' ready flags)
             k_append<<<w->sm_count * 2, 256, 0, st>>>(gp_multi_recv(w->multi, 0), gp_multi_recv(w->multi, 1),
                                                       Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl);
             w->launches++;
+            gp_multi_after_append(w->multi);   // (peer-to-peer transport: hand the buffer credit back)
         }
         prof_mark(w, 1);
         const uint32_t ncnt = w->max_cells + 2;

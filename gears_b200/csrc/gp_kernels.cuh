@@ -540,14 +540,52 @@ __global__ void k_seal_sends(float4* send_l, float4* send_r, const Ctl* ctl) {
     if (send_r) send_r[0] = make_float4(__uint_as_float(min(ctl->n_sent[1], ctl->xcap[1])), 0.f, 0.f, 0.f);
 }
 
+// ---- peer-to-peer transport (one process per GPU, NVLink): K1 writes the records STRAIGHT into the neighbour's
+// receive buffer (peer-mapped through CUDA IPC), so the transfer overlaps K1 itself and no copy kernel runs.
+// Synchronisation is a pair of step counters per face in the receiver's memory, written with release.sys stores and
+// polled with acquire.sys loads (bounded: a library kernel never spins forever).  Receive buffers are double-buffered
+// by step parity; `credit` tells the sender that the buffer of two steps ago has been consumed.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until *f >= want for both flags (nullptr = no neighbour on that side)
+__global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t want, Ctl* ctl) {
+    const uint32_t* f = threadIdx.x == 0 ? f0 : f1;
+    if (threadIdx.x > 1 || !f) return;
+    for (uint32_t spin = 0; spin < (1u << 23); ++spin) {
+        if (ld_acquire_sys(f) >= want) return;
+        __nanosleep(100);
+    }
+    atomicOr(&ctl->step_flags, SF_INTERNAL);  // the neighbour never arrived (~1 s): the step is invalid, not hung
+}
+__global__ void k_post_flags(uint32_t* f0, uint32_t* f1, uint32_t v) {
+    __threadfence_system();
+    if (f0) st_release_sys(f0, v);
+    if (f1) st_release_sys(f1, v);
+}
+// header (count) into the neighbour's buffer, then the ready flag; all of K1's record stores precede this kernel
+__global__ void k_seal_p2p(float4* peer_l, float4* peer_r, uint32_t* ready_l, uint32_t* ready_r, uint32_t step,
+                           const Ctl* ctl) {
+    if (peer_l) peer_l[0] = make_float4(__uint_as_float(min(ctl->n_sent[0], ctl->xcap[0])), 0.f, 0.f, 0.f);
+    if (peer_r) peer_r[0] = make_float4(__uint_as_float(min(ctl->n_sent[1], ctl->xcap[1])), 0.f, 0.f, 0.f);
+    __threadfence_system();
+    if (ready_l) st_release_sys(ready_l, step);
+    if (ready_r) st_release_sys(ready_r, step);
+}
+
 // received records join the input set behind the bodies that were already here; their cell keys enter the
 // histogram before the scan
 __global__ void __launch_bounds__(256)
     k_append(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, const Bodies B0,
              float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
              uint32_t* __restrict__ cell_cnt, Ctl* ctl) {
-    const uint32_t cl = recv_l ? min(__float_as_uint(recv_l[0].x), ctl->xcap[0]) : 0u;
-    const uint32_t cr = recv_r ? min(__float_as_uint(recv_r[0].x), ctl->xcap[1]) : 0u;
+    const uint32_t cl = recv_l ? min(__float_as_uint(__ldcg(recv_l).x), ctl->xcap[0]) : 0u;
+    const uint32_t cr = recv_r ? min(__float_as_uint(__ldcg(recv_r).x), ctl->xcap[1]) : 0u;
     const uint32_t n_in = ctl->n_in;
     uint32_t total = cl + cr;
     if (n_in + total > ctl->cap) {
@@ -558,7 +596,8 @@ __global__ void __launch_bounds__(256)
     const GridParams g = ctl->grid;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const float4* r = (t < cl) ? recv_l + 1 + (size_t)t * XREC : recv_r + 1 + (size_t)(t - cl) * XREC;
-        const float4 p = r[0], v = r[1], a = r[2], lo = r[3], hi = r[4];
+        // (L2 loads: the buffer may have been written by the neighbour GPU)
+        const float4 p = __ldcg(r), v = __ldcg(r + 1), a = __ldcg(r + 2), lo = __ldcg(r + 3), hi = __ldcg(r + 4);
         const uint32_t s = n_in + t;
         B0.P(s) = p, B0.V(s) = v, A[s] = a, B0.Lo(s) = lo, B0.Hi(s) = hi;
         const uint32_t flags = __float_as_uint(a.w);

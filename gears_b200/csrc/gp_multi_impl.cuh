@@ -24,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -55,6 +56,7 @@ static bool nccl_load(std::string* why) {
     GP_SYM(GroupEnd, "ncclGroupEnd")
     GP_SYM(Send, "ncclSend")
     GP_SYM(Recv, "ncclRecv")
+    GP_SYM(AllReduce, "ncclAllReduce")
     GP_SYM(GetErrorString, "ncclGetErrorString")
 #undef GP_SYM
     g_nccl = a;
@@ -65,6 +67,14 @@ struct gp_multi {
     gp_world* w = nullptr;
     gp_slab_config cfg{};
     bool local = false;            // all slabs in this process: peer copies instead of NCCL
+    // peer-to-peer transport (one process per GPU): K1 writes into the neighbour's receive buffer over NVLink
+    bool p2p = false;
+    unsigned char* arena = nullptr;          // [256 B flags][recv L parity 0][recv L 1][recv R 0][recv R 1]
+    size_t arena_bytes = 0;
+    size_t off_recv[2][2] = {{0, 0}, {0, 0}};
+    unsigned char* peer_arena[2] = {nullptr, nullptr};     // the neighbours' arenas, opened through CUDA IPC
+    size_t peer_off_recv[2][2] = {{0, 0}, {0, 0}};         // where MY records go in neighbour s's arena, per parity
+    uint32_t step_id = 0;
     ncclComm_t comm = nullptr;
     gp_world* peer[2] = {nullptr, nullptr};  // local transport: left / right neighbour world
     float4* send[2] = {nullptr, nullptr};
@@ -81,6 +91,9 @@ struct gp_multi {
 
 static void gp_multi_destroy(gp_multi* m) {
     if (!m) return;
+    for (int s = 0; s < 2; ++s)
+        if (m->peer_arena[s]) cudaIpcCloseMemHandle(m->peer_arena[s]);
+    if (m->arena) cudaFree(m->arena);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     for (int s = 0; s < 2; ++s) {
         if (m->send[s]) cudaFree(m->send[s]);
@@ -93,8 +106,51 @@ static void gp_multi_destroy(gp_multi* m) {
     delete m;
 }
 static bool gp_multi_is_local(gp_multi* m) { return m->local; }
-static float4* gp_multi_send(gp_multi* m, int side) { return m->send[side]; }
-static float4* gp_multi_recv(gp_multi* m, int side) { return m->recv[side]; }
+// flag words in an arena: ready[side][parity] = words side*2+parity, credit[side] = words 4+side
+static inline uint32_t* arena_flag(unsigned char* arena, int word) { return arena ? (uint32_t*)arena + word : nullptr; }
+static float4* gp_multi_send(gp_multi* m, int side) {
+    if (!m->p2p) return m->send[side];
+    return m->peer_arena[side] ? (float4*)(m->peer_arena[side] + m->peer_off_recv[side][m->step_id & 1u]) : nullptr;
+}
+static float4* gp_multi_recv(gp_multi* m, int side) {
+    if (!m->p2p) return m->recv[side];
+    return m->peer_arena[side] ? (float4*)(m->arena + m->off_recv[side][m->step_id & 1u]) : nullptr;
+}
+static void gp_multi_begin_step(gp_multi* m) {
+    gp_world* w = m->w;
+    m->step_id++;
+    if (!m->p2p || m->step_id <= 2) return;
+    // the buffer of parity step_id&1 was last filled for step_id-2: the neighbours must have consumed that
+    k_wait_flags<<<1, 2, 0, w->st>>>(m->peer_arena[0] ? arena_flag(m->arena, 4) : nullptr,
+                                     m->peer_arena[1] ? arena_flag(m->arena, 5) : nullptr, m->step_id - 2, w->ctl);
+    w->launches++;
+}
+static void gp_multi_seal(gp_multi* m) {
+    gp_world* w = m->w;
+    if (m->p2p) {
+        const uint32_t par = m->step_id & 1u;
+        // I am my left neighbour's RIGHT side (1) and my right neighbour's LEFT side (0)
+        k_seal_p2p<<<1, 1, 0, w->st>>>(gp_multi_send(m, 0), gp_multi_send(m, 1), arena_flag(m->peer_arena[0], 1 * 2 + par),
+                                       arena_flag(m->peer_arena[1], 0 * 2 + par), m->step_id, w->ctl);
+    } else {
+        k_seal_sends<<<1, 1, 0, w->st>>>(m->send[0], m->send[1], w->ctl);
+    }
+    w->launches++;
+}
+static void gp_multi_before_append(gp_multi* m) {
+    gp_world* w = m->w;
+    if (!m->p2p) return;
+    const uint32_t par = m->step_id & 1u;
+    k_wait_flags<<<1, 2, 0, w->st>>>(m->peer_arena[0] ? arena_flag(m->arena, 0 * 2 + par) : nullptr,
+                                     m->peer_arena[1] ? arena_flag(m->arena, 1 * 2 + par) : nullptr, m->step_id, w->ctl);
+    w->launches++;
+}
+static void gp_multi_after_append(gp_multi* m) {
+    gp_world* w = m->w;
+    if (!m->p2p) return;
+    k_post_flags<<<1, 1, 0, w->st>>>(arena_flag(m->peer_arena[0], 4 + 1), arena_flag(m->peer_arena[1], 4 + 0), m->step_id);
+    w->launches++;
+}
 
 #define CKN(call)                                                                                             \
     do {                                                                                                      \
@@ -105,7 +161,7 @@ static float4* gp_multi_recv(gp_multi* m, int side) { return m->recv[side]; }
 
 static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
     gp_world* w = m->w;
-    if (m->local) return GP_OK;  // gp_step_group drives the copies of all worlds
+    if (m->local || m->p2p) return GP_OK;  // gp_step_group drives the copies / K1 already wrote into the neighbour
     static const bool skip = getenv("GP_DEBUG_SKIP_EXCHANGE") != nullptr;  // timing experiments only (results wrong)
     if (skip) return GP_OK;
     const int rank = m->cfg.rank;
@@ -228,6 +284,80 @@ static gp_status slab_alloc_buffers(gp_world* w, const uint32_t cap[2]) {
     return GP_OK;
 }
 
+// Peer-to-peer transport: one arena per world (flags + double-buffered receive buffers), shared with the two
+// neighbours through CUDA IPC; the handles travel over the NCCL communicator once, at set-up.
+struct ArenaInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long off_recv[2][2];
+    unsigned long long valid;
+};
+static gp_status slab_setup_p2p(gp_world* w) {
+    gp_multi* m = w->multi;
+    const int rank = m->cfg.rank, nr = m->cfg.nranks;
+    size_t off = 256;
+    for (int s = 0; s < 2; ++s)
+        for (int par = 0; par < 2; ++par) {
+            m->off_recv[s][par] = off;
+            off += (m->buf_bytes[s] + 255) & ~(size_t)255;
+        }
+    m->arena_bytes = off;
+    CK(cudaMalloc((void**)&m->arena, m->arena_bytes));
+    CK(cudaMemset(m->arena, 0, m->arena_bytes));
+    ArenaInfo mine{}, theirs[2]{};
+    CK(cudaIpcGetMemHandle(&mine.handle, m->arena));
+    for (int s = 0; s < 2; ++s)
+        for (int par = 0; par < 2; ++par) mine.off_recv[s][par] = m->off_recv[s][par];
+    mine.valid = 1;
+    ArenaInfo* d = nullptr;  // [0] mine, [1] left's, [2] right's
+    CK(cudaMalloc((void**)&d, 3 * sizeof(ArenaInfo)));
+    CK(cudaMemset(d, 0, 3 * sizeof(ArenaInfo)));
+    CK(cudaMemcpyAsync(d, &mine, sizeof mine, cudaMemcpyHostToDevice, w->st));
+    CKN(g_nccl.GroupStart());
+    if (rank > 0) CKN(g_nccl.Send(d, sizeof(ArenaInfo), ncclChar, rank - 1, m->comm, w->st));
+    if (rank + 1 < nr) CKN(g_nccl.Send(d, sizeof(ArenaInfo), ncclChar, rank + 1, m->comm, w->st));
+    if (rank > 0) CKN(g_nccl.Recv(d + 1, sizeof(ArenaInfo), ncclChar, rank - 1, m->comm, w->st));
+    if (rank + 1 < nr) CKN(g_nccl.Recv(d + 2, sizeof(ArenaInfo), ncclChar, rank + 1, m->comm, w->st));
+    CKN(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(theirs, d + 1, 2 * sizeof(ArenaInfo), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    cudaFree(d);
+    bool ok = true;
+    for (int s = 0; s < 2; ++s) {
+        if (!theirs[s].valid) continue;  // no neighbour on that side
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, theirs[s].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        m->peer_arena[s] = (unsigned char*)p;
+        // on neighbour s I am its side 1-s
+        for (int par = 0; par < 2; ++par) m->peer_off_recv[s][par] = (size_t)theirs[s].off_recv[1 - s][par];
+    }
+    // every rank must take the same decision (a face cannot mix transports)
+    {
+        int* dflag = nullptr;
+        CK(cudaMalloc((void**)&dflag, sizeof(int)));
+        const int mine_ok = ok ? 1 : 0;
+        int all_ok = 0;
+        CK(cudaMemcpyAsync(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, w->st));
+        CKN(g_nccl.AllReduce(dflag, dflag, 1, ncclInt32, ncclMin, m->comm, w->st));
+        CK(cudaMemcpyAsync(&all_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, w->st));
+        CK(cudaStreamSynchronize(w->st));
+        cudaFree(dflag);
+        ok = all_ok != 0;
+    }
+    if (!ok) {  // no peer access between some devices: stay on the NCCL exchange
+        for (int s = 0; s < 2; ++s)
+            if (m->peer_arena[s]) cudaIpcCloseMemHandle(m->peer_arena[s]), m->peer_arena[s] = nullptr;
+        cudaFree(m->arena);
+        m->arena = nullptr;
+        return GP_OK;
+    }
+    m->p2p = true;
+    return GP_OK;
+}
+
 extern "C" gp_status gp_comm_unique_id(uint8_t id[GP_UNIQUE_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) <= GP_UNIQUE_ID_BYTES, "unique id does not fit");
     memset(id, 0, GP_UNIQUE_ID_BYTES);
@@ -273,7 +403,11 @@ extern "C" gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYT
     CK(cudaMemcpyAsync(got, sc + 8, sizeof got, cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
     const uint32_t cap[2] = {std::max(got[0], got[1]), std::max(got[0], got[2])};
-    return slab_alloc_buffers(w, cap);
+    gp_status sb = slab_alloc_buffers(w, cap);
+    if (sb != GP_OK) return sb;
+    const char* tr = getenv("GP_SLAB_TRANSPORT");
+    if (tr && !strcmp(tr, "nccl")) return GP_OK;  // keep ncclSend/ncclRecv for the per-step exchange
+    return slab_setup_p2p(w);
 }
 
 extern "C" gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, const gp_slab_config* cfgs) {
