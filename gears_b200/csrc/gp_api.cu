@@ -65,6 +65,11 @@ struct gp_world {
     float* reach = nullptr;       // per body: largest displacement over the earlier sweeps of this step
     uint32_t *moved_bits = nullptr, *esc_bits = nullptr;  // per body: moved at all / left the outer margin
     uint2* watch = nullptr;       // lazy candidates: pairs between the inner and the outer margin
+    // component-local repair scratch
+    uint32_t *dirty_bits = nullptr, *dlist = nullptr, *dpairs = nullptr, *offs2 = nullptr, *deg2 = nullptr;
+    unsigned long long* adj2 = nullptr;
+    uint32_t* dheavy = nullptr;
+    int repair_grid = 0;
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
     // control
@@ -127,7 +132,7 @@ static void free_all(gp_world* w) {
     void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of, w->entity_dev,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
                     w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
-                    w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->moved_bits, w->esc_bits, w->watch, w->ctl, w->ctl_snap, w->d_small, w->stage};
+                    w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->moved_bits, w->esc_bits, w->watch, w->dirty_bits, w->dlist, w->dpairs, w->offs2, w->deg2, w->adj2, w->dheavy, w->ctl, w->ctl_snap, w->d_small, w->stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
@@ -191,6 +196,12 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
             break;
         }
         w->sweep_grid = std::min(occ, 4) * w->sm_count;
+        int occ_r = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_repair_local, 256, 0) != cudaSuccess || occ_r < 1) {
+            rs = GP_ERR_NO_DEVICE;
+            break;
+        }
+        w->repair_grid = std::min(occ_r, 4) * w->sm_count;
         if (cudaFuncSetAttribute(k_find_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(FindPairsSmem)) != cudaSuccess ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs, FP_THREADS, sizeof(FindPairsSmem)) !=
@@ -252,6 +263,11 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     CK(dmalloc(&w->escapees, cap));
     CK(dmalloc(&w->moved_bits, (size_t)cap / 32 + 1));
     CK(dmalloc(&w->esc_bits, (size_t)cap / 32 + 1));
+    CK(dmalloc(&w->dirty_bits, (size_t)cap / 32 + 1));
+    CK(cudaMemset(w->dirty_bits, 0, sizeof(uint32_t) * ((size_t)cap / 32 + 1)));
+    CK(dmalloc(&w->dlist, cap));
+    CK(dmalloc(&w->offs2, cap));
+    CK(dmalloc(&w->deg2, cap));
     CK(cudaMemset(w->dmax, 0, sizeof(float) * (size_t)cap));
     w->cap = cap;
     return GP_OK;
@@ -262,6 +278,9 @@ static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
     CK(dmalloc(&w->pairs, 2 * pair_cap));  // 32 B records
     CK(dmalloc(&w->adj, 2 * pair_cap));
     CK(dmalloc(&w->watch, pair_cap));
+    CK(dmalloc(&w->dpairs, pair_cap));
+    CK(dmalloc(&w->adj2, 2 * pair_cap));
+    CK(dmalloc(&w->dheavy, w->heavy_cap + 0));
     CK(dmalloc(&w->frontier[0], pair_cap));
     CK(dmalloc(&w->frontier[1], pair_cap));
     w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);
@@ -623,19 +642,10 @@ extern "C" gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out) {
 // Upper bound of the live body count that sizes the grids (the exact count is device-resident: ctl->n).
 static inline uint32_t n_bound(const gp_world* w) { return w->multi ? w->cap : w->n; }
 
-// K5 + K6: chain offsets, fill, sort, cooperative sweep.  gate != nullptr: every kernel is a no-op
-// unless *gate != 0 (repair rounds that turn out not to be needed cost a few empty launches).
-static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
-    const uint32_t nb = n_bound(w);
+// K6: the cooperative sweep.  local_list: repair sweep over the pairs k_repair_local collected (gated).
+static gp_status enqueue_sweep(gp_world* w, const uint32_t* gate, bool local_list) {
     cudaStream_t st = w->st;
     const int o = w->cur ^ 1;
-    exclusive_scan_u32(w->chain_cnt, nb, w->offs, w->tile_sums, st, &w->launches, gate);
-    k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
-                                                   w->ctl, gate);
-    k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, gate);
-    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, gate);
-    w->launches += 3;
-    if (!gate) prof_mark(w, 5);
     Bodies Bn{w->B[o]};
     const float4* box = w->sbox;
     uint4* pairs = w->pairs;
@@ -646,10 +656,25 @@ static gp_status enqueue_chains_and_sweep(gp_world* w, const uint32_t* gate) {
     uint32_t *mvb = w->moved_bits, *esb = w->esc_bits;
     uint32_t* esc = w->escapees;
     uint32_t esc_cap = w->cap;
-    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate};
+    const uint32_t* list = local_list ? w->dpairs : nullptr;
+    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate, &list};
     CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(256), args, 0, st));
     w->launches++;
     return GP_OK;
+}
+
+// K5 + K6: chain offsets, fill, sort + link, first sweep.
+static gp_status enqueue_chains_and_sweep(gp_world* w) {
+    const uint32_t nb = n_bound(w);
+    cudaStream_t st = w->st;
+    exclusive_scan_u32(w->chain_cnt, nb, w->offs, w->tile_sums, st, &w->launches, nullptr);
+    k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
+                                                   w->ctl, nullptr);
+    k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
+    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
+    w->launches += 3;
+    prof_mark(w, 5);
+    return enqueue_sweep(w, nullptr, false);
 }
 
 // After a sweep: did it stay inside what the candidate set assumed?  k_requery looks for pairs beyond the outer
@@ -664,18 +689,30 @@ static void enqueue_verify(gp_world* w) {
     w->launches += 2;
 }
 
-// One repair round (all kernels gated on ctl->repair_needed), ending with a fresh verification.
+// One repair round (4 launches, all gated on ctl->repair_needed): component-local undo + re-chain, repair sweep
+// over the collected pairs, fresh verification.
 static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
     cudaStream_t st = w->st;
     const int c = w->cur, o = c ^ 1;
-    const uint32_t* gate = &w->ctl->repair_needed;
-    k_restore<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->perm, Bodies{w->B[c]},
-                                               w->A[c], Bodies{w->B[o]}, w->chain_cnt, w->dmax, w->reach, w->ctl, dt, d[0], d[1],
-                                               d[2]);
-    k_recount<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->chain_cnt, w->ctl);
-    k_repair_reset<<<1, 1, 0, st>>>(w->ctl);
-    w->launches += 3;
-    gp_status s = enqueue_chains_and_sweep(w, gate);
+    uint4* pairs = w->pairs;
+    uint32_t pair_cap = (uint32_t)w->pair_cap;
+    const uint32_t* offs = w->offs;
+    const unsigned long long* adj = w->adj;
+    uint32_t* chain_cnt = w->chain_cnt;
+    const uint32_t* perm = w->perm;
+    Bodies B0{w->B[c]}, B1{w->B[o]};
+    const float4* A0 = w->A[c];
+    float *dmax = w->dmax, *reach = w->reach;
+    const uint32_t* esc = w->escapees;
+    uint32_t esc_cap = w->cap;
+    RepairArrays ra{w->dirty_bits, w->dlist, w->dpairs, w->offs2, w->deg2, w->adj2, w->dheavy, w->heavy_cap};
+    Ctl* ctl = w->ctl;
+    float dtv = dt, d0 = d[0], d1 = d[1], d2 = d[2];
+    void* args[] = {&pairs, &pair_cap, &offs, &adj, &chain_cnt, &perm, &B0, &A0, &B1, &dmax, &reach, &esc, &esc_cap,
+                    &ra, &ctl, &dtv, &d0, &d1, &d2};
+    CK(cudaLaunchCooperativeKernel((void*)k_repair_local, dim3(w->repair_grid), dim3(256), args, 0, st));
+    w->launches++;
+    gp_status s = enqueue_sweep(w, &w->ctl->repair_needed, true);
     if (s != GP_OK) return s;
     k_repair_done<<<1, 1, 0, st>>>(w->ctl);
     w->launches += 1;
@@ -750,7 +787,7 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
             w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
         prof_mark(w, 4);
-        enqueue_chains_and_sweep(w, nullptr);
+        enqueue_chains_and_sweep(w);
         // speculative broad phase: look for pairs the candidate set missed, repair, look again
         enqueue_verify(w);
         for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);

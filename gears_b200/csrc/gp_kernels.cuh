@@ -113,6 +113,11 @@ struct Ctl {
     uint32_t repair_needed;      // set by k_requery when it appended pairs; gates the repair kernels
     uint32_t n_repairs;          // repair sweeps executed this step
     uint32_t n_pairs_swept;      // pairs covered by the last sweep (k_requery appends after them)
+    uint32_t n_pairs_k4;         // pairs emitted by K4 (the per-body adjacency of K5 covers exactly these)
+    // component-local repair (k_repair_local): bodies / pairs whose result the new pairs can influence
+    uint32_t n_dirty, n_dpairs, dirty_bump, n_dheavy, dirty_all, n_hits_cleared;
+    uint32_t dirty_level[3];     // bodies appended to the dirty list per BFS level (rotating)
+    uint32_t n_resweep;          // stats: pairs re-swept by repair rounds this step
     uint32_t n_escapees_total;   // stats: escapees of the first sweep
     // uniform grid of the current step; re-derived by k_finish_step whenever the margin changes
     GridParams grid;
@@ -1189,7 +1194,7 @@ __global__ void __launch_bounds__(256)
     k_sweep(const Bodies B, const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
             uint32_t* __restrict__ frontier0, uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax,
             uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
-            uint32_t esc_cap, const uint32_t* __restrict__ gate) {
+            uint32_t esc_cap, const uint32_t* __restrict__ gate, const uint32_t* __restrict__ list) {
     if (gate && *gate == 0) return;  // uniform across the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
     __shared__ FrontierStage fs;
@@ -1197,10 +1202,15 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const uint32_t np = min(ctl->n_pairs, pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    // round 0 frontier: pairs at the head of all their chains
-    for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gsz) {
-        const uint32_t pid = p0 + threadIdx.x;
-        if (pid < np && __ldcg(&pair_link(pairs, pid)[2]) == 0) stage_push(fs, pid);
+    // round 0 frontier: pairs at the head of all their chains.  First sweep: every pair is a candidate for it;
+    // repair sweep (list != nullptr): only the pairs of the dirty components are swept again.
+    const uint32_t nl = list ? ctl->n_dpairs : np;
+    for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < nl; p0 += gsz) {
+        const uint32_t li = p0 + threadIdx.x;
+        if (li < nl) {
+            const uint32_t pid = list ? list[li] : li;
+            if (__ldcg(&pair_link(pairs, pid)[2]) == 0) stage_push(fs, pid);
+        }
         stage_flush(fs, frontier0, &ctl->frontier_n[0], blockDim.x);
     }
     stage_flush(fs, frontier0, &ctl->frontier_n[0], FB_CAP);
@@ -1284,8 +1294,9 @@ __global__ void __launch_bounds__(256)
         if (maxabs > 0.0f) atomicMax(&ctl->max_abs_disp_bits, __float_as_uint(maxabs));
     }
     if (gtid == 0) {
-        ctl->n_rounds = rounds;
+        ctl->n_rounds = max(ctl->n_rounds, rounds);
         ctl->n_pairs_swept = np;
+        if (!list) ctl->n_pairs_k4 = np;
     }
 }
 
@@ -1294,9 +1305,8 @@ __global__ void __launch_bounds__(256)
 //  k_requery : for every escapee x, find the bodies y with swept(x) ^ swept(y) != {} that are NOT
 //              candidates yet, append those pairs, raise ctl->repair_needed.  One warp per escapee; the
 //              grid rows its query box covers are contiguous runs of the cell-sorted AABB array.
-//  k_restore : (gated) undo the sweep: re-integrate the bodies written by hit pairs from the untouched
-//              input buffers, clear hit flags / chain counters / pending / escapee marks.
-//  k_recount : (gated) chain degrees over old + new pairs.  Then scan, fill, sort and sweep run again.
+//  k_repair_local : (gated) undo and re-chain only the connected components the new pairs touch (see below);
+//              the repair sweep then covers those pairs only.
 // When k_requery appends nothing the last sweep saw every pair that could intersect at its turn: the
 // result equals the reference's full O(N^2) sweep.
 // ---------------------------------------------------------------------------------------------
@@ -1381,63 +1391,266 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void __launch_bounds__(256)
-    k_restore(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ sval,
-              const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
-              uint32_t* __restrict__ chain_cnt, float* __restrict__ dmax, float* __restrict__ reach, Ctl* ctl,
-              float dt, float d16, float d18, float d35) {
-    if (ctl->repair_needed == 0) return;
-    const uint32_t np = min(ctl->n_pairs, pair_cap);
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (uint32_t pid = gtid; pid < np; pid += gsz) {
-        uint4 r = pairs[2 * (size_t)pid];
-        pairs[2 * (size_t)pid + 1] = link_init();
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const uint32_t t = s ? r.y : r.x;
-            if (t & TOPBIT) continue;
-            chain_cnt[t] = 0;
-            if (r.w & TOPBIT) {  // the sweep wrote this body: recompute its post-integration state (idempotent)
-                const uint32_t s0 = sval[t];  // its slot in the untouched input set
-                float4 p = B0.P(s0), v = B0.V(s0);
-                const float4 a = A0[s0];
-                if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
-                B1.P(t) = p;
-                B1.V(t) = v;
-                // the pairs within the grown reach are candidates now: commit it (several pairs may share t: the max
-                // is atomic, non-negative floats order like their bit patterns), start a fresh sweep record
-                const float dm = dmax[t];
-                if (dm != 0.0f) {
-                    atomicMax(reinterpret_cast<uint32_t*>(&reach[t]), __float_as_uint(dm * REACH_SLACK));
-                    dmax[t] = 0.0f;
-                }
-            }
-        }
-        if (r.w & TOPBIT) pairs[2 * (size_t)pid].w = r.w & ~TOPBIT;
-    }
+// ---------------------------------------------------------------------------------------------
+// Component-local repair (ONE cooperative launch, gated on ctl->repair_needed).  The pairs that verification
+// appended can only change the result of bodies in their connected components of the sweep-pair graph; every other
+// component keeps the result of the sweep that already ran.  Phases (a grid barrier between them):
+//   seed     dynamic endpoints of the new pairs are DIRTY
+//   closure  breadth-first over the per-body adjacency of K5 (+ the few pairs appended since K4), level by level
+//   restore  dirty bodies go back to their post-integration state; their pairs are collected (each once), lose their
+//            hit flag and links; every escapee commits its reach
+//   chains   degrees, segments (bump allocation in adj2), fill, sort by partner rank, successor links, pending
+// The repair sweep then runs over the collected pairs only (k_sweep, list mode).  If more than a third of the live
+// bodies turn dirty (a pile: one giant component) everything is declared dirty and the same code re-does it all.
+// ---------------------------------------------------------------------------------------------
+struct RepairArrays {
+    uint32_t* dirty_bits;        // per slot
+    uint32_t* dlist;             // dirty bodies
+    uint32_t* dpairs;            // pairs of the dirty components
+    uint32_t* offs2;             // per slot: start of the body's segment in adj2
+    uint32_t* deg2;              // per slot: its length
+    unsigned long long* adj2;    // chain entries of the dirty bodies
+    uint32_t* dheavy;            // dirty bodies whose chain needs the block-wide sorter
+    uint32_t dheavy_cap;
+};
+
+__device__ __forceinline__ bool mark_dirty(uint32_t x, const RepairArrays& ra, Ctl* ctl, uint32_t* level_counter) {
+    const uint32_t bit = 1u << (x & 31u);
+    if (atomicOr(&ra.dirty_bits[x >> 5], bit) & bit) return false;
+    ra.dlist[atomicAdd(&ctl->n_dirty, 1u)] = x;
+    atomicAdd(level_counter, 1u);
+    return true;
+}
+__device__ __forceinline__ bool is_dirty(uint32_t x, const RepairArrays& ra) {
+    return (__ldcg(&ra.dirty_bits[x >> 5]) >> (x & 31u)) & 1u;
 }
 
 __global__ void __launch_bounds__(256)
-    k_recount(const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ chain_cnt, Ctl* ctl) {
-    if (ctl->repair_needed == 0) return;
-    const uint32_t np = min(ctl->n_pairs, pair_cap);
+    k_repair_local(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
+                   const unsigned long long* __restrict__ adj, uint32_t* __restrict__ chain_cnt,
+                   const uint32_t* __restrict__ perm, const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
+                   float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ escapees,
+                   uint32_t esc_cap, RepairArrays ra, Ctl* ctl, float dt, float d16, float d18, float d35) {
+    if (ctl->repair_needed == 0) return;  // uniform: nobody reaches a barrier
+    cg::grid_group grid = cg::this_grid();
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (uint32_t pid = gtid; pid < np; pid += gsz) {
-        const uint4 r = pairs[2 * (size_t)pid];
+    const uint32_t n = ctl->n;
+    const uint32_t np0 = ctl->n_pairs_k4, np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    if (gtid == 0) {
+        ctl->n_dirty = 0, ctl->n_dpairs = 0, ctl->dirty_bump = 0, ctl->n_dheavy = 0, ctl->dirty_all = 0;
+        ctl->n_hits_cleared = 0;
+        ctl->dirty_level[0] = ctl->dirty_level[1] = ctl->dirty_level[2] = 0;
+    }
+    grid.sync();
+    // ---- seed (counted as level 0) ----
+    for (uint32_t i = np1 + gtid; i < np2; i += gsz) {
+        const uint4 r = pairs[2 * (size_t)i];
+        if (!(r.x & TOPBIT)) mark_dirty(r.x, ra, ctl, &ctl->dirty_level[0]);
+        if (!(r.y & TOPBIT)) mark_dirty(r.y & ~TOPBIT, ra, ctl, &ctl->dirty_level[0]);
+    }
+    grid.sync();
+    // ---- closure, level by level: level k reads the bodies [lb, le) and appends level k+1 ----
+    uint32_t lb = 0, le = __ldcg(&ctl->dirty_level[0]);
+    bool all = false;
+    for (uint32_t lvl = 0; le > lb; ++lvl) {
+        // counter of level lvl+2 was last read at the end of level lvl-1 (behind that barrier)
+        if (gtid == 0) ctl->dirty_level[(lvl + 2u) % 3u] = 0u;
+        uint32_t* nxt = &ctl->dirty_level[(lvl + 1u) % 3u];
+        for (uint32_t i = lb + gtid; i < le; i += gsz) {
+            const uint32_t x = __ldcg(&ra.dlist[i]);
+            for (uint32_t e = offs[x]; e < offs[x + 1]; ++e) {
+                const uint32_t ent = (uint32_t)adj[e];
+                const uint4 r = pairs[2 * (size_t)(ent & ~TOPBIT)];
+                const uint32_t y = (ent & TOPBIT) ? r.x : r.y;  // the partner of x in this pair
+                if (!(y & TOPBIT)) mark_dirty(y, ra, ctl, nxt);
+            }
+        }
+        // pairs appended since K4 are not in the adjacency: scan them (a few hundred)
+        for (uint32_t i = np0 + gtid; i < np2; i += gsz) {
+            const uint4 r = pairs[2 * (size_t)i];
+            if ((r.x | r.y) & TOPBIT) continue;
+            const bool dx = is_dirty(r.x, ra), dy = is_dirty(r.y, ra);
+            if (dx != dy) mark_dirty(dx ? r.y : r.x, ra, ctl, nxt);
+        }
+        grid.sync();
+        lb = le;
+        le += __ldcg(nxt);
+        if (le > n / 3u + 1024u) {  // (uniform: every thread computes the same le)
+            all = true;
+            break;
+        }
+    }
+    if (all) {  // one giant component: everything is dirty
+        grid.sync();  // everybody has left the loop before the list is rebuilt
+        if (gtid == 0) ctl->n_dirty = 0, ctl->dirty_all = 1;
+        grid.sync();
+        for (uint32_t x = gtid; x < n; x += gsz) {
+            const uint32_t f = __float_as_uint(A0[perm[x]].w);
+            if (f & F_STATIC) continue;
+            atomicOr(&ra.dirty_bits[x >> 5], 1u << (x & 31u));
+            ra.dlist[atomicAdd(&ctl->n_dirty, 1u)] = x;
+        }
+        grid.sync();
+    }
+    const uint32_t nd = __ldcg(&ctl->n_dirty);
+    // ---- restore the dirty bodies, collect their pairs ----
+    uint32_t cleared = 0;
+    for (uint32_t i = gtid; i < nd; i += gsz) {
+        const uint32_t x = __ldcg(&ra.dlist[i]);
+        const uint32_t s0 = perm[x];  // its slot in the untouched input set
+        float4 p = B0.P(s0), v = B0.V(s0);
+        const float4 a = A0[s0];
+        if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
+        B1.P(x) = p;
+        B1.V(x) = v;
+        const float dm = dmax[x];
+        if (dm != 0.0f) {  // the pairs within the grown reach are candidates now: commit it, start a fresh record
+            reach[x] = fmaxf(reach[x], dm * REACH_SLACK);
+            dmax[x] = 0.0f;
+        }
+        chain_cnt[x] = 0;
+        for (uint32_t e = offs[x]; e < offs[x + 1]; ++e) {
+            const uint32_t ent = (uint32_t)adj[e], pid = ent & ~TOPBIT;
+            const uint4 r = pairs[2 * (size_t)pid];
+            // a pair is collected by its first dynamic endpoint (all its dynamic endpoints are dirty)
+            if ((ent & TOPBIT) && !(r.x & TOPBIT)) continue;
+            ra.dpairs[atomicAdd(&ctl->n_dpairs, 1u)] = pid;
+            if (r.w & TOPBIT) {
+                pairs[2 * (size_t)pid].w = r.w & ~TOPBIT;
+                ++cleared;
+            }
+            pairs[2 * (size_t)pid + 1] = link_init();
+        }
+    }
+    for (uint32_t i = np0 + gtid; i < np2; i += gsz) {  // pairs appended since K4
+        const uint4 r = pairs[2 * (size_t)i];
+        const bool d = (!(r.x & TOPBIT) && is_dirty(r.x, ra)) || (!(r.y & TOPBIT) && is_dirty(r.y & ~TOPBIT, ra));
+        if (!d) continue;
+        ra.dpairs[atomicAdd(&ctl->n_dpairs, 1u)] = i;
+        if (r.w & TOPBIT) {
+            pairs[2 * (size_t)i].w = r.w & ~TOPBIT;
+            ++cleared;
+        }
+        pairs[2 * (size_t)i + 1] = link_init();
+    }
+    {  // every escapee commits the reach of the sweep that ran (clean ones keep their sweep record)
+        const uint32_t ne = min(ctl->n_escapees, esc_cap);
+        for (uint32_t i = gtid; i < ne; i += gsz) {
+            const uint32_t x = escapees[i];
+            if (!is_dirty(x, ra)) reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
+        }
+    }
+    cleared = __reduce_add_sync(0xffffffffu, cleared);
+    if ((threadIdx.x & 31) == 0 && cleared) atomicAdd(&ctl->n_hits_cleared, cleared);
+    grid.sync();
+    // ---- chains of the dirty bodies ----
+    const uint32_t ndp = __ldcg(&ctl->n_dpairs);
+    for (uint32_t j = gtid; j < ndp; j += gsz) {  // degrees
+        const uint4 r = pairs[2 * (size_t)__ldcg(&ra.dpairs[j])];
         if (!(r.x & TOPBIT)) atomicAdd(&chain_cnt[r.x], 1u);
         if (!(r.y & TOPBIT)) atomicAdd(&chain_cnt[r.y], 1u);
     }
+    grid.sync();
+    for (uint32_t i = gtid; i < nd; i += gsz) {  // segments
+        const uint32_t x = __ldcg(&ra.dlist[i]);
+        const uint32_t d = __ldcg(&chain_cnt[x]);
+        ra.deg2[x] = d;
+        ra.offs2[x] = d ? atomicAdd(&ctl->dirty_bump, d) : 0u;
+    }
+    grid.sync();
+    for (uint32_t j = gtid; j < ndp; j += gsz) {  // fill
+        const uint32_t pid = __ldcg(&ra.dpairs[j]);
+        const uint4 r = pairs[2 * (size_t)pid];
+        const uint32_t rk_a = r.z & ~TOPBIT, rk_b = r.w & ~TOPBIT;
+        if (!(r.x & TOPBIT)) {
+            const uint32_t a = r.x;
+            ra.adj2[__ldcg(&ra.offs2[a]) + atomicSub(&chain_cnt[a], 1u) - 1u] = ((unsigned long long)rk_b << 32) | pid;
+        }
+        if (!(r.y & TOPBIT)) {
+            const uint32_t b = r.y;
+            ra.adj2[__ldcg(&ra.offs2[b]) + atomicSub(&chain_cnt[b], 1u) - 1u] =
+                ((unsigned long long)rk_a << 32) | TOPBIT | pid;
+        }
+    }
+    grid.sync();
+    for (uint32_t i = gtid; i < nd; i += gsz) {  // sort + link (short chains)
+        const uint32_t x = __ldcg(&ra.dlist[i]);
+        const uint32_t d = __ldcg(&ra.deg2[x]);
+        if (d == 0) continue;
+        if (d > CHAIN_INLINE) {
+            const uint32_t hs = atomicAdd(&ctl->n_dheavy, 1u);
+            if (hs < ra.dheavy_cap)
+                ra.dheavy[hs] = x;
+            else
+                atomicOr(&ctl->step_flags, SF_HEAVY_OVERFLOW);
+            continue;
+        }
+        unsigned long long* seg = ra.adj2 + __ldcg(&ra.offs2[x]);
+        // the segment was filled by other SMs in the previous phase: fetch it from L2 once, sort a private copy
+        unsigned long long buf[CHAIN_INLINE];
+        for (uint32_t k = 0; k < d; ++k) buf[k] = __ldcg(&seg[k]);
+        for (uint32_t k = 1; k < d; ++k) {
+            const unsigned long long v = buf[k];
+            uint32_t j = k;
+            while (j > 0 && buf[j - 1] > v) {
+                buf[j] = buf[j - 1];
+                --j;
+            }
+            buf[j] = v;
+        }
+        for (uint32_t k = 1; k < d; ++k) {
+            const uint32_t prev = (uint32_t)buf[k - 1], cur = (uint32_t)buf[k] & ~TOPBIT;
+            pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
+            atomicAdd(&pair_link(pairs, cur)[2], 1u);
+        }
+    }
+    grid.sync();
+    {  // heavy chains: one CTA per body, bitonic sort in global memory (same network as k_sort_heavy)
+        const uint32_t nh = min(__ldcg(&ctl->n_dheavy), ra.dheavy_cap);
+        for (uint32_t hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+            const uint32_t x = __ldcg(&ra.dheavy[hi]);
+            unsigned long long* seg = ra.adj2 + __ldcg(&ra.offs2[x]);
+            const uint32_t d = __ldcg(&ra.deg2[x]);
+            uint32_t m = 1;
+            while (m < d) m <<= 1;
+            for (uint32_t k = 2; k <= m; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
+                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                        const uint32_t l = i ^ mask;
+                        if (l > i && l < d) {
+                            const unsigned long long vi = __ldcg(&seg[i]), vl = __ldcg(&seg[l]);
+                            if (vi > vl) {
+                                __stcg(&seg[i], vl);
+                                __stcg(&seg[l], vi);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t k = threadIdx.x + 1; k < d; k += blockDim.x) {
+                const uint32_t prev = (uint32_t)__ldcg(&seg[k - 1]), cur = (uint32_t)__ldcg(&seg[k]) & ~TOPBIT;
+                pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
+                atomicAdd(&pair_link(pairs, cur)[2], 1u);
+            }
+            __syncthreads();
+        }
+    }
+    grid.sync();
+    // ---- leave the dirty marks clean for the next round; per-sweep counters back to zero ----
+    for (uint32_t i = gtid; i < nd; i += gsz) {
+        const uint32_t x = __ldcg(&ra.dlist[i]);
+        atomicAnd(&ra.dirty_bits[x >> 5], ~(1u << (x & 31u)));
+    }
+    if (gtid == 0) {
+        ctl->n_contacts -= min(ctl->n_contacts, ctl->n_hits_cleared);
+        ctl->frontier_n[0] = ctl->frontier_n[1] = ctl->frontier_n[2] = 0;
+        ctl->n_repairs += 1;
+        ctl->n_resweep += ndp;
+    }
 }
 
-// between k_recount and the repair sweep: per-sweep counters back to zero (after every reader of them ran)
-__global__ void k_repair_reset(Ctl* ctl) {
-    if (ctl->repair_needed == 0) return;
-    ctl->max_disp_bits = 0;
-    ctl->n_contacts = 0;
-    ctl->n_heavy = 0;
-    ctl->frontier_n[0] = ctl->frontier_n[1] = ctl->frontier_n[2] = 0;
-    ctl->n_repairs += 1;
-}
 // after the repair sweep: the next k_requery decides again
 __global__ void k_repair_done(Ctl* ctl) { ctl->repair_needed = 0; }
 
@@ -1520,6 +1733,8 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.n_pairs = 0, c.n_snapshot = 0, c.n_contacts = 0, c.n_rounds = 0, c.max_disp_bits = 0;
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.step_flags = 0;
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
+    c.n_pairs_k4 = 0, c.n_dirty = 0, c.n_dpairs = 0, c.dirty_bump = 0, c.n_dheavy = 0, c.dirty_all = 0;
+    c.n_hits_cleared = 0, c.n_resweep = 0, c.dirty_level[0] = c.dirty_level[1] = c.dirty_level[2] = 0;
     c.n_watch = 0, c.n_activated = 0, c.n_requeried = 0;
     c.n_recv = 0, c.n_sent[0] = 0, c.n_sent[1] = 0, c.n_migrated_out = 0, c.n_migrated_in = 0, c.n_unverified = 0;
     c.taint_flag[0] = 0, c.taint_flag[1] = 0, c.taint_flag[2] = 0;
