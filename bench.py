@@ -354,7 +354,7 @@ def run_reference(args) -> dict | None:
     return {
         "impl": "reference", "metric": "body-steps/sec", "value": r["value"], "unit": "body-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "bodies": gen.get("n"), "dt": float(DT), "box": gen.get("L"),
                    "parallelism": "host CPU"},

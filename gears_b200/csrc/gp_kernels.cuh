@@ -1190,7 +1190,8 @@ __device__ __forceinline__ void track_move(const BodyRW& x, uint32_t ix, float4 
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int COOP_THREADS = 768;  // cooperative kernels: ONE large CTA per SM (a grid barrier costs per CTA)
+__global__ void __launch_bounds__(COOP_THREADS, 1)
     k_sweep(const Bodies B, const float4* __restrict__ box, uint4* __restrict__ pairs, uint32_t pair_cap,
             uint32_t* __restrict__ frontier0, uint32_t* __restrict__ frontier1, Ctl* ctl, float* __restrict__ dmax,
             uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
@@ -1425,7 +1426,7 @@ __device__ __forceinline__ bool is_dirty(uint32_t x, const RepairArrays& ra) {
     return (__ldcg(&ra.dirty_bits[x >> 5]) >> (x & 31u)) & 1u;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(COOP_THREADS, 1)
     k_repair_local(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
                    const unsigned long long* __restrict__ adj, uint32_t* __restrict__ chain_cnt,
                    const uint32_t* __restrict__ perm, const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
@@ -1760,7 +1761,7 @@ __device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __r
 
 // ONE cooperative launch: clear, seed, propagate to the fixed point (a grid barrier per round), count.
 constexpr uint32_t TAINT_MAX_ROUNDS = 64;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(COOP_THREADS, 1)
     k_taint_closure(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
                     const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits,
                     const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,

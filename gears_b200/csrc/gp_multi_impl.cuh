@@ -188,7 +188,7 @@ static void gp_multi_enqueue_verification(gp_multi* m) {
     const float4* A = w->A[w->cur ^ 1];
     Ctl* ctl = w->ctl;
     void* args[] = {&sbox, &dmax, &reach, &mvb, &tb, &pairs, &pair_cap, &watch, &A, &ctl};
-    cudaLaunchCooperativeKernel((void*)k_taint_closure, dim3(m->taint_grid), dim3(256), args, 0, w->st);
+    cudaLaunchCooperativeKernel((void*)k_taint_closure, dim3(m->taint_grid), dim3(COOP_THREADS), args, 0, w->st);
     w->launches += 1;
 }
 
@@ -248,11 +248,11 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
         }
         m->proposal = c.max_exchange ? c.max_exchange : 2u * std::max(counts[0], counts[1]) + 8192u;
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_taint_closure, 256, 0) != cudaSuccess || occ < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_taint_closure, COOP_THREADS, 0) != cudaSuccess || occ < 1) {
             rs = fail(w, GP_ERR_CUDA, "slab setup: no occupancy for the verification kernel");
             break;
         }
-        m->taint_grid = std::min(occ, 4) * w->sm_count;
+        m->taint_grid = w->sm_count;
         if (cudaStreamSynchronize(w->st) != cudaSuccess) rs = fail(w, GP_ERR_CUDA, "slab setup failed");
     } while (0);
     if (rs != GP_OK) {
