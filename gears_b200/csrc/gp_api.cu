@@ -41,6 +41,7 @@ struct gp_world {
     int cur = 0;
     float* ext = nullptr;
     uint32_t* slot_of = nullptr;  // body id -> current slot (rebuilt on demand: slots change every step)
+    float4* rawbox = nullptr;        // per body id: the un-rotated collision box (ray cast, obstacle grid)
     uint32_t* entity_dev = nullptr;  // caller's entity ids as uploaded (become the body ids of a slab world)
     bool have_entity = false;
     bool slot_valid = false;
@@ -129,7 +130,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 static void free_all(gp_world* w) {
-    void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of, w->entity_dev,
+    void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of, w->entity_dev, w->rawbox,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
                     w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
                     w->frontier[0], w->frontier[1], w->heavy, w->dmax, w->reach, w->escapees, w->moved_bits, w->esc_bits, w->watch, w->dirty_bits, w->dlist, w->dpairs, w->offs2, w->deg2, w->adj2, w->dheavy, w->ctl, w->ctl_snap, w->d_small, w->stage};
@@ -250,6 +251,7 @@ static gp_status alloc_bodies(gp_world* w, uint32_t cap) {
     CK(dmalloc(&w->ext, cap));
     CK(dmalloc(&w->slot_of, cap));
     CK(dmalloc(&w->entity_dev, cap));
+    CK(dmalloc(&w->rawbox, 2 * (size_t)cap));
     CK(dmalloc(&w->sbox, 2 * (size_t)cap));
     CK(dmalloc(&w->key, cap));
     CK(dmalloc(&w->lrank, cap));
@@ -467,7 +469,7 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
             acc3 ? (const float*)(sg + o_acc) : nullptr, (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
             (const float*)(sg + o_mass), (const float*)(sg + o_rest), (const uint8_t*)(sg + o_stat),
             entity ? (const uint32_t*)(sg + o_ent) : nullptr, rank ? (const uint32_t*)(sg + o_rank) : nullptr,
-            Bodies{w->B[0]}, w->A[0], w->ext, 0, nullptr);
+            Bodies{w->B[0]}, w->A[0], w->ext, 0, nullptr, w->rawbox);
         w->launches++;
         CK(cudaGetLastError());
         w->have_entity = entity != nullptr;
@@ -582,7 +584,7 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
                                             (const float*)(sg + o_bmin), (const float*)(sg + o_bmax),
                                             (const float*)(sg + o_mass), (const float*)(sg + o_rest),
                                             (const uint8_t*)(sg + o_stat), nullptr, nullptr, Bodies{w->B[w->cur]},
-                                            w->A[w->cur], nullptr, 1, w->slot_of);
+                                            w->A[w->cur], nullptr, 1, w->slot_of, w->rawbox);
     w->launches++;
     CK(cudaGetLastError());
     // a body that outgrew the cell joins the big list; the grid itself is kept
@@ -1047,6 +1049,100 @@ extern "C" gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint
     } while (0);
     cudaFree(k0), cudaFree(k1), cudaFree(v0), cudaFree(v1), cudaFree(cnt), cudaFree(hist), cudaFree(outp);
     return rs;
+}
+
+// ---- "next" rows ----
+static gp_status next_rows_ready(gp_world* w, const char* what) {
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "%s before gp_upload", what);
+    if (w->multi) return fail(w, GP_ERR_STATE, "%s addresses bodies by upload index: not available on a slab world", what);
+    CK(cudaSetDevice(w->device));
+    return ensure_slot_map(w);
+}
+
+extern "C" gp_status gp_instances(gp_world* w, const float* rot4, const float* scale3, float* out25) {
+    if (!w || !out25) return GP_ERR_BAD_ARG;
+    gp_status s = next_rows_ready(w, "gp_instances");
+    if (s != GP_OK) return s;
+    const uint32_t n = w->n;
+    if (n == 0) return GP_OK;
+    const size_t b_rot = ((size_t)n * 16 + 255) & ~(size_t)255, b_sc = ((size_t)n * 12 + 255) & ~(size_t)255;
+    const size_t b_out = (size_t)n * 100;
+    s = ensure_stage(w, b_rot + b_sc + b_out + 256);
+    if (s != GP_OK) return s;
+    float* d_rot = (float*)w->stage;
+    float* d_sc = (float*)(w->stage + b_rot);
+    float* d_out = (float*)(w->stage + b_rot + b_sc);
+    if (rot4) CK(cudaMemcpyAsync(d_rot, rot4, (size_t)n * 16, cudaMemcpyHostToDevice, w->st));
+    if (scale3) CK(cudaMemcpyAsync(d_sc, scale3, (size_t)n * 12, cudaMemcpyHostToDevice, w->st));
+    k_instances<<<cdiv(n, 128), 128, 0, w->st>>>(n, Bodies{w->B[w->cur]}, rot4 ? d_rot : nullptr, scale3 ? d_sc : nullptr,
+                                                d_out);
+    w->launches++;
+    CK(cudaMemcpyAsync(out25, d_out, b_out, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_raycast(gp_world* w, uint32_t nrays, const float* origin3, const float* dir3, uint32_t ntargets,
+                                const uint32_t* targets, uint8_t* hits) {
+    if (!w || !hits || (nrays && (!origin3 || !dir3))) return GP_ERR_BAD_ARG;
+    gp_status s = next_rows_ready(w, "gp_raycast");
+    if (s != GP_OK) return s;
+    if (!targets) ntargets = w->n;
+    for (uint32_t i = 0; targets && i < ntargets; ++i)
+        if (targets[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_raycast: targets[%u]=%u out of range", i, targets[i]);
+    const size_t total = (size_t)nrays * ntargets;
+    if (total == 0) return GP_OK;
+    const size_t b_ray = ((size_t)nrays * 12 + 255) & ~(size_t)255, b_t = ((size_t)ntargets * 4 + 255) & ~(size_t)255;
+    s = ensure_stage(w, 2 * b_ray + b_t + total + 256);
+    if (s != GP_OK) return s;
+    float* d_o = (float*)w->stage;
+    float* d_d = (float*)(w->stage + b_ray);
+    uint32_t* d_t = (uint32_t*)(w->stage + 2 * b_ray);
+    uint8_t* d_h = (uint8_t*)(w->stage + 2 * b_ray + b_t);
+    CK(cudaMemcpyAsync(d_o, origin3, (size_t)nrays * 12, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemcpyAsync(d_d, dir3, (size_t)nrays * 12, cudaMemcpyHostToDevice, w->st));
+    if (targets) CK(cudaMemcpyAsync(d_t, targets, (size_t)ntargets * 4, cudaMemcpyHostToDevice, w->st));
+    k_raycast<<<cdiv(total, 256), 256, 0, w->st>>>(nrays, d_o, d_d, ntargets, targets ? d_t : nullptr, w->slot_of,
+                                                  Bodies{w->B[w->cur]}, w->rawbox, d_h);
+    w->launches++;
+    CK(cudaMemcpyAsync(hits, d_h, total, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_obstacle_grid(gp_world* w, uint32_t k, const uint32_t* idx, float cell_size,
+                                      const int32_t origin[3], const uint32_t dims[3], uint32_t* bitmap,
+                                      int32_t bounds_out[6]) {
+    if (!w || !origin || !dims || !bitmap) return GP_ERR_BAD_ARG;
+    gp_status s = next_rows_ready(w, "gp_obstacle_grid");
+    if (s != GP_OK) return s;
+    if (!idx) k = w->n;
+    for (uint32_t i = 0; idx && i < k; ++i)
+        if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_obstacle_grid: idx[%u]=%u out of range", i, idx[i]);
+    const unsigned long long cells = (unsigned long long)dims[0] * dims[1] * dims[2];
+    if (cells == 0 || cells > (1ull << 36)) return fail(w, GP_ERR_BAD_ARG, "gp_obstacle_grid: bad dims");
+    const size_t words = (size_t)((cells + 31) / 32);
+    const size_t b_idx = ((size_t)k * 4 + 255) & ~(size_t)255;
+    s = ensure_stage(w, b_idx + words * 4 + 256 + 64);
+    if (s != GP_OK) return s;
+    uint32_t* d_idx = (uint32_t*)w->stage;
+    int* d_bounds = (int*)(w->stage + b_idx);
+    uint32_t* d_bits = (uint32_t*)(w->stage + b_idx + 64);
+    const int init[6] = {2147483647, 2147483647, 2147483647, -2147483647 - 1, -2147483647 - 1, -2147483647 - 1};
+    CK(cudaMemcpyAsync(d_bounds, init, sizeof init, cudaMemcpyHostToDevice, w->st));
+    CK(cudaMemsetAsync(d_bits, 0, words * 4, w->st));
+    if (idx && k) CK(cudaMemcpyAsync(d_idx, idx, (size_t)k * 4, cudaMemcpyHostToDevice, w->st));
+    if (k) {
+        k_obstacle_grid<<<cdiv((uint64_t)k * 32, 256), 256, 0, w->st>>>(k, idx ? d_idx : nullptr, w->slot_of,
+                                                                        Bodies{w->B[w->cur]}, w->rawbox, cell_size, origin[0],
+                                                                        origin[1], origin[2], dims[0], dims[1], dims[2], d_bits,
+                                                                        d_bounds);
+        w->launches++;
+    }
+    CK(cudaMemcpyAsync(bitmap, d_bits, words * 4, cudaMemcpyDeviceToHost, w->st));
+    if (bounds_out) CK(cudaMemcpyAsync(bounds_out, d_bounds, sizeof init, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
 }
 
 // ---- test hooks ----

@@ -59,26 +59,51 @@ __global__ void __launch_bounds__(SC_THREADS) sc_reduce(const uint32_t* __restri
 
 // out[i] = sum_{j<i} in[j]; the last tile also writes out[n] = grand total.
 // `in` and `out` may be the same array (every thread reads its 16 elements before it writes them).
+// Warp-striped access: item i of lane l sits at warp*512 + i*32 + l, so every load/store instruction of a warp
+// covers one contiguous 128 B line; the scan order is restored through a 32x16 transpose in shared memory.
 __global__ void __launch_bounds__(SC_THREADS) sc_scan(const uint32_t* in, uint32_t n,
                                                       const uint32_t* __restrict__ tile_offsets, uint32_t* out,
                                                       const uint32_t* __restrict__ gate) {
     __shared__ uint32_t sm[33];
+    __shared__ uint32_t tr[SC_THREADS / 32][32 * SC_ITEMS + 32];  // +1 word per 16: conflict-free transposes
     if (gate && *gate == 0) return;
-    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wbase = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)warp * (32 * SC_ITEMS);
+    uint32_t* t = tr[warp];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        const uint64_t p = wbase + (uint64_t)i * 32 + lane;
+        const uint32_t e = i * 32 + lane;  // element index within the warp's 512
+        t[e + (e >> 4)] = (p < n) ? in[p] : 0u;
+    }
+    __syncwarp();
+    // lane l owns the 16 consecutive elements [16 l, 16 l + 16)
     uint32_t v[SC_ITEMS];
     uint32_t s = 0;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
-        v[i] = (base + i < n) ? in[base + i] : 0u;
+        const uint32_t e = lane * SC_ITEMS + i;
+        v[i] = t[e + (e >> 4)];
         s += v[i];
     }
     uint32_t run = block_exclusive_scan_256(s, nullptr, sm) + tile_offsets[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
-        if (base + i < n) out[base + i] = run;
+        const uint32_t e = lane * SC_ITEMS + i;
+        t[e + (e >> 4)] = run;
         run += v[i];
-        if (base + i + 1 == n) out[n] = run;
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        const uint64_t p = wbase + (uint64_t)i * 32 + lane;
+        const uint32_t e = i * 32 + lane;
+        if (p < n) out[p] = t[e + (e >> 4)];
+    }
+    // the grand total goes to out[n]: the thread that owns element n-1 knows it
+    const uint64_t last = (uint64_t)n - 1;
+    // (elements at or beyond n were read as 0, so this thread's running sum after its 16 elements is the total)
+    if (n && last >= wbase && last < wbase + 32 * SC_ITEMS && (uint32_t)((last - wbase) >> 4) == lane) out[n] = run;
 }
 
 // tile_sums: ceil(n/SC_TILE) u32 of scratch.  out has n+1 entries; out == in (in place) is allowed.

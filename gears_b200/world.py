@@ -164,6 +164,36 @@ class PhysicsWorld:
         self.last_unverified = unv[: n.value]
         return ent[: n.value], pos[: n.value], vel[: n.value]
 
+    # -- next rows --
+    def instances(self, rot=None, scale=None) -> np.ndarray:
+        """InstanceRaw of every body (n, 25): 4x4 model + 3x3 normal, column-major (instance.rs:22-42)."""
+        rot, scale = _f32(rot, 4), _f32(scale, 3)
+        out = np.zeros((max(1, self.n), 25), np.float32)
+        self._check(self._lib.gp_instances(self._h, _ptr(rot), _ptr(scale), _ptr(out)))
+        return out[: self.n]
+
+    def raycast(self, origins, dirs, targets=None) -> np.ndarray:
+        """hits[r, t]: Weapon::ray_intersects_aabb (interactive.rs:94-158) of ray r against body targets[t]."""
+        origins, dirs = _f32(origins, 3), _f32(dirs, 3)
+        t = None if targets is None else np.ascontiguousarray(targets, dtype=np.uint32)
+        nt = self.n if t is None else len(t)
+        hits = np.zeros((len(origins), max(1, nt)), np.uint8)
+        self._check(self._lib.gp_raycast(self._h, len(origins), _ptr(origins), _ptr(dirs), nt, _ptr(t), _ptr(hits)))
+        return hits[:, :nt].astype(bool)
+
+    def obstacle_grid(self, cell_size: float, origin, dims, idx=None):
+        """(bitmap as bool array [z, y, x], bounds(6)): PathfindingGrid::add_obstacle (pathfinding.rs:296-338)."""
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32)
+        o = np.ascontiguousarray(origin, dtype=np.int32)
+        d = np.ascontiguousarray(dims, dtype=np.uint32)
+        cells = int(d[0]) * int(d[1]) * int(d[2])
+        bits = np.zeros((cells + 31) // 32, np.uint32)
+        bounds = np.zeros(6, np.int32)
+        self._check(self._lib.gp_obstacle_grid(self._h, 0 if ix is None else len(ix), _ptr(ix), C.c_float(cell_size),
+                                               _ptr(o), _ptr(d), _ptr(bits), _ptr(bounds)))
+        flat = np.unpackbits(bits.view(np.uint8), bitorder="little")[:cells].astype(bool)
+        return flat.reshape(int(d[2]), int(d[1]), int(d[0])), bounds
+
     def pairs(self, which: int) -> np.ndarray:
         n = C.c_uint64()
         self._check(self._lib.gp_pairs(self._h, which, None, 0, C.byref(n)))

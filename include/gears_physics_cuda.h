@@ -204,6 +204,25 @@ gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt, const floa
 gp_status gp_owned_count(gp_world* w, uint32_t* n);
 gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified);
 
+/* ---- next rows: consumers of the body state right after the step ----
+ * All three address bodies by upload index (single-GPU worlds only). */
+/* N1  pass 3 of update_physics (update_systems.rs:489-527): Instance::to_raw (gears-renderer instance.rs:22-31) of
+ * every body in one launch.  out25: n rows of 25 floats = 4x4 model matrix + 3x3 normal matrix, both column-major
+ * as cgmath's `.into()` lays them out (= struct InstanceRaw, 100 B).  rot4 / scale3: host arrays in upload order
+ * (Pos3.rot in cgmath order; Instance.scale); NULL = identity / (1,1,1). */
+gp_status gp_instances(gp_world* w, const float* rot4, const float* scale3, float* out25);
+/* N3  Weapon::ray_intersects_aabb (gears-ecs interactive.rs:94-158), batched: hits[r * ntargets + t] = 1 if ray r hits
+ * body targets[t] (targets NULL: all bodies, ntargets ignored = n).  Like the reference, the test uses
+ * pos + collision_box.min/max and ignores rotation and scale. */
+gp_status gp_raycast(gp_world* w, uint32_t nrays, const float* origin3, const float* dir3, uint32_t ntargets,
+                     const uint32_t* targets, uint8_t* hits);
+/* N4  PathfindingGrid::add_obstacle (gears-ecs pathfinding.rs:296-338) for k bodies (idx NULL: all): sets the bits of
+ * the cells GridPos::from_world_pos(pos + box.min) ..= from_world_pos(pos + box.max) (pathfinding.rs:57-63) in a dense
+ * bitmap over the window [origin, origin + dims): bit = (x-ox) + dims[0]*((y-oy) + dims[1]*(z-oz)); cells outside the
+ * window are dropped.  bounds_out (nullable): min xyz / max xyz cell over all obstacles, as the reference tracks. */
+gp_status gp_obstacle_grid(gp_world* w, uint32_t k, const uint32_t* idx, float cell_size, const int32_t origin[3],
+                           const uint32_t dims[3], uint32_t* bitmap, int32_t bounds_out[6]);
+
 /* ---- test hooks (used by tests/ only; stable but not part of the drop-in surface) ---- */
 gp_status gp_test_radix_sort(int32_t device, uint32_t n, uint32_t key_bits, uint32_t* keys_inout,
                              uint32_t* vals_inout);

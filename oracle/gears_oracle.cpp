@@ -664,6 +664,78 @@ void go_cap_velocity(float* vel3) {
     vel3[0] = v.x, vel3[1] = v.y, vel3[2] = v.z;
 }
 
+// ---- "next" rows ----------------------------------------------------------
+// N1  Instance::to_raw, crates/gears-renderer/src/instance.rs:22-31:
+//     model = Matrix4::from_translation(p) * Matrix4::from(q) * Matrix4::from_nonuniform_scale(s); normal = Matrix3::from(q).
+//     cgmath 0.18.0 semantics restated (not vendored): Matrix3/4::from(Quaternion) builds x2 = x+x ..., xx2 = x2*x ...,
+//     columns (1-yy2-zz2, xy2+sz2, xz2-sy2), (xy2-sz2, 1-xx2-zz2, yz2+sx2), (xz2+sy2, yz2-sx2, 1-xx2-yy2);
+//     Matrix4*Matrix4: column j = ((a*r[j][0] + b*r[j][1]) + c*r[j][2]) + d*r[j][3] with a..d the columns of the left
+//     operand.  Output: 16 floats column-major + 9 floats column-major (what `.into()` yields).
+static void mat4_mul(const float* A, const float* R, float* O) {  // column-major 4x4
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            float acc = A[0 * 4 + i] * R[j * 4 + 0];
+            acc = acc + A[1 * 4 + i] * R[j * 4 + 1];
+            acc = acc + A[2 * 4 + i] * R[j * 4 + 2];
+            acc = acc + A[3 * 4 + i] * R[j * 4 + 3];
+            O[j * 4 + i] = acc;
+        }
+}
+void go_instance_raw(const float* pos3, const float* rot4 /*v.xyz, s*/, const float* scale3, float* out25) {
+    const float x = rot4[0], y = rot4[1], z = rot4[2], w = rot4[3];
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx2 = x2 * x, xy2 = x2 * y, xz2 = x2 * z, yy2 = y2 * y, yz2 = y2 * z, zz2 = z2 * z;
+    const float sy2 = y2 * w, sz2 = z2 * w, sx2 = x2 * w;
+    const float r3[9] = {1.0f - yy2 - zz2, xy2 + sz2, xz2 - sy2, xy2 - sz2, 1.0f - xx2 - zz2,
+                         yz2 + sx2,        xz2 + sy2, yz2 - sx2, 1.0f - xx2 - yy2};
+    const float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, pos3[0], pos3[1], pos3[2], 1};
+    const float R[16] = {r3[0], r3[1], r3[2], 0, r3[3], r3[4], r3[5], 0, r3[6], r3[7], r3[8], 0, 0, 0, 0, 1};
+    const float S[16] = {scale3[0], 0, 0, 0, 0, scale3[1], 0, 0, 0, 0, scale3[2], 0, 0, 0, 0, 1};
+    float TR[16];
+    mat4_mul(T, R, TR);
+    mat4_mul(TR, S, out25);
+    for (int k = 0; k < 9; ++k) out25[16 + k] = r3[k];
+}
+
+// N3  Weapon::ray_intersects_aabb, crates/gears-ecs/src/components/interactive.rs:94-158 (slab method; uses
+//     pos + collision_box.min/max: rotation and scale are ignored by the reference)
+int go_ray_intersects_aabb(const float* origin3, const float* dir3, const float* pos3, const float* bmin3,
+                           const float* bmax3) {
+    float tmin = 0.0f, tmax = 3.40282347e+38f;  // f32::MAX
+    for (int i = 0; i < 3; ++i) {
+        const float o = origin3[i], d = dir3[i];
+        const float mn = pos3[i] + bmin3[i], mx = pos3[i] + bmax3[i];
+        if (fabsf(d) < 1e-8f) {
+            if (o < mn || o > mx) return 0;
+        } else {
+            const float inv = 1.0f / d;
+            float t1 = (mn - o) * inv, t2 = (mx - o) * inv;
+            if (t1 > t2) std::swap(t1, t2);
+            tmin = fmaxf(tmin, t1);  // f32::max / f32::min = IEEE maxNum / minNum
+            tmax = fminf(tmax, t2);
+            if (tmin > tmax) return 0;
+        }
+    }
+    return (tmax >= 0.0f && tmin <= tmax) ? 1 : 0;
+}
+
+// N4  PathfindingGrid::add_obstacle, crates/gears-ecs/src/components/pathfinding.rs:296-338 with
+//     GridPos::from_world_pos (:57-63): cell = round(coord / cell_size) (f32::round = half away from zero, `as i32`
+//     saturates, NaN -> 0).  Writes the inclusive cell range [lo, hi] of the obstacle.
+static int32_t f2i_sat(float f) {
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (-2147483647 - 1);
+    return (int32_t)f;
+}
+void go_obstacle_cells(const float* pos3, const float* bmin3, const float* bmax3, float cell_size, int32_t* lo3,
+                       int32_t* hi3) {
+    for (int i = 0; i < 3; ++i) {
+        lo3[i] = f2i_sat(roundf((pos3[i] + bmin3[i]) / cell_size));
+        hi3[i] = f2i_sat(roundf((pos3[i] + bmax3[i]) / cell_size));
+    }
+}
+
 // exp(-c*dt) for c in {1.6, 1.8, 3.5} with the platform libm expf — what Rust's f32::exp calls.
 void go_damping_factors(float dt, float* out3) {
     out3[0] = expf(-1.6f * dt);

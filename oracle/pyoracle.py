@@ -145,5 +145,27 @@ def damping_factors(dt: float):
     return out
 
 
+def instance_raw(pos, rot, scale) -> np.ndarray:
+    """Instance::to_raw (instance.rs:22-31): 16 model + 9 normal floats, column-major."""
+    out = np.zeros(25, np.float32)
+    pos, rot, scale = _f(pos, 3), _f(rot, 4), _f(scale, 3)
+    lib().go_instance_raw(_p(pos, f32p), _p(rot, f32p), _p(scale, f32p), _p(out, f32p))
+    return out
+
+
+def ray_intersects_aabb(origin, direction, pos, bmin, bmax) -> bool:
+    a = [_f(x, 3) for x in (origin, direction, pos, bmin, bmax)]
+    lib().go_ray_intersects_aabb.restype = C.c_int
+    return bool(lib().go_ray_intersects_aabb(*[_p(x, f32p) for x in a]))
+
+
+def obstacle_cells(pos, bmin, bmax, cell_size: float):
+    lo, hi = np.zeros(3, np.int32), np.zeros(3, np.int32)
+    a = [_f(x, 3) for x in (pos, bmin, bmax)]
+    lib().go_obstacle_cells(*[_p(x, f32p) for x in a], C.c_float(cell_size), lo.ctypes.data_as(C.c_void_p),
+                            hi.ctypes.data_as(C.c_void_p))
+    return lo, hi
+
+
 def max_threads() -> int:
     return int(lib().go_max_threads())

@@ -1,0 +1,124 @@
+"""Next rows of the scope table: instance hand-off (N1), ray cast (N3), obstacle grid (N4).
+CPU part: the oracle against hand-derived answers and the reference's own expectations; GPU part: bit-exact
+parity of the CUDA kernels with the oracle through the C ABI."""
+import numpy as np
+import pytest
+
+from gears_b200 import scenes
+
+DT = np.float32(1.0) / np.float32(60.0)
+
+
+# ---------------- oracle (CPU) ----------------
+def test_oracle_instance_raw_identity_and_scale(oracle):
+    r = oracle.instance_raw([1, 2, 3], [0, 0, 0, 1], [2, 3, 4])
+    model = r[:16].reshape(4, 4).T  # column-major -> rows
+    assert np.array_equal(model, np.float32([[2, 0, 0, 1], [0, 3, 0, 2], [0, 0, 4, 3], [0, 0, 0, 1]]))
+    assert np.array_equal(r[16:].reshape(3, 3), np.eye(3, dtype=np.float32))
+
+
+def test_oracle_instance_raw_quarter_turn_about_y(oracle):
+    h = np.float32(np.sqrt(0.5))
+    r = oracle.instance_raw([0, 0, 0], [0, h, 0, h], [1, 1, 1])
+    normal = r[16:].reshape(3, 3).T
+    # a rotation of +90 degrees about y maps x -> -z, z -> x
+    assert np.allclose(normal @ np.float32([1, 0, 0]), [0, 0, -1], atol=1e-6)
+    assert np.allclose(normal @ np.float32([0, 0, 1]), [1, 0, 0], atol=1e-6)
+
+
+def test_oracle_ray_slab_cases(oracle):
+    box = ([-1, -1, -1], [1, 1, 1])
+    assert oracle.ray_intersects_aabb([0, 0, -5], [0, 0, 1], [0, 0, 0], *box)
+    assert not oracle.ray_intersects_aabb([0, 0, -5], [0, 0, -1], [0, 0, 0], *box)      # behind the origin
+    assert not oracle.ray_intersects_aabb([3, 0, -5], [0, 0, 1], [0, 0, 0], *box)       # parallel, outside the slab
+    assert oracle.ray_intersects_aabb([1, 0, -5], [0, 0, 1], [0, 0, 0], *box)           # grazing the face counts
+    assert oracle.ray_intersects_aabb([0, 0, 0], [1, 0, 0], [0, 0, 0], *box)            # origin inside
+    assert oracle.ray_intersects_aabb([-5, -5, -5], [1, 1, 1], [0, 0, 0], *box)
+
+
+def test_oracle_obstacle_cells_round_half_away_from_zero(oracle):
+    lo, hi = oracle.obstacle_cells([0.4, 2.5, -2.5], [-1, -1, -1], [1, 1, 1], 1.0)
+    assert list(lo) == [-1, 2, -4] and list(hi) == [1, 4, -2]
+    lo, hi = oracle.obstacle_cells([10, 0, 0], [-3, -0.1, -3], [3, 0.1, 3], 2.0)
+    assert list(lo) == [4, 0, -2] and list(hi) == [7, 0, 2]   # 3.5 -> 4, 6.5 -> 7, -1.5 -> -2
+
+
+# ---------------- CUDA vs oracle (GPU) ----------------
+def _world_after_steps(s, steps=3):
+    from gears_b200.world import PhysicsWorld
+    w = PhysicsWorld()
+    w.upload(s)
+    for _ in range(steps):
+        w.step(DT)
+    return w
+
+
+@pytest.mark.gpu
+def test_instances_match_oracle_bitwise(oracle):
+    n = 3000
+    s = scenes.uniform(n, L=25.0, seed=201, rank_seed=202)
+    m = s["pos"].shape[0]
+    rng = np.random.default_rng(7)
+    q = rng.normal(size=(m, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    sc = (0.5 + rng.random((m, 3))).astype(np.float32)
+    with _world_after_steps(s) as w:
+        pos, _ = w.download()
+        got = w.instances(q, sc)
+        got_id = w.instances()
+    for i in range(0, m, 7):
+        assert np.array_equal(got[i].view(np.uint32), oracle.instance_raw(pos[i], q[i], sc[i]).view(np.uint32)), i
+        assert np.array_equal(got_id[i].view(np.uint32),
+                              oracle.instance_raw(pos[i], [0, 0, 0, 1], [1, 1, 1]).view(np.uint32)), i
+
+
+@pytest.mark.gpu
+def test_raycast_matches_oracle(oracle):
+    s = scenes.uniform(400, L=12.0, seed=211, rank_seed=212)
+    s["box_min"][:50] = (-0.2, -0.9, -0.4)   # asymmetric boxes: the reference uses the raw box, not the rotated one
+    s["box_max"][:50] = (0.7, 0.3, 0.6)
+    rng = np.random.default_rng(11)
+    nr = 40
+    org = (rng.random((nr, 3)) * 12).astype(np.float32)
+    d = rng.normal(size=(nr, 3)).astype(np.float32)
+    d[0] = (0, 0, 1)
+    d[1] = (1, 0, 0)          # axis-parallel rays exercise the |dir| < 1e-8 branch
+    d[2] = (0, -1, 0)
+    with _world_after_steps(s) as w:
+        pos, _ = w.download()
+        hits = w.raycast(org, d)
+        sub = np.array([3, 17, 399, 400], np.uint32)
+        hits_sub = w.raycast(org, d, targets=sub)
+    m = s["pos"].shape[0]
+    ref = np.zeros((nr, m), bool)
+    for r in range(nr):
+        for t in range(m):
+            ref[r, t] = oracle.ray_intersects_aabb(org[r], d[r], pos[t], s["box_min"][t], s["box_max"][t])
+    assert ref.any() and not ref.all()
+    assert np.array_equal(hits, ref)
+    assert np.array_equal(hits_sub, ref[:, sub])
+
+
+@pytest.mark.gpu
+def test_obstacle_grid_matches_oracle(oracle):
+    s = scenes.mixed(600, L=40.0, seed=221, rank_seed=222)
+    cell = 1.5
+    origin, dims = np.int32([-2, -2, -2]), np.uint32([34, 20, 34])   # clips part of the scene on purpose
+    with _world_after_steps(s, steps=2) as w:
+        pos, _ = w.download()
+        statics = np.nonzero(s["is_static"])[0].astype(np.uint32)
+        grid, bounds = w.obstacle_grid(cell, origin, dims, idx=statics)
+        grid_all, _ = w.obstacle_grid(cell, origin, dims)
+    ref = np.zeros((dims[2], dims[1], dims[0]), bool)
+    blo, bhi = np.full(3, 2**31 - 1, np.int64), np.full(3, -2**31, np.int64)
+    for i in statics:
+        lo, hi = oracle.obstacle_cells(pos[i], s["box_min"][i], s["box_max"][i], cell)
+        blo, bhi = np.minimum(blo, lo), np.maximum(bhi, hi)
+        l = np.maximum(lo.astype(np.int64) - origin, 0)
+        h = np.minimum(hi.astype(np.int64) - origin, dims.astype(np.int64) - 1)
+        if np.all(l <= h):
+            ref[l[2]:h[2] + 1, l[1]:h[1] + 1, l[0]:h[0] + 1] = True
+    assert ref.any()
+    assert np.array_equal(grid, ref)
+    assert np.array_equal(bounds, np.concatenate([blo, bhi]).astype(np.int32))
+    assert grid_all.sum() >= grid.sum() and np.all(grid_all[grid])
