@@ -360,8 +360,8 @@ static gp_status setup_grid(gp_world* w) {
         for (int k = 0; k <= b; ++k) n_grid += h_small[k];
         const double vol = std::max(1e-30, ((double)hi[0] - lo[0]) * ((double)hi[1] - lo[1]) * ((double)hi[2] - lo[2]));
         const char* env = getenv("GP_TARGET_OCC");
-        const double occ = env ? atof(env) : 0.5;  // measured on uniform_16M: pair find gets cheaper with finer cells,
-                                                   // the table scan dearer; 0.5 body per cell is the sweet spot
+        const double occ = env ? atof(env) : 0.3;  // measured on uniform_16M: pair find gets cheaper with finer cells,
+                                                   // the table memset + scan dearer; ~0.3 body per cell is the sweet spot
         if (n_grid > 0 && occ > 0 && !user_bounds_degenerate(lo, hi)) {
             const float auto_cell = (float)cbrt(occ * vol / (double)n_grid);
             if (auto_cell > cell_min) cell_min = auto_cell;
