@@ -39,6 +39,8 @@ WORKLOADS = {
                     dict(max_pairs=4 * 16_777_216)),
     "uniform_1M": (dict(kind="uniform", n=1_048_576, L=275.8, seed=1003, rank_seed=2003),
                    dict(max_pairs=8 * 1_048_576)),
+    "uniform_2M": (dict(kind="uniform", n=2_097_152, L=347.5, seed=1003, rank_seed=2003),
+                   dict(max_pairs=8 * 2_097_152)),
     "uniform_100k": (dict(kind="uniform", n=100_000, L=126.0, seed=1001, rank_seed=2001),
                      dict()),
     "pile_1M": (dict(kind="pile", nx=100, ny=100, nz=100, seed=1002, rank_seed=2002), dict()),
