@@ -674,7 +674,7 @@ static gp_status enqueue_chains_and_sweep(gp_world* w) {
     k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
                                                    w->ctl, nullptr);
     k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
-    k_sort_heavy<<<64, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
+    k_sort_heavy<<<w->sm_count * 8, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
     w->launches += 3;
     prof_mark(w, 5);
     return enqueue_sweep(w, nullptr, false);

@@ -1034,39 +1034,74 @@ __global__ void __launch_bounds__(256)
     link_chain(adj + b, 0u, d, 1u, pairs);
 }
 
-// one CTA per heavy body: bitonic sort of its segment in global memory (any length)
+// A chain longer than CHAIN_INLINE is sorted by ONE WARP: bitonic network in its all-ascending form (the first
+// sub-step of each stage mirrors the partner: l = i ^ (k-1), the rest use l = i ^ j), so every compare-exchange moves
+// the smaller key to the lower index and the virtual +inf padding at [d, m) never has to move.  Up to WSORT_SMEM
+// entries the chain is staged in the warp's shared-memory buffer; longer chains are sorted in place in global memory
+// (through L2: the lanes exchange data there).  Then the warp links the chain (successor pointers + pending counts).
+constexpr uint32_t WSORT_SMEM = 128;
+__device__ __forceinline__ void warp_sort_and_link(unsigned long long* seg, uint32_t d, unsigned long long* wbuf,
+                                                   uint4* __restrict__ pairs) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t m = 1;
+    while (m < d) m <<= 1;
+    if (d <= WSORT_SMEM) {
+        for (uint32_t i = lane; i < d; i += 32) wbuf[i] = __ldcg(&seg[i]);
+        __syncwarp();
+        for (uint32_t k = 2; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
+                for (uint32_t i = lane; i < m; i += 32) {
+                    const uint32_t l = i ^ mask;
+                    if (l > i && l < d) {
+                        const unsigned long long vi = wbuf[i], vl = wbuf[l];
+                        if (vi > vl) wbuf[i] = vl, wbuf[l] = vi;
+                    }
+                }
+                __syncwarp();
+            }
+        for (uint32_t i = lane; i < d; i += 32) __stcg(&seg[i], wbuf[i]);
+        for (uint32_t i = lane + 1; i < d; i += 32) {
+            const uint32_t prev = (uint32_t)wbuf[i - 1], cur = (uint32_t)wbuf[i] & ~TOPBIT;
+            pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
+            atomicAdd(&pair_link(pairs, cur)[2], 1u);
+        }
+        __syncwarp();
+        return;
+    }
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
+            for (uint32_t i = lane; i < m; i += 32) {
+                const uint32_t l = i ^ mask;
+                if (l > i && l < d) {
+                    const unsigned long long vi = __ldcg(&seg[i]), vl = __ldcg(&seg[l]);
+                    if (vi > vl) __stcg(&seg[i], vl), __stcg(&seg[l], vi);
+                }
+            }
+            __syncwarp();
+        }
+    for (uint32_t i = lane + 1; i < d; i += 32) {
+        const uint32_t prev = (uint32_t)__ldcg(&seg[i - 1]), cur = (uint32_t)__ldcg(&seg[i]) & ~TOPBIT;
+        pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
+        atomicAdd(&pair_link(pairs, cur)[2], 1u);
+    }
+    __syncwarp();
+}
+
+// one warp per heavy body (a dense pile makes EVERY chain heavy: a million of them)
 __global__ void __launch_bounds__(256)
     k_sort_heavy(const uint32_t* __restrict__ offs, unsigned long long* __restrict__ adj, uint4* __restrict__ pairs,
                  const uint32_t* __restrict__ heavy, uint32_t heavy_cap, const Ctl* ctl,
                  const uint32_t* __restrict__ gate) {
+    __shared__ unsigned long long wbuf[8][WSORT_SMEM];
     if (gate && *gate == 0) return;
     const uint32_t nh = min(ctl->n_heavy, heavy_cap);
-    for (uint32_t hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t hi = warp; hi < nh; hi += nwarps) {
         const uint32_t x = heavy[hi];
         const uint32_t b = offs[x], d = offs[x + 1] - b;
-        uint32_t m = 1;
-        while (m < d) m <<= 1;
-        // bitonic network in its all-ascending form (first sub-step of each stage mirrors the partner:
-        // l = i ^ (k-1), the rest use l = i ^ j).  Every compare-exchange moves the smaller key to the
-        // lower index, so the virtual +inf padding at [d, m) never has to move.
-        for (uint32_t k = 2; k <= m; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
-                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                    const uint32_t l = i ^ mask;
-                    if (l > i && l < d) {
-                        const unsigned long long vi = adj[b + i], vl = adj[b + l];
-                        if (vi > vl) {
-                            adj[b + i] = vl;
-                            adj[b + l] = vi;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        link_chain(adj + b, threadIdx.x, d, blockDim.x, pairs);
-        __syncthreads();
+        warp_sort_and_link(adj + b, d, wbuf[threadIdx.x >> 5], pairs);
     }
 }
 
@@ -1610,36 +1645,12 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
         }
     }
     grid.sync();
-    {  // heavy chains: one CTA per body, bitonic sort in global memory (same network as k_sort_heavy)
+    {  // heavy chains: one warp per body (same sorter as k_sort_heavy)
+        __shared__ unsigned long long wbuf[COOP_THREADS / 32][WSORT_SMEM];
         const uint32_t nh = min(__ldcg(&ctl->n_dheavy), ra.dheavy_cap);
-        for (uint32_t hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+        for (uint32_t hi = gtid >> 5; hi < nh; hi += gsz >> 5) {
             const uint32_t x = __ldcg(&ra.dheavy[hi]);
-            unsigned long long* seg = ra.adj2 + __ldcg(&ra.offs2[x]);
-            const uint32_t d = __ldcg(&ra.deg2[x]);
-            uint32_t m = 1;
-            while (m < d) m <<= 1;
-            for (uint32_t k = 2; k <= m; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    const uint32_t mask = (j == (k >> 1)) ? (k - 1u) : j;
-                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                        const uint32_t l = i ^ mask;
-                        if (l > i && l < d) {
-                            const unsigned long long vi = __ldcg(&seg[i]), vl = __ldcg(&seg[l]);
-                            if (vi > vl) {
-                                __stcg(&seg[i], vl);
-                                __stcg(&seg[l], vi);
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            for (uint32_t k = threadIdx.x + 1; k < d; k += blockDim.x) {
-                const uint32_t prev = (uint32_t)__ldcg(&seg[k - 1]), cur = (uint32_t)__ldcg(&seg[k]) & ~TOPBIT;
-                pair_link(pairs, prev & ~TOPBIT)[prev >> 31] = cur;
-                atomicAdd(&pair_link(pairs, cur)[2], 1u);
-            }
-            __syncthreads();
+            warp_sort_and_link(ra.adj2 + __ldcg(&ra.offs2[x]), __ldcg(&ra.deg2[x]), wbuf[threadIdx.x >> 5], pairs);
         }
     }
     grid.sync();
