@@ -31,7 +31,7 @@ from gears_b200 import scenes  # noqa: E402
 DT = np.float32(1.0) / np.float32(60.0)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's main kernel, from the ncu --set full capture
 # under profiles/ (uniform_16M, 1 GPU); None = not captured for that group
-NCU_TRAFFIC = {"find_pairs": 942e6, "scatter": 3.78e9, "keys": 1.73e9}
+NCU_TRAFFIC = {"find_pairs": 1.027e9, "scatter": 3.85e9, "keys": 1.88e9, "sweep": 1.73e9}
 
 WORKLOADS = {
     # name: (generator kwargs, world kwargs)
