@@ -18,7 +18,7 @@ GP_FLAG_RECORD_PAIRS = 0x1
 GP_FLAG_NO_RETRY = 0x2
 GP_FLAG_PROFILE = 0x4
 GP_NUM_KERNEL_GROUPS = 8
-KERNEL_GROUPS = ["keys", "cell_scan", "scatter", "find_pairs", "chains", "sweep", "finish", "exchange"]
+KERNEL_GROUPS = ["keys", "exchange", "cell_scan", "scatter", "find_pairs", "chains", "sweep", "finish"]
 GP_UNIQUE_ID_BYTES = 128
 
 f32p = C.POINTER(C.c_float)

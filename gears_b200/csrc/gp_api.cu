@@ -676,7 +676,7 @@ static gp_status enqueue_chains_and_sweep(gp_world* w) {
     k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
     k_sort_heavy<<<w->sm_count * 8, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
     w->launches += 3;
-    prof_mark(w, 5);
+    prof_mark(w, 6);
     return enqueue_sweep(w, nullptr, false);
 }
 
@@ -748,7 +748,7 @@ static gp_status enqueue_phase_a(gp_world* w, float dt, const float* damp3) {
         CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
         if (w->multi) {
             gp_multi_begin_step(w->multi);  // (peer-to-peer transport: wait for buffer credit)
-            k_keys<true><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
+            k_keys<true><<<cdiv(nb, 256 * K1_TILES), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
                                                         gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), dt, d[0],
                                                         d[1], d[2]);
             w->launches += 1;
@@ -771,32 +771,33 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
     const uint32_t nb = n_bound(w);
     if (nb) {
         if (w->multi) {
+            prof_mark(w, 1);
             gp_multi_before_append(w->multi);  // (peer-to-peer transport: wait for the neighbours' ready flags)
             k_append<<<w->sm_count * 2, 256, 0, st>>>(gp_multi_recv(w->multi, 0), gp_multi_recv(w->multi, 1),
                                                       Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl);
             w->launches++;
             gp_multi_after_append(w->multi);   // (peer-to-peer transport: hand the buffer credit back)
         }
-        prof_mark(w, 1);
+        prof_mark(w, 2);
         const uint32_t ncnt = w->max_cells + 2;
         exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
-        prof_mark(w, 2);
+        prof_mark(w, 3);
         k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
                                                        w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
                                                        w->moved_bits, w->esc_bits, w->LB, w->ctl, dt, d[0], d[1], d[2]);
         w->launches += 1;
-        prof_mark(w, 3);
+        prof_mark(w, 4);
         k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
             w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
-        prof_mark(w, 4);
+        prof_mark(w, 5);
         enqueue_chains_and_sweep(w);
         // speculative broad phase: look for pairs the candidate set missed, repair, look again
         enqueue_verify(w);
         for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
         if (w->multi) gp_multi_enqueue_verification(w->multi);
     }
-    prof_mark(w, 6);
+    prof_mark(w, 7);
     k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
     w->launches++;
     prof_end_step(w);

@@ -162,11 +162,12 @@ uint64_t gp_kernel_launches(const gp_world* w);
 #define GP_NUM_KERNEL_GROUPS 8
 typedef struct gp_kernel_times {
     uint32_t steps;                       /* steps covered by the sums                                */
-    float ms[GP_NUM_KERNEL_GROUPS];       /* 0 cell keys + histogram (K1; on a slab also packing),     */
-                                          /* 1 cell scan (K2; on a slab also append), 2 scatter into    */
-                                          /* cell order + integrate + AABBs (K3), 3 pair find (K4),     */
-                                          /* 4 chain build (K5: scan, fill, sort+link), 5 contact sweep */
-                                          /* + verification + repair rounds (K6), 6 finish, 7 unused    */
+    float ms[GP_NUM_KERNEL_GROUPS];       /* 0 cell keys + histogram (K1; on a slab also packing/sending),  */
+                                          /* 1 slab exchange: wait for the neighbours + append (multi-GPU),  */
+                                          /* 2 cell scan (K2), 3 scatter into cell order + integrate + AABBs */
+                                          /* (K3), 4 pair find (K4), 5 chain build (K5: scan, fill, sort +   */
+                                          /* link), 6 contact sweep + verification + repair rounds (K6),     */
+                                          /* 7 finish                                                        */
     uint32_t launches[GP_NUM_KERNEL_GROUPS]; /* kernel launches per group over those steps            */
 } gp_kernel_times;
 gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
