@@ -1,0 +1,79 @@
+"""Two processes, two GPUs (one rank per GPU): the slab worlds exchange halo copies and migrating bodies with the
+peer-to-peer transport (and, second case, with ncclSend/ncclRecv) and must reproduce the single-GPU result bit for
+bit.  Skipped on boxes with fewer than two GPUs (the single-GPU slab tests cover the same logic in one process)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from gears_b200 import scenes, slabs
+    from gears_b200.world import PhysicsWorld
+    rank, ws, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    DT = np.float32(1) / np.float32(60)
+    steps = 10
+    s = scenes.uniform(200_000, L=158.7, seed=301, rank_seed=302)
+    rep = slabs.big_static_mask(s, 4.0)
+    faces = slabs.bounds(s, ws, "balanced", replicate=rep, halo=6.0)
+    part = slabs.partition(s, faces, rep)[rank]
+    w = PhysicsWorld(device=lr, max_bodies=int(part["pos"].shape[0] * 1.5) + 65536)
+    w.upload(part)
+    slabs.comm_init(w, dist, rank, ws, faces, halo=6.0, device=torch.device("cuda", lr))
+    w.step_async(DT, steps)
+    st = w.sync()
+    ent, pos, vel = w.download_owned()
+    out = [None] * ws if rank == 0 else None
+    dist.gather_object((ent, pos, vel, st["unverified_total"], st["steps_inexact"], st["n_migrated_out"]), out, dst=0)
+    if rank == 0:
+        e = np.concatenate([o[0] for o in out]); p = np.concatenate([o[1] for o in out]); v = np.concatenate([o[2] for o in out])
+        order = np.argsort(e, kind="stable")
+        n = s["pos"].shape[0]
+        assert np.array_equal(e[order], np.arange(n, dtype=np.uint32)), "every body owned exactly once"
+        assert sum(o[3] for o in out) == 0 and sum(o[4] for o in out) == 0
+        with PhysicsWorld(device=lr) as ref:
+            ref.upload(s)
+            ref.step_async(DT, steps)
+            assert ref.sync()["steps_inexact"] == 0
+            rp, rv = ref.download()
+        assert np.array_equal(p[order].view(np.uint32), rp.view(np.uint32)), "positions differ from the single-GPU run"
+        assert np.array_equal(v[order].view(np.uint32), rv.view(np.uint32)), "velocities differ from the single-GPU run"
+        print("MULTI_OK transport=" + os.environ.get("GP_SLAB_TRANSPORT", "p2p"))
+    w.close()
+    dist.destroy_process_group()
+""")
+
+
+def _gpus() -> int:
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_two_ranks_match_single_gpu(tmp_path, transport):
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ)
+    if transport == "nccl":
+        env["GP_SLAB_TRANSPORT"] = "nccl"
+    else:
+        env.pop("GP_SLAB_TRANSPORT", None)
+    port = "29731" if transport == "p2p" else "29732"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", port, str(script)], env=env,
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
