@@ -162,8 +162,6 @@ static void gp_multi_after_append(gp_multi* m) {
 static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
     gp_world* w = m->w;
     if (m->local || m->p2p) return GP_OK;  // gp_step_group drives the copies / K1 already wrote into the neighbour
-    static const bool skip = getenv("GP_DEBUG_SKIP_EXCHANGE") != nullptr;  // timing experiments only (results wrong)
-    if (skip) return GP_OK;
     const int rank = m->cfg.rank;
     CKN(g_nccl.GroupStart());
     // fixed-size messages (the count travels in the header): no host round trip to size them

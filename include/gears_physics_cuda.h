@@ -37,7 +37,8 @@ typedef struct gp_world gp_world;
 typedef enum gp_status {
     GP_OK = 0,
     /* warnings (> 0): the call completed */
-    GP_WARN_MARGIN_RETRIED = 1, /* a step was re-run with a larger broad-phase margin (result exact)   */
+    GP_WARN_MARGIN_RETRIED = 1, /* bodies out-ran the broad-phase margin or the pair buffers had to grow:  */
+                                /* the step repaired itself / was re-run; the result is exact            */
     /* errors (< 0) */
     GP_ERR_BAD_ARG = -1,
     GP_ERR_CUDA = -2,        /* CUDA runtime error, see gp_last_error                                   */
@@ -61,11 +62,14 @@ typedef struct gp_config {
     int32_t device;       /* CUDA device ordinal                                                      */
     uint32_t max_bodies;  /* capacity; 0 = sized by the first gp_upload                               */
     uint64_t max_pairs;   /* candidate-pair capacity; 0 = 16 * max_bodies (min 1 Mi)                   */
-    float margin_init;    /* initial (and minimum) broad-phase margin mu, RELATIVE: every AABB is     */
-                          /* inflated by mu * (its largest extent); <=0 = 0.05.  Adapts per step.     */
+    float margin_init;    /* initial (and minimum) OUTER broad-phase margin mu, RELATIVE: every AABB   */
+                          /* is inflated by mu * (its largest extent); <=0 = 0.05.  Adapts per step.  */
+                          /* (Candidates within a smaller, self-tuning inner margin enter the contact */
+                          /* sweep at once, the rest wait on a watch list: DESIGN.md section 1.2)     */
     float margin_max;     /* upper bound for the adaptive mu; <=0 = 2.0                               */
-    float cell_size;      /* minimum uniform-grid cell edge; <=0 = auto: (largest grid-class extent)  */
-                          /* * (1 + 2 mu), re-derived on the device whenever mu changes               */
+    float cell_size;      /* minimum uniform-grid cell edge; <=0 = auto: at least (largest grid-class  */
+                          /* extent) * (1 + 2 mu), and no finer than ~0.3 body per cell; re-derived on */
+                          /* the device whenever mu changes                                           */
     uint32_t max_big;     /* bodies larger than the cell go to a brute-force list of at most this     */
                           /* many (0 = 64); the cell grows until the rest fit                         */
     uint32_t flags;
@@ -79,7 +83,7 @@ typedef struct gp_step_stats {
     uint64_t n_snapshot;     /* |S_snapshot|: exact overlaps on the post-integration state            */
     uint64_t n_contacts;     /* |S_sweep|: pairs whose exact test was true at their turn              */
     uint32_t n_rounds;       /* dependency levels executed by the contact sweep                       */
-    uint32_t n_retries;      /* times this step was re-run (margin / capacity)                        */
+    uint32_t n_retries;      /* re-runs for capacity + repair sweeps (component-local) of this step   */
     float margin;            /* relative margin mu used for this step                                 */
     float max_displacement;  /* largest per-axis move of any AABB during the sweep / its extent       */
     float cell_size;
