@@ -44,6 +44,8 @@ WORKLOADS = {
     "uniform_100k": (dict(kind="uniform", n=100_000, L=126.0, seed=1001, rank_seed=2001),
                      dict()),
     "pile_1M": (dict(kind="pile", nx=100, ny=100, nz=100, seed=1002, rank_seed=2002), dict()),
+    # BASELINE configs[4]: 100:1 extent ratio, 10 % static, + floor
+    "mixed_4M": (dict(kind="mixed", n=4_194_304, L=2500.0, seed=1004, rank_seed=2004), dict(max_pairs=4 * 4_194_304)),
 }
 
 
@@ -163,7 +165,8 @@ def run_ours(args) -> dict:
         n_local = int(scene["pos"].shape[0])
         wkw = dict(wkw)
         wkw["max_pairs"] = max(1 << 20, wkw.get("max_pairs", 16 * n_total) // world_size * 2)
-        w = PhysicsWorld(device=local_rank, profile=True, max_bodies=int(n_local * 1.25) + 262144, **wkw)
+        w = PhysicsWorld(device=local_rank, profile=True, max_bodies=int(n_local * 1.25) + 262144,
+                         big_static_only=True, **wkw)
         w.upload(scene)
         slabs.comm_init(w, dist, rank, world_size, faces, halo=args.halo, max_exchange=args.max_exchange,
                         device=torch.device("cuda", local_rank))

@@ -17,6 +17,7 @@ GP_ERR_PAIR_OVERFLOW, GP_ERR_MARGIN, GP_ERR_NCCL, GP_ERR_STATE = -5, -6, -7, -8
 GP_FLAG_RECORD_PAIRS = 0x1
 GP_FLAG_NO_RETRY = 0x2
 GP_FLAG_PROFILE = 0x4
+GP_FLAG_BIG_STATIC_ONLY = 0x8
 GP_NUM_KERNEL_GROUPS = 8
 KERNEL_GROUPS = ["keys", "exchange", "cell_scan", "scatter", "find_pairs", "chains", "sweep", "finish"]
 GP_UNIQUE_ID_BYTES = 128

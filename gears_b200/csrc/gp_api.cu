@@ -188,7 +188,7 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
         if (cudaSetDevice(w->device) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         if (cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
-        if (dmalloc(&w->ctl, 1) || dmalloc(&w->ctl_snap, 1) || dmalloc(&w->d_small, EXT_BUCKETS + 8)) { rs = GP_ERR_CUDA; break; }
+            if (dmalloc(&w->ctl, 1) || dmalloc(&w->ctl_snap, 1) || dmalloc(&w->d_small, 2 * EXT_BUCKETS + 8)) { rs = GP_ERR_CUDA; break; }
         if (cudaMallocHost((void**)&w->h_ctl, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         if (cudaMemset(w->ctl, 0, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         int occ = 0;
@@ -301,14 +301,14 @@ static bool user_bounds_degenerate(const float* lo, const float* hi) {
 static gp_status setup_grid(gp_world* w) {
     const uint32_t n = w->n;
     uint32_t* d_hist = w->d_small;
-    uint32_t* d_bounds = w->d_small + EXT_BUCKETS;
-    uint32_t h_small[EXT_BUCKETS + 8];
-    CK(cudaMemsetAsync(d_hist, 0, EXT_BUCKETS * sizeof(uint32_t), w->st));
+    uint32_t* d_bounds = w->d_small + 2 * EXT_BUCKETS;
+    uint32_t h_small[2 * EXT_BUCKETS + 8];
+    CK(cudaMemsetAsync(d_hist, 0, 2 * EXT_BUCKETS * sizeof(uint32_t), w->st));
     if (n) {
-        k_ext_hist<<<std::min<uint32_t>(cdiv(n, 256), 1024), 256, 0, w->st>>>(n, w->ext, d_hist);
+        k_ext_hist<<<std::min<uint32_t>(cdiv(n, 256), 1024), 256, 0, w->st>>>(n, w->ext, w->A[w->cur], d_hist);
         w->launches++;
     }
-    CK(cudaMemcpyAsync(h_small, d_hist, EXT_BUCKETS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaMemcpyAsync(h_small, d_hist, 2 * EXT_BUCKETS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
     const uint32_t max_big = w->cfg.max_big ? w->cfg.max_big : 64u;
     // smallest bucket edge that leaves at most max_big bodies above it
@@ -317,6 +317,17 @@ static gp_status setup_grid(gp_world* w) {
     for (; b > 0; --b) {
         if (above + h_small[b] > max_big) break;
         above += h_small[b];
+    }
+    if (w->cfg.flags & GP_FLAG_BIG_STATIC_ONLY) {
+        // slab worlds replicate big bodies instead of exchanging them, so only static bodies may be big: the grid
+        // must host every dynamic body, whatever that costs in cell size
+        int b_dyn = 0;
+        for (int k = EXT_BUCKETS - 1; k > 0; --k)
+            if (h_small[EXT_BUCKETS + k]) {
+                b_dyn = k;
+                break;
+            }
+        if (b < b_dyn) b = b_dyn;
     }
     // b = highest bucket that must stay in the grid; its upper edge bounds every grid-class extent
     float thr = ext_bucket_edge(b);
@@ -589,7 +600,7 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
     CK(cudaGetLastError());
     // a body that outgrew the cell joins the big list; the grid itself is kept
     k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->thr, Bodies{w->B[w->cur]}, w->A[w->cur],
-                                                   w->d_small + EXT_BUCKETS);
+                                                   w->d_small + 2 * EXT_BUCKETS);
     w->launches++;
     CK(cudaStreamSynchronize(w->st));
     return GP_OK;

@@ -278,14 +278,19 @@ __device__ __forceinline__ int ext_bucket(float e) {
 }
 __host__ __device__ inline float ext_bucket_edge(int b) { return exp2f((float)(b - 64) * 0.25f); }
 
-__global__ void k_ext_hist(uint32_t n, const float* __restrict__ ext, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[EXT_BUCKETS];
-    for (int i = threadIdx.x; i < EXT_BUCKETS; i += blockDim.x) sh[i] = 0;
+// hist[0 .. EXT_BUCKETS) counts every body, hist[EXT_BUCKETS .. 2 EXT_BUCKETS) the dynamic ones only
+__global__ void k_ext_hist(uint32_t n, const float* __restrict__ ext, const float4* __restrict__ A,
+                           uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[2 * EXT_BUCKETS];
+    for (int i = threadIdx.x; i < 2 * EXT_BUCKETS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&sh[ext_bucket(ext[i])], 1u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = ext_bucket(ext[i]);
+        atomicAdd(&sh[b], 1u);
+        if (!(__float_as_uint(A[i].w) & F_STATIC)) atomicAdd(&sh[EXT_BUCKETS + b], 1u);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < EXT_BUCKETS; i += blockDim.x)
+    for (int i = threadIdx.x; i < 2 * EXT_BUCKETS; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 

@@ -122,6 +122,7 @@ class LocalSlabs:
         for r, part in enumerate(parts):
             kw = dict(world_kw)
             kw.setdefault("max_bodies", int(part["pos"].shape[0] * 1.5) + max(65536, n_total // 8))
+            kw.setdefault("big_static_only", True)
             w = PhysicsWorld(device=devices[r], **kw)
             w.upload(part)
             self.worlds.append(w)

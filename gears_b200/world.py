@@ -35,7 +35,8 @@ def _f32(a, cols=None):
 class PhysicsWorld:
     def __init__(self, device: int = 0, max_bodies: int = 0, max_pairs: int = 0, margin_init: float = 0.0,
                  margin_max: float = 0.0, cell_size: float = 0.0, max_big: int = 0, record_pairs: bool = False,
-                 no_retry: bool = False, profile: bool = False, grid_min=None, grid_max=None):
+                 no_retry: bool = False, profile: bool = False, grid_min=None, grid_max=None,
+                 big_static_only: bool = False):
         self._lib = capi.lib()
         cfg = capi.GpConfig()
         cfg.struct_size = C.sizeof(capi.GpConfig)
@@ -47,7 +48,7 @@ class PhysicsWorld:
         cfg.cell_size = cell_size
         cfg.max_big = max_big
         cfg.flags = (capi.GP_FLAG_RECORD_PAIRS if record_pairs else 0) | (capi.GP_FLAG_NO_RETRY if no_retry else 0) | \
-            (capi.GP_FLAG_PROFILE if profile else 0)
+            (capi.GP_FLAG_PROFILE if profile else 0) | (capi.GP_FLAG_BIG_STATIC_ONLY if big_static_only else 0)
         if grid_min is not None:
             cfg.grid_min[:] = [float(x) for x in grid_min]
             cfg.grid_max[:] = [float(x) for x in grid_max]

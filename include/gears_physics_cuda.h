@@ -54,6 +54,9 @@ typedef enum gp_status {
 /* gp_config.flags */
 #define GP_FLAG_RECORD_PAIRS 0x1u /* keep S_snapshot / S_sweep flags so gp_pairs can be called       */
 #define GP_FLAG_NO_RETRY 0x2u     /* never re-run a step: report GP_ERR_MARGIN/PAIR_OVERFLOW instead  */
+#define GP_FLAG_BIG_STATIC_ONLY 0x8u /* only STATIC bodies may go to the brute-force list (the grid cell grows to  */
+                                    /* host every dynamic body): required for slab worlds, which replicate big   */
+                                    /* bodies on every rank instead of exchanging them                           */
 #define GP_FLAG_PROFILE 0x4u      /* bracket every kernel group of a step with CUDA events on the step */
                                   /* stream; read the sums with gp_kernel_times                        */
 

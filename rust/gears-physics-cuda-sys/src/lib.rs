@@ -28,6 +28,7 @@ pub const GP_ERR_STATE: gp_status = -8;
 pub const GP_FLAG_RECORD_PAIRS: u32 = 0x1;
 pub const GP_FLAG_NO_RETRY: u32 = 0x2;
 pub const GP_FLAG_PROFILE: u32 = 0x4;
+pub const GP_FLAG_BIG_STATIC_ONLY: u32 = 0x8;
 pub const GP_SLAB_NO_VERIFY: u32 = 0x1;
 pub const GP_UNIQUE_ID_BYTES: usize = 128;
 pub const GP_NUM_KERNEL_GROUPS: usize = 8;

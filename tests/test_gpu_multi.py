@@ -26,7 +26,7 @@ WORKER = textwrap.dedent("""
     rep = slabs.big_static_mask(s, 4.0)
     faces = slabs.bounds(s, ws, "balanced", replicate=rep, halo=6.0)
     part = slabs.partition(s, faces, rep)[rank]
-    w = PhysicsWorld(device=lr, max_bodies=int(part["pos"].shape[0] * 1.5) + 65536)
+    w = PhysicsWorld(device=lr, max_bodies=int(part["pos"].shape[0] * 1.5) + 65536, big_static_only=True)
     w.upload(part)
     slabs.comm_init(w, dist, rank, ws, faces, halo=6.0, device=torch.device("cuda", lr))
     w.step_async(DT, steps)
