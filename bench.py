@@ -158,7 +158,8 @@ def run_ours(args) -> dict:
         from gears_b200 import slabs
         ext = (scene["box_max"] - scene["box_min"]).max(axis=1)
         rep = slabs.big_static_mask(scene, 4.0 * float(ext[scene["is_static"] == 0].max()))
-        faces = slabs.bounds(scene, world_size, "balanced", replicate=rep, halo=args.halo)
+        halo_est = args.halo if args.halo > 0 else 4.0 * float(ext[~rep].max())
+        faces = slabs.bounds(scene, world_size, "balanced", replicate=rep, halo=halo_est)
         part = slabs.partition(scene, faces, rep)[rank]
         del scene
         scene = part
@@ -394,7 +395,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768, help="bodies in the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--halo", type=float, default=4.0, help="slab coverage H beyond a face (multi-GPU)")
+    ap.add_argument("--halo", type=float, default=0.0,
+                    help="slab coverage H beyond a face (multi-GPU); 0 = 4 x the largest grid-class extent")
     ap.add_argument("--max-exchange", type=int, default=0, help="records per slab face buffer (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

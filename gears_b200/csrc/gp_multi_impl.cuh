@@ -204,9 +204,9 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
     CK(cudaStreamSynchronize(w->st));
     CK(cudaMemcpy(w->h_ctl, w->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
     Ctl hc = *w->h_ctl;
-    // coverage: three (largest grid-class extents) unless the caller says otherwise: about 2.5 layers of contact
+    // coverage: four (largest grid-class extents) unless the caller says otherwise: about three layers of contact
     // neighbours at the usual margins.  Too small a halo is not silent: the verification counts what it cannot prove.
-    if (!(c.halo > 0)) c.halo = 3.0f * hc.ext_max;
+    if (!(c.halo > 0)) c.halo = 4.0f * hc.ext_max;
     if (c.nranks > 1 && c.x_hi - c.x_lo < 2.0f * c.halo && c.rank > 0 && c.rank + 1 < c.nranks)
         return fail(w, GP_ERR_BAD_ARG, "slab width %g is below twice the halo %g: a body could reach a rank two slabs away",
                     c.x_hi - c.x_lo, c.halo);

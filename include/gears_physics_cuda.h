@@ -197,7 +197,7 @@ typedef struct gp_slab_config {
     uint32_t struct_size;  /* = sizeof(gp_slab_config)                                                      */
     int32_t rank, nranks;  /* slab index along x, number of slabs                                           */
     float x_lo, x_hi;      /* this rank's slab                                                              */
-    float halo;            /* coverage H beyond a face that the neighbour mirrors; <=0 = 3 x the largest    */
+    float halo;            /* coverage H beyond a face that the neighbour mirrors; <=0 = 4 x the largest    */
                            /* grid-class extent.  Inner slabs must be >= 2 H wide                            */
     uint32_t max_exchange; /* records per face buffer; 0 = 2 x (bodies within 2 H of a face today) + 8192.   */
                            /* Both sides of a face must use the same value (messages have a fixed size)     */
