@@ -316,3 +316,48 @@ def test_step_before_upload_is_an_error():
         with pytest.raises(GpError) as e:
             w.step(DT)
         assert e.value.status == -8
+
+
+def _scene_golden_cases():
+    import importlib.util
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_scene_goldens", os.path.join(here, "golden", "make_scene_goldens.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    return gen
+
+
+@pytest.mark.parametrize("name", ["physics_example_ascending_1000", "physics_example_shuffle_1000",
+                                  "uniform_5k_shuffled_20", "pile_8x8x8_60", "mixed_3k_10"])
+def test_scene_goldens(name):
+    """CUDA path vs the COMMITTED fixtures (no live oracle involved)."""
+    gen = _scene_golden_cases()
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scene_goldens.json")))["cases"][name]
+    scene, steps = next((s, k) for n, s, k in gen.cases() if n == name)
+    with world() as w:
+        w.upload(scene)
+        for _ in range(steps):
+            w.step(DT)
+        pos, vel = w.download()
+        sweep, snap = w.pairs(1), w.pairs(0)
+    assert gen.digest(pos) == gold["pos_sha256"] and gen.digest(vel) == gold["vel_sha256"]
+    assert len(sweep) == gold["n_sweep"] and gen.digest(sweep) == gold["sweep_sha256"]
+    assert len(snap) == gold["n_snapshot"] and gen.digest(snap) == gold["snapshot_sha256"]
+
+
+def test_nan_body_does_not_poison_the_others(oracle):
+    """A body with a NaN position (an external writer gone wrong) must neither crash the step nor change any other
+    body: every comparison with NaN is false, in the reference as here."""
+    s = scenes.uniform(3000, L=20.0, seed=91, rank_seed=92)
+    s["pos"][7] = (np.nan, 5.0, 5.0)
+    with world() as w:
+        w.upload(s)
+        for _ in range(3):
+            w.step(DT)
+        pos, vel = w.download()
+    r = oracle.step(s, DT, 3, mode=0)
+    ok = np.ones(len(pos), bool)
+    ok[7] = False
+    assert_same_bits(pos[ok], r["pos"][ok], "pos of the finite bodies")
+    assert_same_bits(vel[ok], r["vel"][ok], "vel of the finite bodies")
+    assert np.isnan(pos[7, 0]) and np.isnan(r["pos"][7, 0])
