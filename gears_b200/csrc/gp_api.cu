@@ -282,11 +282,11 @@ static gp_status alloc_pairs(gp_world* w, uint64_t pair_cap) {
     CK(dmalloc(&w->watch, pair_cap));
     CK(dmalloc(&w->dpairs, pair_cap));
     CK(dmalloc(&w->adj2, 2 * pair_cap));
-    CK(dmalloc(&w->dheavy, w->heavy_cap + 0));
     CK(dmalloc(&w->frontier[0], pair_cap));
     CK(dmalloc(&w->frontier[1], pair_cap));
-    w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);
+    w->heavy_cap = (uint32_t)(2 * pair_cap / CHAIN_INLINE + 16);  // a heavy chain has > CHAIN_INLINE of the 2*pair_cap entries
     CK(dmalloc(&w->heavy, w->heavy_cap));
+    CK(dmalloc(&w->dheavy, w->heavy_cap));
     w->pair_cap = pair_cap;
     return GP_OK;
 }
