@@ -737,7 +737,7 @@ __device__ __forceinline__ float max_separation(const float4 alo, const float4 a
 }
 
 constexpr int FP_THREADS = 256;   // bodies per tile = threads per CTA
-constexpr int FP_RANGES = 6;      // candidate slot ranges per body: 5 cell-row runs + the big list
+constexpr int FP_RANGES = 5;      // candidate slot ranges per body in the flattened walk: 5 cell-row runs
 constexpr int FP_BATCH = 4;       // tests per thread per batch
 constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_WSTAGE = 160;    // staged pair records per warp (flushed above 32: a batch adds <= 128)
@@ -899,8 +899,18 @@ __global__ void __launch_bounds__(FP_THREADS)
                 q0[3] = b3, len[3] = e3 - b3;
                 q0[4] = b4, len[4] = e4 - b4;
             }
-            const uint32_t qb = max(p + 1, n_small);  // big list: every body tests the big bodies after it
-            q0[5] = qb, len[5] = n > qb ? n - qb : 0u;
+        }
+        // big list (a floor, walls: at most max_big bodies): every body tests the big bodies behind it, directly --
+        // one or two tests per body do not deserve the range bookkeeping below.  Warp-uniform loop.
+        {
+            float4 mlo = make_float4(0, 0, 0, 0), mhi = mlo;
+            if (live) mlo = sbox[2 * (size_t)p], mhi = sbox[2 * (size_t)p + 1];
+            for (uint32_t q = n_small; q < n; ++q) {
+                if (live && q > p) test(mlo, mhi, p, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
+                __syncwarp();
+                if (*wcnt > 32u) flush();
+                if (*wwcnt > 32u) flush_watch();
+            }
         }
         // compact the non-empty ranges (thread-major order) and scan their lengths
         uint32_t nne = 0;
