@@ -1,0 +1,125 @@
+// gp_slab_kernels.cuh — multi-GPU slabs: per-step exactness proof, owned-body download, set-up.
+// Part of the physics step; see gp_kernels.cuh for the map of kernels to reference lines.
+#pragma once
+#include "gp_common.cuh"
+#include "gp_pairfind_kernels.cuh"
+#include "gp_repair_kernels.cuh"
+
+namespace gp {
+
+// ---------------------------------------------------------------------------------------------
+// Slab verification (multi-GPU).  A rank knows its own bodies and, per the halo rule, every neighbour body whose
+// inflated AABB comes within H of the shared face.  A body whose own reach (margin, or swept displacement if
+// larger) pokes beyond that coverage may have a partner this rank has never seen: it is TAINTED.  The result of a
+// body can only depend on bodies of its connected component of the candidate graph (sweep pairs + watch pairs), so
+// taint spreads over components; every owned body that stays clean is bit-identical to the single-GPU result
+// (multi-GPU exactness).  n_unverified counts the owned bodies that do not stay clean.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __restrict__ taint_bits, uint32_t* flag) {
+    if ((x | y) & TOPBIT) return;  // an edge through a static body carries nothing
+    const bool tx = (__ldcg(&taint_bits[x >> 5]) >> (x & 31u)) & 1u, ty = (__ldcg(&taint_bits[y >> 5]) >> (y & 31u)) & 1u;
+    if (tx == ty) return;
+    const uint32_t z = tx ? y : x;
+    atomicOr(&taint_bits[z >> 5], 1u << (z & 31u));
+    *flag = 1u;
+}
+
+// ONE cooperative launch: clear, seed, propagate to the fixed point (a grid barrier per round), count.
+constexpr uint32_t TAINT_MAX_ROUNDS = 64;
+__global__ void __launch_bounds__(COOP_THREADS, 1)
+    k_taint_closure(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
+                    const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits,
+                    const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,
+                    const float4* __restrict__ A, Ctl* ctl) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t n = ctl->n;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t wd = gtid; wd < (n + 31u) / 32u; wd += gsz) taint_bits[wd] = 0u;
+    if (gtid == 0) ctl->taint_flag[0] = 0u, ctl->taint_flag[1] = 0u, ctl->taint_flag[2] = 0u;
+    grid.sync();
+    // seeds: bodies whose reach pokes beyond what the neighbours mirror
+    for (uint32_t i = gtid; i < n; i += gsz) {
+        const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
+        if (box_static(lo)) continue;  // static bodies never change: nothing to get wrong
+        float r = box_margin(lo);
+        if ((moved_bits[i >> 5] >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(reach[i], dmax[i] * REACH_SLACK));
+        const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
+        const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
+        if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
+    }
+    grid.sync();
+    const uint32_t np = min(ctl->n_pairs, pair_cap), nw = min(ctl->n_watch, pair_cap);
+    uint32_t it = 0;
+    bool open = true;
+    while (open && it < TAINT_MAX_ROUNDS) {
+        // three rotating flags: round `it` raises flag it%3 and clears flag (it+1)%3, which was last READ at the end
+        // of round it-2, i.e. behind the barrier of round it-1 (with two flags a fast thread would clear the flag a
+        // slow thread is still about to read, and the grid would disagree about leaving the loop)
+        uint32_t* flag = &ctl->taint_flag[it % 3u];
+        if (gtid == 0) ctl->taint_flag[(it + 1u) % 3u] = 0u;
+        for (uint32_t i = gtid; i < np; i += gsz) {
+            const uint4 r = pairs[2 * (size_t)i];
+            taint_edge(r.x, r.y, taint_bits, flag);
+        }
+        for (uint32_t i = gtid; i < nw; i += gsz) {
+            const uint2 r = watch[i];
+            if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, flag);  // (activated entries are among the pairs)
+        }
+        grid.sync();
+        open = __ldcg(flag) != 0u;
+        ++it;
+    }
+    // owned dynamic bodies that are not provably independent of unseen bodies
+    uint32_t c = 0;
+    for (uint32_t i = gtid; i < n; i += gsz) {
+        const uint32_t f = __float_as_uint(A[i].w);
+        if (!(f & (F_GHOST | F_STATIC)) && (open || ((__ldcg(&taint_bits[i >> 5]) >> (i & 31u)) & 1u))) ++c;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->n_unverified, c);
+}
+
+// owned bodies (no halo copies; replicated big statics only on the rank that has no left neighbour) -> host layout
+__global__ void __launch_bounds__(256)
+    k_compact_owned(const Ctl* ctl, const Bodies B, const float4* __restrict__ A, int is_first_rank, uint32_t* counter,
+                    uint32_t* __restrict__ ids, float* __restrict__ pos3, float* __restrict__ vel3,
+                    const uint32_t* __restrict__ taint_bits, uint8_t* __restrict__ unverified) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->n_in) return;  // between steps n_in = the live bodies of the last step
+    const uint32_t f = __float_as_uint(A[i].w);
+    if (f & F_GHOST) return;
+    if ((f & F_BIG) && !is_first_rank) return;
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    const uint32_t s = base + g.thread_rank();
+    if (!ids) return;  // counting pass
+    const float4 p = B.P(i), v = B.V(i);
+    ids[s] = __float_as_uint(B.Lo(i).w);
+    pos3[3 * (size_t)s] = p.x, pos3[3 * (size_t)s + 1] = p.y, pos3[3 * (size_t)s + 2] = p.z;
+    vel3[3 * (size_t)s] = v.x, vel3[3 * (size_t)s + 1] = v.y, vel3[3 * (size_t)s + 2] = v.z;
+    if (taint_bits && unverified) unverified[s] = (taint_bits[i >> 5] >> (i & 31u)) & 1u;  // of the LAST step
+}
+
+// gp_comm_init: body ids become the caller's global entity ids; count what the faces would send right now
+__global__ void k_slab_prepare(uint32_t n, const Bodies B, const float4* __restrict__ A,
+                               const uint32_t* __restrict__ entity, uint32_t* __restrict__ counts /*[3]: L, R, dyn big*/,
+                               const Ctl* ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (entity) B.Lo(i).w = __uint_as_float(entity[i]);  // at upload slot == caller index
+    const uint32_t f = __float_as_uint(A[i].w);
+    if (f & F_BIG) {
+        if (!(f & F_STATIC)) atomicAdd(&counts[2], 1u);
+        return;
+    }
+    const float4 p = B.P(i), lo = B.Lo(i), hi = B.Hi(i);
+    const float wlo = lo.x + p.x, whi = hi.x + p.x;
+    const float m = whi - wlo;  // generous: a margin of one extent
+    if (ctl->has_left && wlo - m < ctl->x_lo + 2.0f * ctl->halo) atomicAdd(&counts[0], 1u);
+    if (ctl->has_right && whi + m > ctl->x_hi - 2.0f * ctl->halo) atomicAdd(&counts[1], 1u);
+}
+
+
+}  // namespace gp

@@ -131,7 +131,9 @@ class LocalSlabs:
         hs = (C.c_void_p * nranks)(*[w._h for w in self.worlds])
         st = self.lib.gp_comm_init_local(hs, nranks, cfgs)
         if st < 0:
-            msg = "; ".join(self.lib.gp_last_error(w._h).decode() for w in self.worlds)
+            msg = "; ".join(m for m in (self.lib.gp_last_error(w._h).decode() for w in self.worlds) if m)
+            for w in self.worlds:
+                w.close()
             raise GpError(st, msg)
         self._hs = hs
         self.n = nranks

@@ -27,7 +27,11 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=gears_physics_cuda");
     println!("cargo:rustc-link-lib=dylib=cudart");
-    for f in ["gp_api.cu", "gp_kernels.cuh", "gp_multi.cuh", "gp_multi_impl.cuh", "radix_sort.cuh", "scan.cuh"] {
+    for f in [
+        "gp_api.cu", "gp_kernels.cuh", "gp_common.cuh", "gp_mirror_kernels.cuh", "gp_cellsort_kernels.cuh",
+        "gp_pairfind_kernels.cuh", "gp_chain_kernels.cuh", "gp_sweep_kernels.cuh", "gp_repair_kernels.cuh",
+        "gp_slab_kernels.cuh", "gp_next_kernels.cuh", "gp_multi.cuh", "gp_multi_impl.cuh", "radix_sort.cuh", "scan.cuh",
+    ] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", repo.join("include/gears_physics_cuda.h").display());

@@ -150,6 +150,28 @@ def test_mixed_sizes_and_statics_on_slabs():
         assert flagged < 6 * 0.02 * n
 
 
+def test_exchange_buffer_overflow_is_reported_not_hidden():
+    """A face buffer that is too small must surface as an error at sync (GP_ERR_CAPACITY), never as silently
+    missing halo copies."""
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import GpError
+    s = scenes.uniform(40_000, L=60.0, seed=151, rank_seed=152)
+    with LocalSlabs(s, 2, max_exchange=16) as g:   # a face needs thousands of records
+        g.step(DT, 2)
+        with pytest.raises(GpError) as e:
+            g.sync()
+        assert e.value.status == -4
+
+
+def test_slab_width_below_twice_the_halo_is_rejected():
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import GpError
+    s = scenes.uniform(20_000, L=40.0, seed=161, rank_seed=162)
+    with pytest.raises(GpError) as e:
+        LocalSlabs(s, 4, halo=8.0)   # inner slabs are ~10 wide: a body could reach a rank two slabs away
+    assert e.value.status == -1
+
+
 def test_slab_world_rejects_per_index_calls():
     from gears_b200.slabs import LocalSlabs
     from gears_b200.world import GpError
