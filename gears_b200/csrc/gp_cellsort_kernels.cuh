@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256)
                     const Bodies B0, const float4* __restrict__ A0, const Bodies B1, float4* __restrict__ A1,
                     float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ perm,
                     float* __restrict__ dmax, float* __restrict__ reach, uint32_t* __restrict__ moved_bits,
-                    uint32_t* __restrict__ esc_bits, const uint32_t* __restrict__ LB, Ctl* ctl,
+                    uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ xhead, const uint32_t* __restrict__ LB,
+                    Ctl* ctl,
                     float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncells = ctl->grid.ncells;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(256)
     chain_cnt[s] = 0;
     perm[s] = i;  // slot in the input set: k_restore re-integrates from there
     dmax[s] = 0.0f, reach[s] = 0.0f;
+    xhead[s] = NONE;  // no pair appended after K4 touches this body yet (k_tiny_link)
     if ((s & 31u) == 0u) moved_bits[s >> 5] = 0u, esc_bits[s >> 5] = 0u;  // every word of [0, n) has one such slot
 }
 

@@ -95,7 +95,10 @@ struct Ctl {
     uint32_t n_dirty, n_dpairs, dirty_bump, n_dheavy, dirty_all, n_hits_cleared;
     uint32_t dirty_level[3];     // bodies appended to the dirty list per BFS level (rotating)
     uint32_t n_resweep;          // stats: pairs re-swept by repair rounds this step
+    uint32_t tiny_fallback;      // k_repair_tiny met a component it does not handle: the general repair runs
     uint32_t n_escapees_total;   // stats: escapees of the first sweep
+    uint32_t dbg_tiny[6];        // since creation: rounds done by the tiny repair, rounds that fell back, components
+                                 // repaired, components too large, largest component seen (bodies, pairs)
     // uniform grid of the current step; re-derived by k_finish_step whenever the margin changes
     GridParams grid;
     float lo[3], hi[3];       // bounds of grid-class body centres (from upload / config)

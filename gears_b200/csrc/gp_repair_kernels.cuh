@@ -336,6 +336,317 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiny repair (the usual case).  Verification typically appends a few hundred pairs, each in a component of a handful
+// of bodies.  k_tiny_walk: one WARP per new pair walks its component (K5 adjacency + per-body lists of the pairs
+// appended since K4); the warp of the component's lowest new pair writes the component down.  k_tiny_exec: one warp
+// per component restores the bodies, sorts the component's pairs by (rank_a, rank_b) -- the reference's order itself
+// -- and one lane simply executes them in that order on a shared-memory copy of the bodies.  No chains, no rounds,
+// no grid barriers.  If any component does not fit (more than TINY_MAX_BODIES bodies / TINY_MAX_PAIRS pairs) the walk
+// raises tiny_fallback BEFORE anything was modified: k_tiny_exec does nothing and the general repair
+// (k_repair_local + k_sweep) runs as before.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t TINY_MAX_BODIES = 32, TINY_MAX_PAIRS = 96;
+constexpr uint32_t TINY_REC = 2 + TINY_MAX_BODIES + TINY_MAX_PAIRS + 30;  // u32 per component record (640 B)
+
+// per-body lists of the pairs appended since K4: xhead[body] -> entry (pid | side<<31), xnext[2*pid + side] -> next.
+// Also: every escapee commits the reach of the sweep that ran (its query was answered by k_requery).
+__global__ void __launch_bounds__(256)
+    k_tiny_link(const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ xhead,
+                uint32_t* __restrict__ xnext, const float* __restrict__ dmax, float* __restrict__ reach,
+                const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint32_t rec_cap, Ctl* ctl) {
+    if (ctl->repair_needed == 0) return;
+    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (gtid == 0 && np2 - np1 > rec_cap) ctl->tiny_fallback = 1u;
+    for (uint32_t j = np1 + gtid; j < np2; j += gsz) {
+        const uint4 r = pairs[2 * (size_t)j];
+        if (!(r.x & TOPBIT)) xnext[2 * (size_t)j] = atomicExch(&xhead[r.x], j);
+        if (!(r.y & TOPBIT)) xnext[2 * (size_t)j + 1] = atomicExch(&xhead[r.y], j | TOPBIT);
+    }
+    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+    for (uint32_t i = gtid; i < ne; i += gsz) {
+        const uint32_t x = escapees[i];
+        reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
+    }
+}
+
+struct TinyWalk {
+    uint32_t bodies[TINY_MAX_BODIES];
+    uint32_t pid[TINY_MAX_PAIRS];
+};
+
+__device__ __forceinline__ int tiny_find(const uint32_t* bodies, uint32_t nb, uint32_t x) {
+    for (uint32_t k = 0; k < nb; ++k)
+        if (bodies[k] == x) return (int)k;
+    return -1;
+}
+
+__global__ void __launch_bounds__(256)
+    k_tiny_walk(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
+                const unsigned long long* __restrict__ adj, const uint32_t* __restrict__ xhead,
+                const uint32_t* __restrict__ xnext, uint32_t* __restrict__ recs, uint32_t rec_cap, Ctl* ctl) {
+    __shared__ TinyWalk tw[8];
+    if (ctl->repair_needed == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    TinyWalk& t = tw[threadIdx.x >> 5];
+    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    if (np2 - np1 > rec_cap) return;  // (k_tiny_link raised tiny_fallback)
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t inew = np1 + warp0; inew < np2; inew += nwarps) {
+        __syncwarp();
+        uint32_t nb = 0, npp = 0, min_new = inew;
+        bool over = false;
+        {
+            const uint4 r = pairs[2 * (size_t)inew];
+            if (lane == 0) {
+                if (!(r.x & TOPBIT)) t.bodies[nb++] = r.x;
+                if (!(r.y & TOPBIT) && (nb == 0 || t.bodies[0] != r.y)) t.bodies[nb++] = r.y;
+            }
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+        }
+        __syncwarp();
+        for (uint32_t fi = 0; fi < nb && !over; ++fi) {
+            const uint32_t x = t.bodies[fi];
+            // two sources of pairs of x: the K5 adjacency (pairs K4 emitted), then the list of later pairs
+            const uint32_t e0 = offs[x], e1 = offs[x + 1];
+            uint32_t xl = xhead[x];  // (same value in all lanes)
+            for (uint32_t base = e0; !over; base += 32) {
+                uint32_t ent = NONE;
+                bool valid = false;
+                if (base < e1) {  // adjacency chunk: one entry per lane
+                    if (base + lane < e1) ent = (uint32_t)adj[base + lane], valid = true;
+                } else if (xl != NONE) {  // one list entry at a time (lane 0 holds it)
+                    if (lane == 0) ent = xl, valid = true;
+                    xl = xnext[2 * (size_t)(xl & ~TOPBIT) + (xl >> 31)];
+                } else {
+                    break;
+                }
+                const uint32_t pid = ent & ~TOPBIT;
+                uint4 r = make_uint4(0, 0, 0, 0);
+                if (valid) r = pairs[2 * (size_t)pid];
+                const bool x_is_b = (ent & TOPBIT) != 0;
+                const uint32_t partner = x_is_b ? r.x : r.y;
+                // a pair is collected from its first dynamic endpoint
+                const bool emit = valid && !(x_is_b && !(r.x & TOPBIT));
+                const uint32_t em = __ballot_sync(0xffffffffu, emit);
+                if (npp + __popc(em) > TINY_MAX_PAIRS) {
+                    over = true;
+                    break;
+                }
+                if (emit) t.pid[npp + __popc(em & ((1u << lane) - 1u))] = pid;
+                npp += __popc(em);
+                if (valid && pid >= np1 && pid < min_new) min_new = pid;
+                // new dynamic partners join the component (one at a time: the list stays duplicate-free)
+                uint32_t cm = __ballot_sync(0xffffffffu, valid && !(partner & TOPBIT));
+                while (cm) {
+                    const int L = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const uint32_t y = __shfl_sync(0xffffffffu, partner, L);
+                    if (tiny_find(t.bodies, nb, y) >= 0) continue;
+                    if (nb == TINY_MAX_BODIES) {
+                        over = true;
+                        break;
+                    }
+                    __syncwarp();
+                    if (lane == 0) t.bodies[nb] = y;
+                    ++nb;
+                    __syncwarp();
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) min_new = min(min_new, __shfl_xor_sync(0xffffffffu, min_new, o));
+        uint32_t* rec = recs + (size_t)(inew - np1) * TINY_REC;
+        if (lane == 0) atomicMax(&ctl->dbg_tiny[4], nb), atomicMax(&ctl->dbg_tiny[5], npp);
+        if (over) {
+            if (lane == 0) ctl->tiny_fallback = 1u, rec[0] = 0u, atomicAdd(&ctl->dbg_tiny[3], 1u);
+            continue;
+        }
+        __syncwarp();
+        if (min_new != inew) {  // the warp of the component's lowest new pair owns it
+            if (lane == 0) rec[0] = 0u;
+            continue;
+        }
+        if (lane == 0) rec[0] = nb, rec[1] = npp;
+        if (lane < nb) rec[2 + lane] = t.bodies[lane];
+        for (uint32_t k = lane; k < npp; k += 32) rec[2 + TINY_MAX_BODIES + k] = t.pid[k];
+    }
+}
+
+struct TinyExec {
+    uint32_t bodies[TINY_MAX_BODIES];
+    uint32_t pid[TINY_MAX_PAIRS], rx[TINY_MAX_PAIRS], ry[TINY_MAX_PAIRS], rw[TINY_MAX_PAIRS];
+    uint32_t order[TINY_MAX_PAIRS];
+    unsigned long long key[TINY_MAX_PAIRS];
+    uint8_t la[TINY_MAX_PAIRS], lb[TINY_MAX_PAIRS];  // local index of a / b among `bodies`, 255 = static
+    uint8_t hit[TINY_MAX_PAIRS];
+    float4 P[TINY_MAX_BODIES], V[TINY_MAX_BODIES], Lo[TINY_MAX_BODIES], Hi[TINY_MAX_BODIES], Snap[TINY_MAX_BODIES];
+    float dm[TINY_MAX_BODIES];       // displacement record of this re-execution (track_move, kept on chip)
+    uint8_t bflag[TINY_MAX_BODIES];  // 1: moved, 2: left its margin
+};
+constexpr int TINY_EXEC_WARPS = 4;
+
+// track_move on the shared-memory copy (same comparisons, same NaN behaviour); global effects are applied afterwards
+__device__ __forceinline__ void tiny_track(TinyExec& t, uint32_t l, const BodyRW& x, float mu_verify, float& maxrel,
+                                           float& maxabs) {
+    const float4 lo_snap = t.Snap[l];
+    const V3 lo_now = x.omin + x.pos;
+    const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
+    if (d == 0.0f) return;
+    const float e = fmaxf(x.omax.x - x.omin.x, fmaxf(x.omax.y - x.omin.y, x.omax.z - x.omin.z));
+    maxrel = fmaxf(maxrel, d / e);
+    if (!(d <= t.dm[l])) t.dm[l] = d;
+    uint8_t f = t.bflag[l] | 1;
+    if (!(d <= mu_verify * e)) {
+        f |= 2;
+        maxabs = fmaxf(maxabs, d);
+    }
+    t.bflag[l] = f;
+}
+
+__global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
+    k_tiny_exec(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ recs, uint32_t rec_cap,
+                const uint32_t* __restrict__ perm, const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
+                const float4* __restrict__ box, float* __restrict__ dmax, float* __restrict__ reach,
+                uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
+                uint32_t esc_cap, Ctl* ctl, float dt, float d16, float d18, float d35) {
+    __shared__ TinyExec tw[TINY_EXEC_WARPS];
+    if (ctl->repair_needed == 0 || ctl->tiny_fallback != 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    TinyExec& t = tw[threadIdx.x >> 5];
+    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float mverify = 0.98f * ctl->margin;
+    for (uint32_t inew = np1 + warp0; inew < np2; inew += nwarps) {
+        const uint32_t* rec = recs + (size_t)(inew - np1) * TINY_REC;
+        const uint32_t nb = rec[0];
+        if (nb == 0) continue;
+        const uint32_t npp = rec[1];
+        __syncwarp();
+        // ---- restore the bodies into shared memory, commit their reach, start a fresh displacement record ----
+        if (lane < nb) {
+            const uint32_t x = rec[2 + lane];
+            t.bodies[lane] = x;
+            const uint32_t s0 = perm[x];
+            float4 p = B0.P(s0), v = B0.V(s0);
+            const float4 a = A0[s0];
+            if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
+            t.P[lane] = p, t.V[lane] = v, t.Lo[lane] = ldcg4(&B1.Lo(x)), t.Hi[lane] = ldcg4(&B1.Hi(x));
+            t.Snap[lane] = box[2 * (size_t)x];
+            const float dm = dmax[x];
+            if (dm != 0.0f) reach[x] = fmaxf(reach[x], dm * REACH_SLACK);
+            t.dm[lane] = 0.0f, t.bflag[lane] = 0;
+        }
+        __syncwarp();
+        // ---- pairs: sort keys, local body indices, hit flags off ----
+        uint32_t cleared = 0;
+        for (uint32_t k = lane; k < npp; k += 32) {
+            const uint32_t pid = rec[2 + TINY_MAX_BODIES + k];
+            const uint4 r = pairs[2 * (size_t)pid];
+            t.pid[k] = pid, t.rx[k] = r.x, t.ry[k] = r.y, t.rw[k] = r.w, t.hit[k] = 0;
+            t.key[k] = ((unsigned long long)(r.z & ~TOPBIT) << 32) | (r.w & ~TOPBIT);
+            t.la[k] = (r.x & TOPBIT) ? (uint8_t)255 : (uint8_t)tiny_find(t.bodies, nb, r.x);
+            t.lb[k] = (r.y & TOPBIT) ? (uint8_t)255 : (uint8_t)tiny_find(t.bodies, nb, r.y);
+            cleared += (r.w & TOPBIT) ? 1u : 0u;
+        }
+        __syncwarp();
+        for (uint32_t k = lane; k < npp; k += 32) {  // rank of a key = its place in the reference's order
+            const unsigned long long kk = t.key[k];
+            uint32_t c = 0;
+            for (uint32_t q = 0; q < npp; ++q) c += t.key[q] < kk;
+            t.order[c] = k;
+        }
+        cleared = __reduce_add_sync(0xffffffffu, cleared);
+        __syncwarp();
+        // ---- one lane executes the component's pairs in the reference's order, entirely on chip (static partners
+        //      are read-only in global memory) ----
+        float maxd = 0.0f, maxabs = 0.0f;
+        if (lane == 0) {
+            uint32_t hits = 0;
+            for (uint32_t oi = 0; oi < npp; ++oi) {
+                const uint32_t k = t.order[oi];
+                const uint32_t ia = t.rx[k] & ~TOPBIT, ib = t.ry[k] & ~TOPBIT;
+                const uint32_t la = t.la[k], lb = t.lb[k];
+                BodyRW a, b;
+                a.is_static = la == 255, b.is_static = lb == 255;
+                const float4 pa = a.is_static ? ldcg4(&B1.P(ia)) : t.P[la], pb = b.is_static ? ldcg4(&B1.P(ib)) : t.P[lb];
+                const float4 loa = a.is_static ? ldcg4(&B1.Lo(ia)) : t.Lo[la];
+                const float4 hia = a.is_static ? ldcg4(&B1.Hi(ia)) : t.Hi[la];
+                const float4 lob = b.is_static ? ldcg4(&B1.Lo(ib)) : t.Lo[lb];
+                const float4 hib = b.is_static ? ldcg4(&B1.Hi(ib)) : t.Hi[lb];
+                a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
+                b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
+                const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
+                const V3 bmin = b.omin + b.pos, bmax = b.omax + b.pos;
+                const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y &&
+                                 amin.z < bmax.z && amax.z > bmin.z;
+                if (!hit) continue;
+                ++hits;
+                t.hit[k] = 1;
+                const float4 va = a.is_static ? ldcg4(&B1.V(ia)) : t.V[la], vb = b.is_static ? ldcg4(&B1.V(ib)) : t.V[lb];
+                a.vel = xyz(va), a.rest = va.w;
+                b.vel = xyz(vb), b.rest = vb.w;
+                const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
+                if (!a.is_static) {
+                    t.P[la] = make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass);
+                    t.V[la] = make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest);
+                    if (moved) tiny_track(t, la, a, mverify, maxd, maxabs);
+                }
+                if (!b.is_static) {
+                    t.P[lb] = make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass);
+                    t.V[lb] = make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest);
+                    if (moved) tiny_track(t, lb, b, mverify, maxd, maxabs);
+                }
+            }
+            atomicAdd(&ctl->n_contacts, hits - cleared);  // (unsigned wrap-around = signed difference)
+            atomicAdd(&ctl->n_resweep, npp);
+            if (maxd > 0.0f) atomicMax(&ctl->max_disp_bits, __float_as_uint(maxd));
+            if (maxabs > 0.0f) atomicMax(&ctl->max_abs_disp_bits, __float_as_uint(maxabs));
+            atomicAdd(&ctl->dbg_tiny[2], 1u);
+        }
+        __syncwarp();
+        // ---- results and their side effects go out in parallel ----
+        if (lane < nb) {
+            const uint32_t x = t.bodies[lane];
+            __stcg(&B1.P(x), t.P[lane]);
+            __stcg(&B1.V(x), t.V[lane]);
+            dmax[x] = t.dm[lane];
+            const uint32_t bit = 1u << (x & 31u);
+            const uint8_t f = t.bflag[lane];
+            if (f & 1) atomicOr(&moved_bits[x >> 5], bit);
+            if (f & 2) {
+                const uint32_t prev = atomicOr(&esc_bits[x >> 5], bit);
+                if (!(prev & bit)) {  // first escape of this body in this step
+                    const uint32_t s = atomicAdd(&ctl->n_escapees, 1u);
+                    if (s < esc_cap)
+                        escapees[s] = x;
+                    else
+                        atomicOr(&ctl->step_flags, SF_ESCAPEE_OVERFLOW);
+                }
+            }
+        }
+        for (uint32_t k = lane; k < npp; k += 32) {
+            const uint32_t w0 = t.rw[k], w1 = (w0 & ~TOPBIT) | (t.hit[k] ? TOPBIT : 0u);
+            if (w1 != w0) pairs[2 * (size_t)t.pid[k]].w = w1;
+        }
+    }
+}
+
+// all components fitted: the repair is done (the general repair kernels behind this one become no-ops)
+__global__ void k_tiny_done(Ctl* ctl, uint32_t pair_cap) {
+    if (ctl->repair_needed == 0) return;
+    if (ctl->tiny_fallback == 0) {
+        ctl->repair_needed = 0;
+        ctl->n_repairs += 1;
+        ctl->n_pairs_swept = min(ctl->n_pairs, pair_cap);
+        ctl->dbg_tiny[0] += 1;
+    } else {
+        ctl->dbg_tiny[1] += 1;
+    }
+    ctl->tiny_fallback = 0;
+}
+
 // after the repair sweep: the next k_requery decides again
 __global__ void k_repair_done(Ctl* ctl) { ctl->repair_needed = 0; }
 
@@ -419,7 +730,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.frontier_n[0] = 0, c.frontier_n[1] = 0, c.frontier_n[2] = 0, c.n_heavy = 0, c.step_flags = 0;
     c.n_escapees = 0, c.max_abs_disp_bits = 0, c.repair_needed = 0, c.n_repairs = 0, c.n_pairs_swept = 0;
     c.n_pairs_k4 = 0, c.n_dirty = 0, c.n_dpairs = 0, c.dirty_bump = 0, c.n_dheavy = 0, c.dirty_all = 0;
-    c.n_hits_cleared = 0, c.n_resweep = 0, c.dirty_level[0] = c.dirty_level[1] = c.dirty_level[2] = 0;
+    c.n_hits_cleared = 0, c.n_resweep = 0, c.tiny_fallback = 0, c.dirty_level[0] = c.dirty_level[1] = c.dirty_level[2] = 0;
     c.n_watch = 0, c.n_activated = 0, c.n_requeried = 0;
     c.n_recv = 0, c.n_sent[0] = 0, c.n_sent[1] = 0, c.n_migrated_out = 0, c.n_migrated_in = 0, c.n_unverified = 0;
     c.taint_flag[0] = 0, c.taint_flag[1] = 0, c.taint_flag[2] = 0;

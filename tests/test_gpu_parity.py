@@ -150,6 +150,31 @@ def test_mixed_sizes_and_statics(oracle):
     run_and_compare(oracle, s, 6, mode=1, check_every=3)
 
 
+@pytest.mark.parametrize("tiny", ["1", "0"])
+@pytest.mark.parametrize("scene", ["uniform", "dense", "mixed", "pile"])
+def test_both_repair_paths(oracle, monkeypatch, scene, tiny):
+    """GP_TINY_REPAIR=1 (the default): the warp-per-component repair runs in front of the cooperative one; piles exceed
+    its component limits and exercise the hand-over between the two.  =0: the cooperative path repairs everything."""
+    monkeypatch.setenv("GP_TINY_REPAIR", tiny)
+    s = {"uniform": lambda: scenes.uniform(20_000, L=60.0, seed=31, rank_seed=32),
+         "dense": lambda: scenes.uniform(20_000, L=40.0, seed=33, rank_seed=34),
+         "mixed": lambda: scenes.mixed(20_000, L=110.0),
+         "pile": lambda: scenes.pile(12, 12, 12)}[scene]()
+    retries = 0
+    with world() as w:
+        w.upload(s)
+        cur = dict(s)
+        for step in range(8):
+            retries += w.step(DT)["n_retries"]
+            r = oracle.step(cur, DT, 1, mode=1, want_snapshot=True)
+            pos, vel = w.download()
+            assert_same_bits(pos, r["pos"], f"pos after step {step + 1}")
+            assert_same_bits(vel, r["vel"], f"vel after step {step + 1}")
+            assert np.array_equal(w.pairs(1), r["sweep"]), f"S_sweep at step {step + 1}"
+            cur["pos"], cur["vel"] = r["pos"], r["vel"]
+    assert retries > 0  # verification appended pairs, so a repair ran
+
+
 def test_rotated_scaled_asymmetric_boxes(oracle):
     n = 4000
     s = scenes.uniform(n, L=30.0, seed=21, rank_seed=22)
