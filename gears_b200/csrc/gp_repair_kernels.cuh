@@ -474,18 +474,26 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+constexpr uint32_t TINY_STATICS = 8;
 struct TinyExec {
     uint32_t bodies[TINY_MAX_BODIES];
     uint32_t pid[TINY_MAX_PAIRS], rx[TINY_MAX_PAIRS], ry[TINY_MAX_PAIRS], rw[TINY_MAX_PAIRS];
     uint32_t order[TINY_MAX_PAIRS];
     unsigned long long key[TINY_MAX_PAIRS];
-    uint8_t la[TINY_MAX_PAIRS], lb[TINY_MAX_PAIRS];  // local index of a / b among `bodies`, 255 = static
+    // where a / b live: < 128 index among `bodies`; 128 + i: cached static partner i; 255: static, read from global
+    uint8_t la[TINY_MAX_PAIRS], lb[TINY_MAX_PAIRS];
     uint8_t hit[TINY_MAX_PAIRS];
+    uint32_t sid[TINY_STATICS];  // the component's static partners (usually just the floor), cached like the bodies
+    float4 SP[TINY_STATICS], SV[TINY_STATICS], SLo[TINY_STATICS], SHi[TINY_STATICS];
     float4 P[TINY_MAX_BODIES], V[TINY_MAX_BODIES], Lo[TINY_MAX_BODIES], Hi[TINY_MAX_BODIES], Snap[TINY_MAX_BODIES];
     float dm[TINY_MAX_BODIES];       // displacement record of this re-execution (track_move, kept on chip)
     uint8_t bflag[TINY_MAX_BODIES];  // 1: moved, 2: left its margin
 };
 constexpr int TINY_EXEC_WARPS = 4;
+
+__device__ __forceinline__ float4 tiny_fetch(const float4* dyn, const float4* stat, const float4* glob, uint32_t l) {
+    return l < 128u ? dyn[l] : l < 255u ? stat[l - 128u] : ldcg4(glob);
+}
 
 // track_move on the shared-memory copy (same comparisons, same NaN behaviour); global effects are applied afterwards
 __device__ __forceinline__ void tiny_track(TinyExec& t, uint32_t l, const BodyRW& x, float mu_verify, float& maxrel,
@@ -551,6 +559,38 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
             cleared += (r.w & TOPBIT) ? 1u : 0u;
         }
         __syncwarp();
+        {   // static partners: de-duplicate (serially, there are very few) and cache them
+            uint32_t ns = 0;
+            for (uint32_t k0 = 0; k0 < npp; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint32_t sx = NONE;  // (a pair has at most one static endpoint)
+                bool a_side = false;
+                if (k < npp) {
+                    if (t.rx[k] & TOPBIT) sx = t.rx[k] & ~TOPBIT, a_side = true;
+                    else if (t.ry[k] & TOPBIT) sx = t.ry[k] & ~TOPBIT;
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, sx != NONE);
+                while (m) {
+                    const uint32_t L = (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t y = __shfl_sync(0xffffffffu, sx, L);
+                    int f = tiny_find(t.sid, ns, y);
+                    __syncwarp();
+                    if (f < 0 && ns < TINY_STATICS) {
+                        if (lane == 0) t.sid[ns] = y;
+                        f = (int)ns++;
+                    }
+                    __syncwarp();
+                    if (lane == L) (a_side ? t.la[k] : t.lb[k]) = f < 0 ? (uint8_t)255 : (uint8_t)(128 + f);
+                }
+            }
+            if (lane < ns) {
+                const uint32_t y = t.sid[lane];
+                t.SP[lane] = ldcg4(&B1.P(y)), t.SV[lane] = ldcg4(&B1.V(y));
+                t.SLo[lane] = ldcg4(&B1.Lo(y)), t.SHi[lane] = ldcg4(&B1.Hi(y));
+            }
+        }
+        __syncwarp();
         for (uint32_t k = lane; k < npp; k += 32) {  // rank of a key = its place in the reference's order
             const unsigned long long kk = t.key[k];
             uint32_t c = 0;
@@ -569,12 +609,10 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
                 const uint32_t ia = t.rx[k] & ~TOPBIT, ib = t.ry[k] & ~TOPBIT;
                 const uint32_t la = t.la[k], lb = t.lb[k];
                 BodyRW a, b;
-                a.is_static = la == 255, b.is_static = lb == 255;
-                const float4 pa = a.is_static ? ldcg4(&B1.P(ia)) : t.P[la], pb = b.is_static ? ldcg4(&B1.P(ib)) : t.P[lb];
-                const float4 loa = a.is_static ? ldcg4(&B1.Lo(ia)) : t.Lo[la];
-                const float4 hia = a.is_static ? ldcg4(&B1.Hi(ia)) : t.Hi[la];
-                const float4 lob = b.is_static ? ldcg4(&B1.Lo(ib)) : t.Lo[lb];
-                const float4 hib = b.is_static ? ldcg4(&B1.Hi(ib)) : t.Hi[lb];
+                a.is_static = la >= 128u, b.is_static = lb >= 128u;
+                const float4 pa = tiny_fetch(t.P, t.SP, &B1.P(ia), la), pb = tiny_fetch(t.P, t.SP, &B1.P(ib), lb);
+                const float4 loa = tiny_fetch(t.Lo, t.SLo, &B1.Lo(ia), la), hia = tiny_fetch(t.Hi, t.SHi, &B1.Hi(ia), la);
+                const float4 lob = tiny_fetch(t.Lo, t.SLo, &B1.Lo(ib), lb), hib = tiny_fetch(t.Hi, t.SHi, &B1.Hi(ib), lb);
                 a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
                 b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
                 const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
@@ -584,7 +622,7 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
                 if (!hit) continue;
                 ++hits;
                 t.hit[k] = 1;
-                const float4 va = a.is_static ? ldcg4(&B1.V(ia)) : t.V[la], vb = b.is_static ? ldcg4(&B1.V(ib)) : t.V[lb];
+                const float4 va = tiny_fetch(t.V, t.SV, &B1.V(ia), la), vb = tiny_fetch(t.V, t.SV, &B1.V(ib), lb);
                 a.vel = xyz(va), a.rest = va.w;
                 b.vel = xyz(vb), b.rest = vb.w;
                 const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
