@@ -257,6 +257,11 @@ __global__ void __launch_bounds__(256)
         ctl->n = LB[ncells + 1u];
     }
     if (i >= ctl->n_in + ctl->n_recv) return;
+    // Per-slot state that starts every step at a constant: written by INDEX, not by destination slot -- the live
+    // slots [0, n) are a prefix of the indices handled here, and a coalesced store costs a fraction of a scattered
+    // 4-byte one (partial sectors).  xhead: no pair appended after K4 touches this body yet (k_tiny_link).
+    chain_cnt[i] = 0, dmax[i] = 0.0f, reach[i] = 0.0f, xhead[i] = NONE;
+    if ((i & 31u) == 0u) moved_bits[i >> 5] = 0u, esc_bits[i >> 5] = 0u;
     const uint32_t k = key[i];
     if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here
     const uint32_t s = LB[k] + lrank[i];
@@ -278,11 +283,7 @@ __global__ void __launch_bounds__(256)
     sbox[2 * (size_t)s] = make_float4(wlo.x, wlo.y, wlo.z,
                                       __uint_as_float((__float_as_uint(m) & ~TOPBIT) | ((flags & F_STATIC) ? TOPBIT : 0u)));
     sbox[2 * (size_t)s + 1] = whi;
-    chain_cnt[s] = 0;
-    perm[s] = i;  // slot in the input set: k_restore re-integrates from there
-    dmax[s] = 0.0f, reach[s] = 0.0f;
-    xhead[s] = NONE;  // no pair appended after K4 touches this body yet (k_tiny_link)
-    if ((s & 31u) == 0u) moved_bits[s >> 5] = 0u, esc_bits[s >> 5] = 0u;  // every word of [0, n) has one such slot
+    perm[s] = i;  // slot in the input set: the repair kernels re-integrate from there
 }
 
 
