@@ -31,7 +31,8 @@ from gears_b200 import scenes  # noqa: E402
 DT = np.float32(1.0) / np.float32(60.0)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's main kernel, from the ncu --set full capture
 # under profiles/ (uniform_16M, 1 GPU); None = not captured for that group
-NCU_TRAFFIC = {"find_pairs": 1.027e9, "scatter": 3.85e9, "keys": 1.88e9, "sweep": 1.73e9}
+# (scatter: no capture of the current kernel -- the last one, 4.7e9, predates the coalesced per-slot constants)
+NCU_TRAFFIC = {"find_pairs": 1.027e9, "scatter": None, "keys": 1.88e9, "sweep": 1.73e9}
 
 WORKLOADS = {
     # name: (generator kwargs, world kwargs)
@@ -121,7 +122,7 @@ def algorithmic_bytes(n: int, st: dict) -> dict:
     return {
         "keys": 96 * n + 4 * ncells,        # R 64 body + 16 acc|flags, W key 4 + arrival rank 4, histogram RMW 8; table memset
         "cell_scan": 8 * ncells,            # in-place exclusive scan of the cell histogram
-        "scatter": 220 * n,                 # R 8 + 80 + 4 (cell start), W 80 body + 32 AABB + 4 + 4 + 8 per-body scratch
+        "scatter": 224 * n,                 # R 8 + 80 + 4 (cell start), W 80 body + 32 AABB + 5 x 4 per-body scratch
         "find_pairs": 32 * n + 4 * ncells + 40 * npairs + 8 * nw,  # AABBs + cell table once; W 32 pair (+8 degree atomics), 8 watch
         "chains": 8 * n + 72 * npairs,      # degree scan; fill R 16 + W 16 + 8; sort+link R/W 16 + W 8 + 8
         "sweep": (1 + r) * (144 * npairs + 150 * c + 8 * nw) + r * (64 * npairs + 224 * c),  # sweeps, verification, restore

@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(256)
 // K2: exclusive scan of the cell histogram in place (scan.cuh) -> LB[c] = first slot of cell c, for
 // c in [0, ncells+2] (key ncells = big list, key ncells+1 = dead); LB[ncells+2] = bodies entering the step.
 // K3: scatter the bodies into cell order (slot = LB[key] + arrival rank within the cell), integrate, emit
-// world AABBs.  R 8 (key, rank) + R 80 (own record, coalesced) + W 80 (next set) + W 32 (AABB) + W 12.
+// world AABBs.  R 8 (key, rank) + R 80 (own record, coalesced) + R 4 (cell start) + W 80 (next set) + W 32 (AABB)
+// + W 4 (perm, scattered) + W 16 (per-slot constants, coalesced).
 // The order inside a cell is the arrival order of the atomics: results do not depend on it (the contact
 // sweep orders by the reference's iteration rank, never by slot).
 // ---------------------------------------------------------------------------------------------

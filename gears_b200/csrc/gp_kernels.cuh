@@ -11,8 +11,10 @@
 //   K5  k_fill_chains / k_sort_chains / k_sort_heavy   (new) per-body contact chains in the reference's pair order
 //   K6  k_sweep           check_and_resolve_collision             physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
 //                         in the order of update_systems.rs:408-487
-//       k_requery / k_verify_watch / k_repair_local               (new) verification + component-local repair of the
-//                                                                  speculative pair set
+//       k_requery / k_verify_watch                                (new) verification of the speculative pair set
+//       k_tiny_link / k_tiny_walk / k_tiny_exec                   (new) repair, small components: one warp re-executes a
+//                                                                  component's pairs in (rank_a, rank_b) order on chip
+//       k_repair_local + k_sweep (list mode)                      (new) repair, large components (cooperative)
 //       k_taint_closure   (new) multi-GPU: which owned bodies are provably independent of unseen bodies
 //
 // Ordering argument: the reference visits pairs (i,j), i<j in iteration order,

@@ -14,8 +14,10 @@ namespace gp {
 //  k_requery : for every escapee x, find the bodies y with swept(x) ^ swept(y) != {} that are NOT
 //              candidates yet, append those pairs, raise ctl->repair_needed.  One warp per escapee; the
 //              grid rows its query box covers are contiguous runs of the cell-sorted AABB array.
-//  k_repair_local : (gated) undo and re-chain only the connected components the new pairs touch (see below);
-//              the repair sweep then covers those pairs only.
+//  k_tiny_*  : (gated) the usual repair: one warp per small connected component the new pairs touch re-executes
+//              the component's pairs in the reference's order (see below).
+//  k_repair_local : (gated, when a component is too large for that) undo and re-chain only the connected
+//              components the new pairs touch; the repair sweep then covers those pairs only.
 // When k_requery appends nothing the last sweep saw every pair that could intersect at its turn: the
 // result equals the reference's full O(N^2) sweep.
 // ---------------------------------------------------------------------------------------------
