@@ -140,4 +140,22 @@ unsafe extern "C" {
     pub fn gp_download_owned(
         w: *mut gp_world, entity: *mut u32, pos3: *mut f32, vel3: *mut f32, unverified: *mut u8,
     ) -> gp_status;
+
+    // next rows: pass-3 instance rows, batched ray-vs-AABB, occupancy grid (see the header for the layouts)
+    pub fn gp_instances(w: *mut gp_world, rot4: *const f32, scale3: *const f32, out25: *mut f32) -> gp_status;
+    pub fn gp_raycast(
+        w: *mut gp_world, nrays: u32, origin3: *const f32, dir3: *const f32, ntargets: u32, targets: *const u32,
+        hits: *mut u8,
+    ) -> gp_status;
+    pub fn gp_obstacle_grid(
+        w: *mut gp_world, k: u32, idx: *const u32, cell_size: f32, origin: *const i32, dims: *const u32,
+        bitmap: *mut u32, bounds_out: *mut i32,
+    ) -> gp_status;
+
+    // test hooks (not part of the drop-in surface)
+    pub fn gp_test_radix_sort(device: i32, n: u32, key_bits: u32, keys_inout: *mut u32, vals_inout: *mut u32)
+        -> gp_status;
+    pub fn gp_test_radix_sort64(device: i32, n: u32, key_bits: u32, keys_inout: *mut u64, vals_inout: *mut u32)
+        -> gp_status;
+    pub fn gp_test_exclusive_scan(device: i32, n: u32, data_inout: *mut u32, total: *mut u32) -> gp_status;
 }
