@@ -175,6 +175,23 @@ def test_both_repair_paths(oracle, monkeypatch, scene, tiny):
     assert retries > 0  # verification appended pairs, so a repair ran
 
 
+@pytest.mark.skipif(not os.environ.get("GP_EXPERIMENTAL"),
+                    reason="kernels that have not run on hardware yet are tested only on request (GP_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("scene", ["uniform", "dense", "mixed", "pile", "one_cell"])
+def test_experimental_pair_find(oracle, monkeypatch, scene):
+    """GP_PAIRFIND=warp selects k_find_pairs_warp (gp_pairfind_warp.cuh) instead of k_find_pairs."""
+    monkeypatch.setenv("GP_PAIRFIND", "warp")
+    if scene == "one_cell":  # thousands of bodies in one grid cell: the body-at-a-time branch
+        s = scenes.uniform(5000, L=1.5, seed=41, rank_seed=42)  # (12.5 M pairs, every body a heavy chain)
+        run_and_compare(oracle, s, 1, mode=1, max_pairs=40_000_000)
+        return
+    s = {"uniform": lambda: scenes.uniform(100_000, L=126.0, seed=1001, rank_seed=2001),
+         "dense": lambda: scenes.uniform(20_000, L=40.0, seed=33, rank_seed=34),
+         "mixed": lambda: scenes.mixed(20_000, L=110.0),
+         "pile": lambda: scenes.pile(12, 12, 12)}[scene]()
+    run_and_compare(oracle, s, 4, mode=0 if scene == "uniform" else 1)
+
+
 def test_rotated_scaled_asymmetric_boxes(oracle):
     n = 4000
     s = scenes.uniform(n, L=30.0, seed=21, rank_seed=22)
