@@ -76,7 +76,7 @@ struct gp_world {
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
     int fp_grid_warp = 0;        // k_find_pairs_warp (experimental, GP_PAIRFIND=warp)
-    bool pairfind_warp = false;
+    int pairfind_warp = 0;       // 0: k_find_pairs, 1: k_find_pairs_warp<false>, 2: k_find_pairs_warp<true>
     // control
     Ctl *ctl = nullptr, *ctl_snap = nullptr;
     Ctl* h_ctl = nullptr;  // pinned
@@ -216,7 +216,7 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
             break;
         }
         w->fp_grid = occ * w->sm_count;  // persistent CTAs: every SM slot filled once
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs_warp, WP_THREADS, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs_warp<false>, WP_THREADS, 0) != cudaSuccess ||
             occ < 1) {
             rs = GP_ERR_NO_DEVICE;
             break;
@@ -224,7 +224,7 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
         w->fp_grid_warp = occ * w->sm_count;
         {
             const char* e = getenv("GP_PAIRFIND");
-            w->pairfind_warp = e && strcmp(e, "warp") == 0;
+            w->pairfind_warp = !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "warp256") == 0 ? 2 : 0;
         }
     } while (0);
     if (rs != GP_OK) {
@@ -834,8 +834,11 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
                                                        d[2]);
         w->launches += 1;
         prof_mark(w, 4);
-        if (w->pairfind_warp)
-            k_find_pairs_warp<<<std::min<uint32_t>(w->fp_grid_warp, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
+        if (w->pairfind_warp == 1)
+            k_find_pairs_warp<false><<<std::min<uint32_t>(w->fp_grid_warp, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
+                w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+        else if (w->pairfind_warp == 2)
+            k_find_pairs_warp<true><<<std::min<uint32_t>(w->fp_grid_warp, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
                 w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         else
             k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(

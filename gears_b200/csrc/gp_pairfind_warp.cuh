@@ -1,4 +1,6 @@
-// gp_pairfind_warp.cuh — EXPERIMENTAL variant of K4 (selected with GP_PAIRFIND=warp; the default is k_find_pairs).
+// gp_pairfind_warp.cuh — EXPERIMENTAL variant of K4 (selected with GP_PAIRFIND=warp or =warp256; the default is
+// k_find_pairs).  warp256 additionally fetches every 32 B AABB record with ONE 256-bit load (LDG.E.ENL2.256, new on
+// sm_100) instead of two 128-bit ones.
 // STATUS: compiles for sm_100a, has NOT run on hardware yet (written after the round's GPU budget was spent).
 // tests/test_gpu_parity.py::test_experimental_pair_find runs it against the oracle when GP_EXPERIMENTAL=1.
 //
@@ -37,6 +39,19 @@ struct WarpPairSmem {
     uint32_t stage_cnt, wstage_cnt, pad[2];
 };
 
+// one AABB record (lo, hi): 32 B, 32 B-aligned, read-only during K4
+template <bool WIDE>
+__device__ __forceinline__ void ld_box(const float4* __restrict__ sbox, uint32_t q, float4& lo, float4& hi) {
+    if constexpr (WIDE) {
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                     : "l"(sbox + 2 * (size_t)q));
+    } else {
+        lo = sbox[2 * (size_t)q], hi = sbox[2 * (size_t)q + 1];
+    }
+}
+
+template <bool WIDE>
 __global__ void __launch_bounds__(WP_THREADS)
     k_find_pairs_warp(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
                       uint2* __restrict__ watch, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(WP_THREADS)
 #pragma unroll
         for (int r = 0; r < FP_RANGES; ++r) q0[r] = 0, len[r] = 0;
         if (live) {
-            alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+            ld_box<WIDE>(sbox, p, alo, ahi);
             if (p < n_small) {
                 // same expression as body_key() in K1: bit-identical cell
                 const uint32_t k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
@@ -195,8 +210,9 @@ __global__ void __launch_bounds__(WP_THREADS)
                 // (entry 0 exists: nt > 0) all loads of the iteration first, then the tests
                 const uint32_t qa = sm.q[va ? ta : 0u], qb = sm.q[vb ? tb : 0u];
                 const uint32_t ja = sm.j[va ? ta : 0u], jb = sm.j[vb ? tb : 0u];
-                const float4 bla = sbox[2 * (size_t)qa], bha = sbox[2 * (size_t)qa + 1];
-                const float4 blb = sbox[2 * (size_t)qb], bhb = sbox[2 * (size_t)qb + 1];
+                float4 bla, bha, blb, bhb;
+                ld_box<WIDE>(sbox, qa, bla, bha);
+                ld_box<WIDE>(sbox, qb, blb, bhb);
                 if (va) test(sm.abox[2 * ja], sm.abox[2 * ja + 1], p0 + ja, bla, bha, qa);
                 if (vb) test(sm.abox[2 * jb], sm.abox[2 * jb + 1], p0 + jb, blb, bhb, qb);
                 flush_if_needed();
