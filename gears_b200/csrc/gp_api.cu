@@ -76,6 +76,7 @@ struct gp_world {
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
     int fp_grid_warp = 0;        // k_find_pairs_warp (experimental, GP_PAIRFIND=warp)
+    bool wide_scatter = false;   // k_scatter_cells<true> (experimental, GP_WIDE_SCATTER=1)
     int pairfind_warp = 0;       // 0: k_find_pairs, 1: k_find_pairs_warp<false>, 2: k_find_pairs_warp<true>
     // control
     Ctl *ctl = nullptr, *ctl_snap = nullptr;
@@ -224,6 +225,8 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
         w->fp_grid_warp = occ * w->sm_count;
         {
             const char* e = getenv("GP_PAIRFIND");
+            const char* e2 = getenv("GP_WIDE_SCATTER");
+            w->wide_scatter = e2 && atoi(e2) != 0;
             w->pairfind_warp = !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "warp256") == 0 ? 2 : 0;
         }
     } while (0);
@@ -828,10 +831,16 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
         const uint32_t ncnt = w->max_cells + 2;
         exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
         prof_mark(w, 3);
-        k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
-                                                       w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
-                                                       w->moved_bits, w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1],
-                                                       d[2]);
+        if (w->wide_scatter)
+            k_scatter_cells<true><<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
+                                                           w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
+                                                           w->moved_bits, w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1],
+                                                           d[2]);
+        else
+            k_scatter_cells<false><<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
+                                                           w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
+                                                           w->moved_bits, w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1],
+                                                           d[2]);
         w->launches += 1;
         prof_mark(w, 4);
         if (w->pairfind_warp == 1)

@@ -149,6 +149,20 @@ struct Bodies {
     __device__ __forceinline__ float4& Hi(uint32_t i) const { return b[4 * (size_t)i + 3]; }
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two adjacent float4, 32 B-aligned.  Used only by the opt-in
+// experimental variants (GP_PAIRFIND=warp256, GP_WIDE_SCATTER=1) until they have been timed on hardware.
+__device__ __forceinline__ void ld256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st256(float4* p, const float4 a, const float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
 struct V3 {
     float x, y, z;
 };

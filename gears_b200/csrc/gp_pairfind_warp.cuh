@@ -2,7 +2,7 @@
 // k_find_pairs).  warp256 additionally fetches every 32 B AABB record with ONE 256-bit load (LDG.E.ENL2.256, new on
 // sm_100) instead of two 128-bit ones.
 // STATUS: compiles for sm_100a, has NOT run on hardware yet (written after the round's GPU budget was spent).
-// tests/test_gpu_parity.py::test_experimental_pair_find runs it against the oracle when GP_EXPERIMENTAL=1.
+// tests/test_gpu_parity.py::test_experimental_kernel_variants runs it against the oracle when GP_EXPERIMENTAL=1.
 //
 // Why: k_find_pairs flattens the tests of a 256-body tile over the CTA.  That balances perfectly, but pays for it with
 // two block scans, a compaction of the non-empty ranges, one binary search per four tests and four CTA barriers per
