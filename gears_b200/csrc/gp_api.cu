@@ -76,6 +76,7 @@ struct gp_world {
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
     int fp_grid_warp = 0;        // k_find_pairs_warp (experimental, GP_PAIRFIND=warp)
+    bool sweep_skip = false;     // k_sweep skips provably missing pairs (experimental, GP_SWEEP_SKIP=1)
     bool wide_scatter = false;   // k_scatter_cells<true> (experimental, GP_WIDE_SCATTER=1)
     int pairfind_warp = 0;       // 0: k_find_pairs, 1: k_find_pairs_warp<false>, 2: k_find_pairs_warp<true>
     // control
@@ -227,6 +228,8 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
             const char* e = getenv("GP_PAIRFIND");
             const char* e2 = getenv("GP_WIDE_SCATTER");
             w->wide_scatter = e2 && atoi(e2) != 0;
+            const char* e3 = getenv("GP_SWEEP_SKIP");
+            w->sweep_skip = e3 && atoi(e3) != 0;
             w->pairfind_warp = !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "warp256") == 0 ? 2 : 0;
         }
     } while (0);
@@ -694,7 +697,8 @@ static gp_status enqueue_sweep(gp_world* w, const uint32_t* gate, bool local_lis
     uint32_t* esc = w->escapees;
     uint32_t esc_cap = w->cap;
     const uint32_t* list = local_list ? w->dpairs : nullptr;
-    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate, &list};
+    uint32_t skip = (w->sweep_skip && !local_list) ? 1u : 0u;
+    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate, &list, &skip};
     CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(COOP_THREADS), args, 0, st));
     w->launches++;
     return GP_OK;

@@ -177,13 +177,16 @@ def test_both_repair_paths(oracle, monkeypatch, scene, tiny):
 
 @pytest.mark.skipif(not os.environ.get("GP_EXPERIMENTAL"),
                     reason="kernels that have not run on hardware yet are tested only on request (GP_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("variant", ["warp", "warp256", "wide_scatter"])
+@pytest.mark.parametrize("variant", ["warp", "warp256", "wide_scatter", "sweep_skip"])
 @pytest.mark.parametrize("scene", ["uniform", "dense", "mixed", "pile", "one_cell"])
 def test_experimental_kernel_variants(oracle, monkeypatch, scene, variant):
     """GP_PAIRFIND=warp / warp256 selects k_find_pairs_warp (gp_pairfind_warp.cuh) instead of k_find_pairs;
-    GP_WIDE_SCATTER=1 selects k_scatter_cells<true> (256-bit loads / stores of the body and AABB records)."""
+    GP_WIDE_SCATTER=1 selects k_scatter_cells<true> (256-bit loads / stores of the body and AABB records);
+    GP_SWEEP_SKIP=1 lets the first sweep skip pairs that provably miss again without fetching their bodies."""
     if variant == "wide_scatter":
         monkeypatch.setenv("GP_WIDE_SCATTER", "1")
+    elif variant == "sweep_skip":
+        monkeypatch.setenv("GP_SWEEP_SKIP", "1")
     else:
         monkeypatch.setenv("GP_PAIRFIND", variant)
     if scene == "one_cell":  # thousands of bodies in one grid cell: the body-at-a-time branch
