@@ -218,19 +218,21 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
             break;
         }
         w->fp_grid = occ * w->sm_count;  // persistent CTAs: every SM slot filled once
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs_warp<false>, WP_THREADS, 0) != cudaSuccess ||
-            occ < 1) {
-            rs = GP_ERR_NO_DEVICE;
-            break;
-        }
-        w->fp_grid_warp = occ * w->sm_count;
-        {
+        {   // experimental variants: opt-in, and never a reason for gp_create to fail
+            int occ_w = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k_find_pairs_warp<false>, WP_THREADS, 0) !=
+                cudaSuccess) {
+                occ_w = 0;
+                cudaGetLastError();
+            }
+            w->fp_grid_warp = occ_w * w->sm_count;
             const char* e = getenv("GP_PAIRFIND");
             const char* e2 = getenv("GP_WIDE_SCATTER");
             w->wide_scatter = e2 && atoi(e2) != 0;
             const char* e3 = getenv("GP_SWEEP_SKIP");
             w->sweep_skip = e3 && atoi(e3) != 0;
             w->pairfind_warp = !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "warp256") == 0 ? 2 : 0;
+            if (w->fp_grid_warp < 1) w->pairfind_warp = 0;
         }
     } while (0);
     if (rs != GP_OK) {
