@@ -29,10 +29,20 @@ if ROOT not in sys.path:
 from gears_b200 import scenes  # noqa: E402
 
 DT = np.float32(1.0) / np.float32(60.0)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's main kernel, from the ncu --set full capture
-# under profiles/ (uniform_16M, 1 GPU); None = not captured for that group
-# (scatter: no capture of the current kernel -- the last one, 4.7e9, predates the coalesced per-slot constants)
-NCU_TRAFFIC = {"find_pairs": 1.027e9, "scatter": None, "keys": 1.88e9, "sweep": 1.73e9}
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant group's main kernel, read
+# from the committed ncu launch list of this very command (profiles/ncu_traffic.json, written by
+# `python tools/ncu_launches.py <csv> --json`); None when that workload / kernel has not been captured
+GROUP_MAIN_KERNEL = {"keys": "k_keys", "cell_scan": "sc_scan", "scatter": "k_scatter_cells", "find_pairs": "k_find_pairs",
+                     "chains": "k_sort_chains", "sweep": "k_contacts"}
+
+
+def ncu_traffic(workload: str, group: str):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        k = t["workloads"][workload]["kernels"][GROUP_MAIN_KERNEL[group]]
+        return float(k["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 WORKLOADS = {
     # name: (generator kwargs, world kwargs)
@@ -248,7 +258,9 @@ def run_ours(args) -> dict:
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": groups[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": round(groups[dom]["gbs"] / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                    "frac": round(groups[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(args.workload, dom),
+                    "traffic_source": "profiles/ncu_traffic.json (ncu launch list of this command, per launch of "
+                                      + GROUP_MAIN_KERNEL.get(dom, "?") + ")", "peak_source": peak_src,
                     "share_of_step": round(groups[dom]["ms"] / sum(x["ms"] for x in groups.values()), 3),
                     "per_kernel_frac": {g: round(x["gbs"] / peak, 3) for g, x in groups.items() if x["alg_bytes"]}}
 
@@ -301,6 +313,8 @@ def run_ours(args) -> dict:
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference algorithm on a bounded sample ----
     cpu = cpu_baseline(args, gen) if (rank == 0 and world_size == 1 and not args.no_cpu) else None
+    cpu_grid = cpu_baseline_grid(gen, scene) if (rank == 0 and world_size == 1 and not args.no_cpu and
+                                                   not args.no_cpu_grid) else None
 
     out = {
         "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world_size, "steps": args.steps,
@@ -310,7 +324,8 @@ def run_ours(args) -> dict:
                    "l2": "state arrays (80 B/body) exceed the 126 MB L2 by >10x; no flush needed"
                    if n_total * 80 > 4 * 126e6 * world_size else "working set fits L2: numbers are L2-resident",
                    "parallelism": f"x-slabs{world_size}" if world_size > 1 else "single"},
-        "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_grid": cpu_grid,
+        "clocks": clocks,
         "kernels": groups, "wall_ms_per_step": t_wall * 1e3 / args.steps,
         "step_stats": {k: st[k] for k in ("n_bodies", "n_candidates", "n_watch", "n_activated", "n_contacts", "n_rounds",
                                           "n_retries", "margin", "max_displacement", "cell_size", "grid_dim", "n_big",
@@ -329,7 +344,7 @@ def run_ours(args) -> dict:
 def cpu_sample_scene(gen: dict, n_s: int) -> dict:
     """A bounded sample of the workload at the SAME number density (so contacts per body match)."""
     g = dict(gen)
-    if g["kind"] == "uniform":
+    if g["kind"] in ("uniform", "mixed"):
         g["L"] = float(g["L"]) * (n_s / g["n"]) ** (1.0 / 3.0)
         g["n"] = n_s
     elif g["kind"] == "pile":
@@ -338,30 +353,92 @@ def cpu_sample_scene(gen: dict, n_s: int) -> dict:
     return make_scene(g)
 
 
-def time_reference(gen: dict, n_s: int, steps: int, warmup: int) -> dict:
+def workload_bodies(gen: dict) -> int:
+    return int(gen["n"]) if "n" in gen else int(gen["nx"] * gen["ny"] * gen["nz"])
+
+
+REF_SIZES = (1_000, 4_000, 16_000, 64_000, 100_000)   # the brute-force N-sweep
+
+
+def reference_sweep(gen: dict, steps: int, warmup: int, sizes=REF_SIZES, budget_s: float = 60.0) -> dict:
+    """The reference's algorithm (oracle mode 0: pass 1 on all host threads, pass 2 -- the O(N^2) sequential sweep of
+    update_systems.rs:408-487 -- on ONE thread, as in the reference) timed at each N of the sweep on samples of the
+    workload at the same number density, then a least-squares fit t(N) = a + b N + c N^2 extrapolated to the full N.
+    The full workload itself is out of reach of that algorithm (16.7 M bodies = 1.4e14 pair visits per step)."""
     from oracle import pyoracle
     pyoracle.build()
     threads = pyoracle.max_threads()
-    s = cpu_sample_scene(gen, n_s)
-    n = int(s["pos"].shape[0])
-    cur = dict(s)
-    if warmup:
-        r = pyoracle.step(cur, DT, warmup, mode=0, threads=threads, want_snapshot=False)
-        cur["pos"], cur["vel"] = r["pos"], r["vel"]
-    t0 = time.perf_counter()
-    pyoracle.step(cur, DT, steps, mode=0, threads=threads, want_snapshot=False)
-    dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": "body-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{n} bodies of the workload at the same number density, {steps} steps of the reference's "
-                      f"O(N^2) sequential sweep (pass 1 on {threads} OpenMP threads, pass 2 on 1 thread as "
-                      f"update_systems.rs:408); throughput falls ~1/N: at the full N it is ~{n / gen.get('n', n):.2e}x this",
-            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+    n_full = workload_bodies(gen)
+    pts = []
+    t_begin = time.perf_counter()
+    for n_s in sizes:
+        if n_s > n_full:
+            continue
+        sc = cpu_sample_scene(gen, n_s)
+        n = int(sc["pos"].shape[0])
+        cur = dict(sc)
+        w = min(warmup, 1 if n_s >= 16_000 else warmup)
+        if w:
+            r = pyoracle.step(cur, DT, w, mode=0, threads=threads, want_snapshot=False)
+            cur["pos"], cur["vel"] = r["pos"], r["vel"]
+        # steps at this size: all K for the small sizes, fewer for the large ones so the whole sweep stays bounded
+        est = 1.6e-10 * n * n + 2e-8 * n + 2e-5          # seconds per step (measured on this image's cores)
+        k = int(max(1, min(steps, (budget_s / len(sizes)) / est)))
+        t0 = time.perf_counter()
+        pyoracle.step(cur, DT, k, mode=0, threads=threads, want_snapshot=False)
+        dt = (time.perf_counter() - t0) / k
+        pts.append({"n": n, "steps": k, "ms_per_step": dt * 1e3, "body_steps_per_s": n / dt})
+        if time.perf_counter() - t_begin > 2.0 * budget_s:
+            break
+    # least squares on relative error (every point weighs the same): t/N^2 = a/N^2 + b/N + c
+    N = np.array([p["n"] for p in pts], np.float64)
+    T = np.array([p["ms_per_step"] for p in pts], np.float64) * 1e-3
+    A = np.stack([np.ones_like(N), N, N * N], axis=1) / T[:, None]
+    coef, *_ = np.linalg.lstsq(A, np.ones_like(T), rcond=None)
+    a, b, c = [float(x) for x in coef]
+    if c <= 0 or len(pts) < 3:      # degenerate fit: fall back to pure N^2 scaling from the largest point
+        a, b, c = 0.0, 0.0, float(T[-1] / (N[-1] * N[-1]))
+    t_full = a + b * n_full + c * float(n_full) * float(n_full)
+    return {"points": pts, "fit_seconds": {"a": a, "b_per_body": b, "c_per_body2": c},
+            "n_full": n_full, "seconds_per_step_at_full_n": t_full, "value_at_full_n": n_full / t_full,
+            "cores": threads, "seconds": time.perf_counter() - t_begin}
+
+
+def sweep_text(sw: dict) -> str:
+    pts = ", ".join(f"{p['n']}: {p['ms_per_step']:.3g} ms" for p in sw["points"])
+    return (f"EXTRAPOLATED to {sw['n_full']} bodies from the reference's O(N^2) sequential sweep measured at "
+            f"N = {{{pts}}} per step (samples of the workload at the same number density; pass 1 on {sw['cores']} "
+            f"OpenMP threads, pass 2 on 1 thread as update_systems.rs:408), fit t = a + bN + cN^2 with "
+            f"c = {sw['fit_seconds']['c_per_body2']:.3g} s/body^2: {sw['seconds_per_step_at_full_n']:.4g} s per step")
 
 
 def cpu_baseline(args, gen) -> dict:
     try:
-        return time_reference(gen, args.cpu_sample, steps=max(2, args.cpu_steps), warmup=1)
+        sw = reference_sweep(gen, steps=max(2, min(args.steps, 10)), warmup=1, budget_s=15.0)
+        return {"value": sw["value_at_full_n"], "unit": "body-steps/s", "cores": sw["cores"], "kind": "port",
+                "sample": sweep_text(sw), "extrapolated": True, "points": sw["points"], "seconds": sw["seconds"],
+                "largest_measured": sw["points"][-1]}
     except Exception as e:  # the baseline is a reported figure, never a reason to lose the GPU number
+        return {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+
+def cpu_baseline_grid(gen, scene=None, steps: int = 1) -> dict:
+    """The grid-accelerated oracle (mode 1: same results bit for bit, NOT the reference's algorithm) at the FULL N."""
+    try:
+        from oracle import pyoracle
+        pyoracle.build()
+        sc = scene if scene is not None else make_scene(gen)
+        n = int(sc["pos"].shape[0])
+        threads = pyoracle.max_threads()
+        t0 = time.perf_counter()
+        pyoracle.step(sc, DT, steps, mode=1, threads=threads, want_snapshot=False, pair_cap=1 << 16)
+        dt = time.perf_counter() - t0
+        return {"value": n * steps / dt, "unit": "body-steps/s", "cores": 1, "kind": "port",
+                "sample": f"{steps} step(s) of the FULL workload ({n} bodies) with the oracle's uniform-grid sweep: an "
+                          f"algorithmically improved CPU implementation with bit-identical results, not the "
+                          f"reference's O(N^2) algorithm (pass 1 on {threads} threads, the sweep on 1)",
+                "seconds": dt}
+    except Exception as e:
         return {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
 
@@ -370,17 +447,25 @@ def run_reference(args) -> dict | None:
     if rank != 0:
         return None
     gen, _ = WORKLOADS[args.workload]
-    r = time_reference(gen, args.cpu_sample, steps=args.steps, warmup=args.warmup)
+    sw = reference_sweep(gen, steps=args.steps, warmup=args.warmup, budget_s=90.0)
+    n_full = sw["n_full"]
     return {
-        "impl": "reference", "metric": "body-steps/sec", "value": r["value"], "unit": "body-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "impl": "reference", "metric": "body-steps/sec", "value": sw["value_at_full_n"], "unit": "body-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sw["seconds_per_step_at_full_n"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "bodies": gen.get("n"), "dt": float(DT), "box": gen.get("L"),
-                   "parallelism": "host CPU"},
-        "cpu_baseline": {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"]},
-        "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": args.workload, "bodies": n_full, "dt": float(DT), "box": gen.get("L"),
+                   "parallelism": "host CPU", "extrapolated": True,
+                   "measured_bodies": [p["n"] for p in sw["points"]],
+                   "note": "value and ms_per_step are the quadratic fit evaluated at the workload's full body count; "
+                           "what was timed is listed under reference_sweep (each K-step run is a bounded sample)"},
+        "cpu_baseline": {"value": sw["value_at_full_n"], "unit": "body-steps/s", "cores": sw["cores"], "kind": "port",
+                         "sample": sweep_text(sw)},
+        "reference_sweep": sw["points"], "fit_seconds": sw["fit_seconds"],
+        "largest_measured": sw["points"][-1],
+        "e2e": {"value": sw["value_at_full_n"], "unit": "body-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
 
@@ -393,8 +478,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uniform_16M", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-sample", type=int, default=32768, help="bodies in the CPU-baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-grid", action="store_true", help="skip the full-N grid-oracle CPU line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo", type=float, default=0.0,
                     help="slab coverage H beyond a face (multi-GPU); 0 = 4 x the largest grid-class extent")

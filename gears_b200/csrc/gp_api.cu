@@ -71,14 +71,9 @@ struct gp_world {
     unsigned long long* adj2 = nullptr;
     uint32_t* dheavy = nullptr;
     uint32_t *xhead = nullptr, *xnext = nullptr;  // per-body lists of the pairs appended after K4 (tiny repair)
-    int repair_grid = 0;
     bool tiny_repair = false;  // per-component warp repair in front of the cooperative one (set at upload)
     uint32_t* escapees = nullptr;  // bodies that left their margin
     int sweep_grid = 0, fp_grid = 0;
-    int fp_grid_warp = 0;        // k_find_pairs_warp (experimental, GP_PAIRFIND=warp)
-    bool sweep_skip = false;     // k_sweep skips provably missing pairs (experimental, GP_SWEEP_SKIP=1)
-    bool wide_scatter = false;   // k_scatter_cells<true> (experimental, GP_WIDE_SCATTER=1)
-    int pairfind_warp = 0;       // 0: k_find_pairs, 1: k_find_pairs_warp<false>, 2: k_find_pairs_warp<true>
     // control
     Ctl *ctl = nullptr, *ctl_snap = nullptr;
     Ctl* h_ctl = nullptr;  // pinned
@@ -95,6 +90,13 @@ struct gp_world {
     uint64_t prof_mark_launches = 0;
     int prof_group = -1;
 
+    // GP_PROF_FINE=1 (diagnostics): an event after every launch of a step; mean time per kernel printed at gp_destroy
+    bool fine = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> fine_ev;
+    size_t fine_used = 0;
+    std::vector<std::pair<std::string, std::pair<double, uint64_t>>> fine_acc;
+    uint64_t fine_steps = 0;
+
     gp_step_stats last{};
     uint64_t steps_total = 0;
     uint32_t last_np = 0;
@@ -102,6 +104,44 @@ struct gp_world {
     uint64_t launches = 0;
     gp_multi* multi = nullptr;
 };
+
+// ---- fine-grained timing (GP_PROF_FINE=1): everything enqueued since the previous mark is charged to `name` ----
+static void fine_mark(gp_world* w, const char* name) {
+    if (!w->fine || w->fine_used >= (1u << 18)) return;
+    if (w->fine_used == w->fine_ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        w->fine_ev.push_back({name, e});
+    }
+    w->fine_ev[w->fine_used].first = name;
+    cudaEventRecord(w->fine_ev[w->fine_used].second, w->st);
+    w->fine_used++;
+}
+static void fine_collect(gp_world* w) {  // the stream is idle
+    for (size_t i = 1; i < w->fine_used; ++i) {
+        const char* nm = w->fine_ev[i].first;
+        if (!strcmp(nm, "begin")) {
+            w->fine_steps++;
+            continue;
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, w->fine_ev[i - 1].second, w->fine_ev[i].second) != cudaSuccess) continue;
+        auto it = std::find_if(w->fine_acc.begin(), w->fine_acc.end(), [&](const auto& a) { return a.first == nm; });
+        if (it == w->fine_acc.end()) w->fine_acc.push_back({nm, {0.0, 0}}), it = w->fine_acc.end() - 1;
+        it->second.first += ms, it->second.second++;
+    }
+    if (w->fine_used && !strcmp(w->fine_ev[0].first, "begin")) w->fine_steps++;
+    w->fine_used = 0;
+}
+static void fine_print(gp_world* w) {
+    if (!w->fine || !w->fine_steps) return;
+    double tot = 0;
+    for (auto& a : w->fine_acc) tot += a.second.first;
+    fprintf(stderr, "[gp fine] %llu steps, %.1f us/step\n", (unsigned long long)w->fine_steps, 1e3 * tot / w->fine_steps);
+    for (auto& a : w->fine_acc)
+        fprintf(stderr, "[gp fine] %-22s %8.1f us/step  (%.2f launches/step)\n", a.first.c_str(),
+                1e3 * a.second.first / w->fine_steps, (double)a.second.second / w->fine_steps);
+}
 
 static gp_status fail(gp_world* w, gp_status s, const char* fmt, ...) {
     char buf[512];
@@ -198,41 +238,23 @@ extern "C" gp_status gp_create(const gp_config* cfg, gp_world** out) {
         if (cudaMallocHost((void**)&w->h_ctl, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         if (cudaMemset(w->ctl, 0, sizeof(Ctl)) != cudaSuccess) { rs = GP_ERR_CUDA; break; }
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, COOP_THREADS, 0) != cudaSuccess || occ < 1) {
+        if (cudaFuncSetAttribute(k_contacts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ContactSmem)) !=
+                cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_contacts, COOP_THREADS, sizeof(ContactSmem)) !=
+                cudaSuccess ||
+            occ < 1) {
             rs = GP_ERR_NO_DEVICE;  // no kernel image for this device
             break;
         }
-        w->sweep_grid = w->sm_count;
-        int occ_r = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_repair_local, COOP_THREADS, 0) != cudaSuccess || occ_r < 1) {
+        w->sweep_grid = w->sm_count;  // one CTA per SM: a grid barrier costs per CTA
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs, WP_THREADS, 0) != cudaSuccess || occ < 1) {
             rs = GP_ERR_NO_DEVICE;
             break;
         }
-        w->repair_grid = w->sm_count;
-        if (cudaFuncSetAttribute(k_find_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(FindPairsSmem)) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_pairs, FP_THREADS, sizeof(FindPairsSmem)) !=
-                cudaSuccess ||
-            occ < 1) {
-            rs = GP_ERR_NO_DEVICE;
-            break;
-        }
-        w->fp_grid = occ * w->sm_count;  // persistent CTAs: every SM slot filled once
-        {   // experimental variants: opt-in, and never a reason for gp_create to fail
-            int occ_w = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k_find_pairs_warp<false>, WP_THREADS, 0) !=
-                cudaSuccess) {
-                occ_w = 0;
-                cudaGetLastError();
-            }
-            w->fp_grid_warp = occ_w * w->sm_count;
-            const char* e = getenv("GP_PAIRFIND");
-            const char* e2 = getenv("GP_WIDE_SCATTER");
-            w->wide_scatter = e2 && atoi(e2) != 0;
-            const char* e3 = getenv("GP_SWEEP_SKIP");
-            w->sweep_skip = e3 && atoi(e3) != 0;
-            w->pairfind_warp = !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "warp256") == 0 ? 2 : 0;
-            if (w->fp_grid_warp < 1) w->pairfind_warp = 0;
+        w->fp_grid = occ * w->sm_count;  // persistent warps: every SM slot filled once
+        {
+            const char* e = getenv("GP_PROF_FINE");
+            w->fine = e && atoi(e) != 0;
         }
     } while (0);
     if (rs != GP_OK) {
@@ -249,6 +271,8 @@ extern "C" void gp_destroy(gp_world* w) {
     if (!w) return;
     cudaSetDevice(w->device);
     if (w->st) cudaStreamSynchronize(w->st);
+    if (w->fine) fine_collect(w), fine_print(w);
+    for (auto& e : w->fine_ev) cudaEventDestroy(e.second);
     if (w->multi) gp_multi_destroy(w->multi);
     free_all(w);
     for (auto& e : w->prof_ev) cudaEventDestroy(e);
@@ -684,98 +708,54 @@ extern "C" gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out) {
 // Upper bound of the live body count that sizes the grids (the exact count is device-resident: ctl->n).
 static inline uint32_t n_bound(const gp_world* w) { return w->multi ? w->cap : w->n; }
 
-// K6: the cooperative sweep.  local_list: repair sweep over the pairs k_repair_local collected (gated).
-static gp_status enqueue_sweep(gp_world* w, const uint32_t* gate, bool local_list) {
-    cudaStream_t st = w->st;
-    const int o = w->cur ^ 1;
-    Bodies Bn{w->B[o]};
-    const float4* box = w->sbox;
-    uint4* pairs = w->pairs;
-    uint32_t pair_cap = (uint32_t)w->pair_cap;
-    uint32_t *f0 = w->frontier[0], *f1 = w->frontier[1];
-    Ctl* ctl = w->ctl;
-    float* dmax = w->dmax;
-    uint32_t *mvb = w->moved_bits, *esb = w->esc_bits;
-    uint32_t* esc = w->escapees;
-    uint32_t esc_cap = w->cap;
-    const uint32_t* list = local_list ? w->dpairs : nullptr;
-    uint32_t skip = (w->sweep_skip && !local_list) ? 1u : 0u;
-    void* args[] = {&Bn, &box, &pairs, &pair_cap, &f0, &f1, &ctl, &dmax, &mvb, &esb, &esc, &esc_cap, &gate, &list, &skip};
-    CK(cudaLaunchCooperativeKernel((void*)k_sweep, dim3(w->sweep_grid), dim3(COOP_THREADS), args, 0, st));
+// Slab worlds: where the per-step exactness proof keeps its marks (gp_multi_impl.cuh)
+static uint32_t* gp_multi_taint_bits(gp_multi* m);
+
+// K6: the whole contact phase -- ordered sweep, verification of the speculative pair set, repair rounds while they
+// are needed, the slab exactness proof, end of step -- is ONE cooperative launch (gp_contact_kernel.cuh).
+// start_phase 1: the host continues the repair loop of a synchronous step (gp_step).
+static const uint32_t REPAIR_ROUNDS_IN_KERNEL = 6;
+static gp_status enqueue_contacts(gp_world* w, float dt, const float* d, uint32_t start_phase, int latch,
+                                  uint32_t max_rounds) {
+    const int c = w->cur, o = c ^ 1;
+    ContactArgs a{};
+    a.B1 = Bodies{w->B[o]}, a.B0 = Bodies{w->B[c]}, a.A0 = w->A[c], a.A1 = w->A[o];
+    a.sbox = w->sbox, a.LB = w->LB;
+    a.pairs = w->pairs, a.pair_cap = (uint32_t)w->pair_cap, a.watch = w->watch;
+    a.frontier0 = w->frontier[0], a.frontier1 = w->frontier[1];
+    a.ctl = w->ctl, a.ctl_snap = w->ctl_snap;
+    a.dmax = w->dmax, a.reach = w->reach;
+    a.moved_bits = w->moved_bits, a.esc_bits = w->esc_bits, a.escapees = w->escapees, a.esc_cap = w->cap;
+    a.offs = w->offs, a.adj = w->adj, a.chain_cnt = w->chain_cnt, a.perm = w->perm;
+    a.xhead = w->xhead, a.xnext = w->xnext;
+    a.ra = RepairArrays{w->dirty_bits, w->dlist, w->dpairs, w->offs2, w->deg2, w->adj2, w->dheavy, w->heavy_cap};
+    a.recs = (uint32_t*)w->adj2;  // scratch of the general repair, which runs (if at all) behind the per-component one
+    a.rec_cap = (uint32_t)std::min<size_t>(w->pair_cap * 4 / TINY_REC, 1u << 20);
+    a.taint_bits = w->multi ? gp_multi_taint_bits(w->multi) : nullptr;
+    a.dt = dt, a.d16 = d[0], a.d18 = d[1], a.d35 = d[2];
+    a.start_phase = start_phase, a.max_rounds = max_rounds, a.tiny = w->tiny_repair ? 1u : 0u, a.latch = latch;
+    void* args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void*)k_contacts, dim3(w->sweep_grid), dim3(COOP_THREADS), args, sizeof(ContactSmem),
+                                   w->st));
     w->launches++;
+    fine_mark(w, start_phase ? "k_contacts(repair)" : "k_contacts");
     return GP_OK;
 }
 
-// K5 + K6: chain offsets, fill, sort + link, first sweep.
-static gp_status enqueue_chains_and_sweep(gp_world* w) {
+// K5: chain offsets, fill, sort + link.
+static void enqueue_chains(gp_world* w) {
     const uint32_t nb = n_bound(w);
     cudaStream_t st = w->st;
     exclusive_scan_u32(w->chain_cnt, nb, w->offs, w->tile_sums, st, &w->launches, nullptr);
+    fine_mark(w, "chain scan");
     k_fill_chains<<<w->sm_count * 8, 256, 0, st>>>(w->pairs, (uint32_t)w->pair_cap, w->offs, w->chain_cnt, w->adj,
                                                    w->ctl, nullptr);
+    fine_mark(w, "k_fill_chains");
     k_sort_chains<<<cdiv(nb, 256), 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
+    fine_mark(w, "k_sort_chains");
     k_sort_heavy<<<w->sm_count * 8, 256, 0, st>>>(w->offs, w->adj, w->pairs, w->heavy, w->heavy_cap, w->ctl, nullptr);
+    fine_mark(w, "k_sort_heavy");
     w->launches += 3;
-    prof_mark(w, 6);
-    return enqueue_sweep(w, nullptr, false);
-}
-
-// After a sweep: did it stay inside what the candidate set assumed?  k_requery looks for pairs beyond the outer
-// margin that escapees reached, k_verify_watch for watch pairs whose swept boxes touch; both append to the sweep set
-// and raise ctl->repair_needed.
-static void enqueue_verify(gp_world* w) {
-    cudaStream_t st = w->st;
-    k_requery<<<w->sm_count * 4, 256, 0, st>>>(w->sbox, w->sbox, w->LB, w->dmax, w->reach, w->esc_bits, w->escapees,
-                                               w->cap, w->pairs, (uint32_t)w->pair_cap, w->ctl);
-    k_verify_watch<<<w->sm_count * 8, 256, 0, st>>>(w->watch, (uint32_t)w->pair_cap, w->sbox, w->dmax, w->reach,
-                                                    w->moved_bits, w->pairs, (uint32_t)w->pair_cap, w->ctl);
-    w->launches += 2;
-}
-
-// One repair round (4 launches, all gated on ctl->repair_needed): component-local undo + re-chain, repair sweep
-// over the collected pairs, fresh verification.
-static gp_status enqueue_repair_round(gp_world* w, float dt, const float* d) {
-    cudaStream_t st = w->st;
-    const int c = w->cur, o = c ^ 1;
-    uint4* pairs = w->pairs;
-    uint32_t pair_cap = (uint32_t)w->pair_cap;
-    const uint32_t* offs = w->offs;
-    const unsigned long long* adj = w->adj;
-    uint32_t* chain_cnt = w->chain_cnt;
-    const uint32_t* perm = w->perm;
-    Bodies B0{w->B[c]}, B1{w->B[o]};
-    const float4* A0 = w->A[c];
-    float *dmax = w->dmax, *reach = w->reach;
-    const uint32_t* esc = w->escapees;
-    uint32_t esc_cap = w->cap;
-    RepairArrays ra{w->dirty_bits, w->dlist, w->dpairs, w->offs2, w->deg2, w->adj2, w->dheavy, w->heavy_cap};
-    Ctl* ctl = w->ctl;
-    float dtv = dt, d0 = d[0], d1 = d[1], d2 = d[2];
-    void* args[] = {&pairs, &pair_cap, &offs, &adj, &chain_cnt, &perm, &B0, &A0, &B1, &dmax, &reach, &esc, &esc_cap,
-                    &ra, &ctl, &dtv, &d0, &d1, &d2};
-    if (w->tiny_repair) {
-        // the usual case first: small components are repaired by one warp each; if all fitted, the general path
-        // below finds repair_needed == 0 and does nothing
-        uint32_t* recs = (uint32_t*)w->adj2;  // scratch of the general path, which runs (if at all) behind these
-        const uint32_t rec_cap = (uint32_t)std::min<size_t>(w->pair_cap * 4 / TINY_REC, 1u << 20);
-        k_tiny_link<<<w->sm_count, 256, 0, st>>>(w->pairs, pair_cap, w->xhead, w->xnext, w->dmax, w->reach, w->escapees,
-                                                 w->cap, rec_cap, w->ctl);
-        k_tiny_walk<<<w->sm_count * 4, 256, 0, st>>>(w->pairs, pair_cap, w->offs, w->adj, w->xhead, w->xnext, recs,
-                                                     rec_cap, w->ctl);
-        k_tiny_exec<<<w->sm_count * 4, 32 * TINY_EXEC_WARPS, 0, st>>>(w->pairs, pair_cap, recs, rec_cap, w->perm, B0, A0, B1, w->sbox,
-                                                     w->dmax, w->reach, w->moved_bits, w->esc_bits, w->escapees, w->cap,
-                                                     w->ctl, dt, d[0], d[1], d[2]);
-        k_tiny_done<<<1, 1, 0, st>>>(w->ctl, pair_cap);
-        w->launches += 4;
-    }
-    CK(cudaLaunchCooperativeKernel((void*)k_repair_local, dim3(w->repair_grid), dim3(COOP_THREADS), args, 0, st));
-    w->launches++;
-    gp_status s = enqueue_sweep(w, &w->ctl->repair_needed, true);
-    if (s != GP_OK) return s;
-    k_repair_done<<<1, 1, 0, st>>>(w->ctl);
-    w->launches += 1;
-    enqueue_verify(w);
-    return GP_OK;
 }
 
 // One step = phase A (cell keys + histogram; on a slab also the packing of what the neighbours need), the slab
@@ -795,23 +775,28 @@ static gp_status enqueue_phase_a(gp_world* w, float dt, const float* damp3) {
     const int c = w->cur;
     const uint32_t nb = n_bound(w);  // grids are sized for this; kernels stop at the device-resident counts
     prof_begin_step(w);
+    fine_mark(w, "begin");
     w->slot_valid = false;
     if (nb) {
         prof_mark(w, 0);
         // K1 + K2: one-pass radix (bucket) sort by cell key: histogram with the keys, scan, scatter
         const uint32_t ncnt = w->max_cells + 2;  // counters: every cell of the finest grid + big list + dead
         CK(cudaMemsetAsync(w->LB, 0, sizeof(uint32_t) * ((size_t)ncnt + 1), st));
+        fine_mark(w, "memset LB");
         if (w->multi) {
             gp_multi_begin_step(w->multi);  // (peer-to-peer transport: wait for buffer credit)
             k_keys<true><<<cdiv(nb, 256 * K1_TILES), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
                                                         gp_multi_send(w->multi, 0), gp_multi_send(w->multi, 1), dt, d[0],
                                                         d[1], d[2]);
             w->launches += 1;
+            fine_mark(w, "k_keys<slab>");
             gp_multi_seal(w->multi);        // counts into the headers (+ ready flags on the peer-to-peer transport)
+            fine_mark(w, "seal");
         } else {
             k_keys<false><<<cdiv(nb, 256), 256, 0, st>>>(Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl,
                                                          nullptr, nullptr, dt, d[0], d[1], d[2]);
             w->launches++;
+            fine_mark(w, "k_keys");
         }
     }
     CK(cudaGetLastError());
@@ -828,47 +813,40 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
         if (w->multi) {
             prof_mark(w, 1);
             gp_multi_before_append(w->multi);  // (peer-to-peer transport: wait for the neighbours' ready flags)
+            fine_mark(w, "wait neighbours");
             k_append<<<w->sm_count * 2, 256, 0, st>>>(gp_multi_recv(w->multi, 0), gp_multi_recv(w->multi, 1),
                                                       Bodies{w->B[c]}, w->A[c], w->key, w->lrank, w->LB, w->ctl);
             w->launches++;
             gp_multi_after_append(w->multi);   // (peer-to-peer transport: hand the buffer credit back)
+            fine_mark(w, "k_append+credit");
         }
         prof_mark(w, 2);
         const uint32_t ncnt = w->max_cells + 2;
         exclusive_scan_u32(w->LB, ncnt, w->LB, w->lb_tiles, st, &w->launches);
+        fine_mark(w, "cell scan");
         prof_mark(w, 3);
-        if (w->wide_scatter)
-            k_scatter_cells<true><<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
-                                                           w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
-                                                           w->moved_bits, w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1],
-                                                           d[2]);
-        else
-            k_scatter_cells<false><<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]},
-                                                           w->A[o], w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach,
-                                                           w->moved_bits, w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1],
-                                                           d[2]);
+        k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]}, w->A[o],
+                                                       w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach, w->moved_bits,
+                                                       w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1], d[2]);
         w->launches += 1;
+        fine_mark(w, "k_scatter_cells");
         prof_mark(w, 4);
-        if (w->pairfind_warp == 1)
-            k_find_pairs_warp<false><<<std::min<uint32_t>(w->fp_grid_warp, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
-                w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
-        else if (w->pairfind_warp == 2)
-            k_find_pairs_warp<true><<<std::min<uint32_t>(w->fp_grid_warp, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
-                w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
-        else
-            k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, FP_THREADS)), FP_THREADS, sizeof(FindPairsSmem), st>>>(
-                w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
+        k_find_pairs<<<std::min<uint32_t>(w->fp_grid, cdiv(nb, WP_THREADS)), WP_THREADS, 0, st>>>(
+            w->sbox, w->LB, w->pairs, w->watch, w->chain_cnt, (uint32_t)w->pair_cap, w->ctl);
         w->launches += 1;
+        fine_mark(w, "k_find_pairs");
         prof_mark(w, 5);
-        enqueue_chains_and_sweep(w);
-        // speculative broad phase: look for pairs the candidate set missed, repair, look again
-        enqueue_verify(w);
-        for (int rr = 0; rr < repair_rounds; ++rr) enqueue_repair_round(w, dt, d);
-        if (w->multi) gp_multi_enqueue_verification(w->multi);
+        enqueue_chains(w);
+        prof_mark(w, 6);
+        // sweep + verification of the speculative broad phase + repair rounds + (slabs) exactness proof + end of step
+        gp_status s6 = enqueue_contacts(w, dt, d, 0, latch, (uint32_t)repair_rounds);
+        if (s6 != GP_OK) return s6;
+        prof_mark(w, 7);
+    } else {
+        prof_mark(w, 7);
+        k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
+        w->launches++;
     }
-    prof_mark(w, 7);
-    k_finish_step<<<1, 1, 0, st>>>(w->ctl, w->ctl_snap, latch);
-    w->launches++;
     prof_end_step(w);
     CK(cudaGetLastError());
     return GP_OK;
@@ -914,10 +892,11 @@ static void fill_stats(gp_world* w, const Ctl& c, uint32_t retries) {
 static gp_status read_ctl(gp_world* w) {
     CK(cudaMemcpyAsync(w->h_ctl, w->ctl_snap, sizeof(Ctl), cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
+    if (w->fine) fine_collect(w);
     return GP_OK;
 }
 
-static const int REPAIR_ROUNDS_ENQUEUED = 2;  // gated repair rounds pre-enqueued per step (no-ops when not needed)
+static const int REPAIR_ROUNDS_ENQUEUED = (int)REPAIR_ROUNDS_IN_KERNEL;  // repair rounds a step may take on the device
 
 extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_stats* stats) {
     if (!w) return GP_ERR_BAD_ARG;
@@ -945,12 +924,8 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
         // the candidate set was still growing: keep repairing until k_requery finds nothing (exact result)
         int extra = 0;
         while (w->h_ctl->step_flags == SF_MARGIN && !no_retry && extra < 64) {
-            for (int r = 0; r < 2; ++r) {
-                s = enqueue_repair_round(w, dt, d);
-                if (s != GP_OK) return s;
-            }
-            k_finish_step<<<1, 1, 0, w->st>>>(w->ctl, w->ctl_snap, 0);
-            w->launches += 1;
+            s = enqueue_contacts(w, dt, d, 1, 0, REPAIR_ROUNDS_IN_KERNEL);
+            if (s != GP_OK) return s;
             s = read_ctl(w);
             if (s != GP_OK) return s;
             ++extra;

@@ -95,7 +95,8 @@ struct Ctl {
     uint32_t n_dirty, n_dpairs, dirty_bump, n_dheavy, dirty_all, n_hits_cleared;
     uint32_t dirty_level[3];     // bodies appended to the dirty list per BFS level (rotating)
     uint32_t n_resweep;          // stats: pairs re-swept by repair rounds this step
-    uint32_t tiny_fallback;      // k_repair_tiny met a component it does not handle: the general repair runs
+    uint32_t tiny_fallback;      // the per-component repair met a component it does not handle: the general repair runs
+    uint32_t sweep_round;        // level the sweep continues with after CTA 0 ran the tail levels alone
     uint32_t n_escapees_total;   // stats: escapees of the first sweep
     uint32_t dbg_tiny[6];        // since creation: rounds done by the tiny repair, rounds that fell back, components
                                  // repaired, components too large, largest component seen (bodies, pairs)
@@ -149,8 +150,7 @@ struct Bodies {
     __device__ __forceinline__ float4& Hi(uint32_t i) const { return b[4 * (size_t)i + 3]; }
 };
 
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two adjacent float4, 32 B-aligned.  Used only by the opt-in
-// experimental variants (GP_PAIRFIND=warp256, GP_WIDE_SCATTER=1) until they have been timed on hardware.
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two adjacent float4, 32 B-aligned.
 __device__ __forceinline__ void ld256(const float4* p, float4& a, float4& b) {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
@@ -162,6 +162,50 @@ __device__ __forceinline__ void st256(float4* p, const float4 a, const float4 b)
                  "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                  : "memory");
 }
+
+// scratch of the component-local repair
+struct RepairArrays {
+    uint32_t* dirty_bits;        // per slot
+    uint32_t* dlist;             // dirty bodies
+    uint32_t* dpairs;            // pairs of the dirty components
+    uint32_t* offs2;             // per slot: start of the body's segment in adj2
+    uint32_t* deg2;              // per slot: its length
+    unsigned long long* adj2;    // chain entries of the dirty bodies
+    uint32_t* dheavy;            // dirty bodies whose chain needs the block-wide sorter
+    uint32_t dheavy_cap;
+};
+
+// everything the contact kernel (k_contacts) works on
+struct ContactArgs {
+    Bodies B1;                   // the step's output set, in cell order: swept in place
+    Bodies B0;                   // the untouched input set (a repair re-integrates from it) ...
+    const float4* A0;            // ... and its acc|flags
+    const float4* A1;            // acc|flags of the output set
+    const float4* sbox;          // AABB records of the step (written by K3, read-only here)
+    const uint32_t* LB;          // cell start table (read-only here)
+    uint4* pairs;
+    uint32_t pair_cap;
+    uint2* watch;
+    uint32_t *frontier0, *frontier1;
+    Ctl *ctl, *ctl_snap;
+    float *dmax, *reach;
+    uint32_t *moved_bits, *esc_bits, *escapees;
+    uint32_t esc_cap;
+    const uint32_t* offs;        // K5 adjacency (read-only here)
+    const unsigned long long* adj;
+    uint32_t* chain_cnt;
+    const uint32_t* perm;
+    uint32_t *xhead, *xnext;
+    RepairArrays ra;
+    uint32_t* recs;              // component records of the per-component repair (aliases ra.adj2)
+    uint32_t rec_cap;
+    uint32_t* taint_bits;        // slab worlds: per-step exactness proof (nullptr otherwise)
+    float dt, d16, d18, d35;
+    uint32_t start_phase;        // 0: sweep first; 1: continue the repair loop
+    uint32_t max_rounds;         // repair rounds before the step is declared still-growing (SF_MARGIN)
+    uint32_t tiny;               // per-component warp repair in front of the cooperative one
+    int latch;                   // finish_step mode
+};
 
 struct V3 {
     float x, y, z;

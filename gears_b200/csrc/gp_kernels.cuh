@@ -27,8 +27,7 @@
 // All arithmetic: IEEE binary32, compiled with --fmad=false (Rust never contracts), IEEE div/sqrt.
 //
 // Files: gp_common (constants, control block, helpers), gp_mirror_kernels (upload / refresh / download, update_pos),
-// gp_cellsort_kernels (K1, K3, slab exchange helpers), gp_pairfind_kernels (K4; gp_pairfind_warp: an experimental
-// warp-autonomous variant, off by default), gp_chain_kernels (K5),
+// gp_cellsort_kernels (K1, K3, slab exchange helpers), gp_pairfind_kernels (K4), gp_chain_kernels (K5),
 // gp_sweep_kernels (K6), gp_repair_kernels (verification, repair, end of step), gp_slab_kernels (multi-GPU proof),
 // gp_next_kernels (instances, ray cast, obstacle grid, pair export).
 #pragma once
@@ -36,9 +35,9 @@
 #include "gp_mirror_kernels.cuh"
 #include "gp_cellsort_kernels.cuh"
 #include "gp_pairfind_kernels.cuh"
-#include "gp_pairfind_warp.cuh"
 #include "gp_chain_kernels.cuh"
 #include "gp_sweep_kernels.cuh"
 #include "gp_repair_kernels.cuh"
 #include "gp_slab_kernels.cuh"
+#include "gp_contact_kernel.cuh"
 #include "gp_next_kernels.cuh"

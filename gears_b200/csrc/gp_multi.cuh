@@ -9,7 +9,6 @@ static void gp_multi_destroy(gp_multi* m);
 static float4* gp_multi_send(gp_multi* m, int side);  // side 0 = left neighbour, 1 = right; nullptr if none
 static float4* gp_multi_recv(gp_multi* m, int side);
 static gp_status gp_multi_enqueue_exchange(gp_multi* m);     // NCCL transport: send/recv on the step stream
-static void gp_multi_enqueue_verification(gp_multi* m);     // taint kernels (which owned bodies are provably exact)
 static bool gp_multi_is_local(gp_multi* m);
 static void gp_multi_begin_step(gp_multi* m);
 static void gp_multi_seal(gp_multi* m);

@@ -81,7 +81,6 @@ struct gp_multi {
     float4* recv[2] = {nullptr, nullptr};
     size_t buf_bytes[2] = {0, 0};  // per face: 16 B header + xcap[side] records (both sides of a face agree)
     uint32_t proposal = 0;         // records per face buffer this rank asks for
-    int taint_grid = 0;
     uint32_t* taint_bits = nullptr;
     uint32_t* scratch = nullptr;   // [0] taint gate, [1..3] prepare counts, [4] compact counter
     cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
@@ -173,22 +172,7 @@ static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
     return GP_OK;
 }
 
-static void gp_multi_enqueue_verification(gp_multi* m) {
-    gp_world* w = m->w;
-    if (!m->verify) return;
-    const float4* sbox = w->sbox;
-    const float *dmax = w->dmax, *reach = w->reach;
-    const uint32_t* mvb = w->moved_bits;
-    uint32_t* tb = m->taint_bits;
-    const uint4* pairs = w->pairs;
-    uint32_t pair_cap = (uint32_t)w->pair_cap;
-    const uint2* watch = w->watch;
-    const float4* A = w->A[w->cur ^ 1];
-    Ctl* ctl = w->ctl;
-    void* args[] = {&sbox, &dmax, &reach, &mvb, &tb, &pairs, &pair_cap, &watch, &A, &ctl};
-    cudaLaunchCooperativeKernel((void*)k_taint_closure, dim3(m->taint_grid), dim3(COOP_THREADS), args, 0, w->st);
-    w->launches += 1;
-}
+static uint32_t* gp_multi_taint_bits(gp_multi* m) { return m->verify ? m->taint_bits : nullptr; }
 
 // common part of gp_comm_init / gp_comm_init_local
 static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) {
@@ -245,12 +229,6 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
             break;
         }
         m->proposal = c.max_exchange ? c.max_exchange : 2u * std::max(counts[0], counts[1]) + 8192u;
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_taint_closure, COOP_THREADS, 0) != cudaSuccess || occ < 1) {
-            rs = fail(w, GP_ERR_CUDA, "slab setup: no occupancy for the verification kernel");
-            break;
-        }
-        m->taint_grid = w->sm_count;
         if (cudaStreamSynchronize(w->st) != cudaSuccess) rs = fail(w, GP_ERR_CUDA, "slab setup failed");
     } while (0);
     if (rs != GP_OK) {

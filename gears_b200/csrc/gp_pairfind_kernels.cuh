@@ -1,8 +1,7 @@
-// gp_pairfind_kernels.cuh — K4 pair find: TMA-staged tiles, flattened tests, per-warp staged bursts.
+// gp_pairfind_kernels.cuh — K4 pair find: warp-autonomous tiles, 256-bit AABB record loads, per-warp staged bursts.
 // Part of the physics step; see gp_kernels.cuh for the map of kernels to reference lines.
 #pragma once
 #include "gp_common.cuh"
-#include "scan.cuh"
 
 namespace gp {
 
@@ -34,90 +33,60 @@ __device__ __forceinline__ float max_separation(const float4 alo, const float4 a
                  fmaxf(alo.z - bhi.z, blo.z - ahi.z));
 }
 
-constexpr int FP_THREADS = 256;   // bodies per tile = threads per CTA
-constexpr int FP_RANGES = 5;      // candidate slot ranges per body in the flattened walk: 5 cell-row runs
-constexpr int FP_BATCH = 4;       // tests per thread per batch
-constexpr int FP_WARPS = FP_THREADS / 32;
-constexpr int FP_WSTAGE = 160;    // staged pair records per warp (flushed above 32: a batch adds <= 128)
-constexpr int FP_NR = FP_THREADS * FP_RANGES;
+// K4.  A WARP owns a tile of 32 consecutive slots (= bodies in cell order):
+//   1. each lane loads its AABB record with ONE 256-bit load (LDG.E.ENL2.256, new on sm_100; kept in registers and
+//      in the warp's shared-memory tile), its cell key and the 10 cell-table entries that bound its 5 candidate runs
+//      (the rest of its own cell + the 13 forward neighbour cells are 5 contiguous runs of slots): every unordered
+//      pair is found exactly once;
+//   2. one warp scan of the per-lane test counts gives every lane its offset in the tile's flattened test list;
+//      each lane writes its (candidate slot, tile-local body) entries there -- a loop of ~4 short iterations;
+//   3. the warp walks the list, two tests per lane per iteration, candidate records fetched back to back;
+//   4. hits are staged per warp in shared memory and leave in bursts with ONE global atomic per flush.
+// No CTA barrier, no binary search.  Lists longer than WP_LIST are processed in windows; a lane with thousands of
+// candidates (a degenerate cell) switches the tile to a body-at-a-time walk.
+// Measured on uniform_16M (profiles/r02): 0.69 ms against 1.07 ms for the round-1 kernel, which flattened the tests of
+// a 256-body tile over the CTA behind a TMA bulk copy (two block scans, a range compaction, a binary search per four
+// tests and four CTA barriers per tile); the 128-bit-load variant of this kernel took 0.73 ms.  Both were deleted.
+constexpr int WP_RANGES = 5;     // candidate slot ranges per body: 5 cell-row runs
+constexpr int WP_THREADS = 128;
+constexpr int WP_WARPS = WP_THREADS / 32;
+constexpr int WP_LIST = 384;    // flattened tests per window
+constexpr int WP_STAGE = 96;    // staged records per warp: flushed above 32, one iteration adds at most 64
+constexpr uint32_t WP_DENSE = 4096;  // a lane with more candidates than this: body-at-a-time walk
 
-// ---- TMA bulk copy (cp.async.bulk, 1-D) of a tile of AABBs into shared memory, completion on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// bounded wait: a kernel of this library never spins forever (returns false after ~2^26 polls)
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) return true;
-    }
-    return false;
-}
-
-struct FindPairsSmem {
-    float4 abox[2 * FP_THREADS];  // AABB records of the tile's bodies, staged by TMA
-    uint32_t rstart[FP_NR];       // NON-EMPTY candidate ranges of the tile, compacted: first candidate slot,
-    uint32_t roff[FP_NR + 1];     //   exclusive scan of their lengths (test t belongs to range id, roff[id] <= t),
-    uint8_t rbody[FP_NR];         //   and the tile-local body the range belongs to
-    uint4 stage[FP_WARPS][FP_WSTAGE];  // per-warp sweep-pair records waiting for the next flush
-    uint2 wstage[FP_WARPS][FP_WSTAGE]; // per-warp watch-list entries
-    uint32_t scan[33];
-    uint32_t stage_cnt[FP_WARPS], wstage_cnt[FP_WARPS];
-    uint64_t bar;
+struct WarpPairSmem {
+    float4 abox[64];            // the tile's 32 AABB records (lo, hi)
+    uint4 stage[WP_STAGE];      // sweep-pair records waiting for the next flush
+    uint2 wstage[WP_STAGE];     // watch-list entries
+    uint32_t q[WP_LIST];        // candidate slot of test t of the window
+    uint8_t j[WP_LIST];         // tile-local body of test t
+    uint32_t stage_cnt, wstage_cnt, pad[2];
 };
 
-// K4.  Persistent CTAs; a tile is 256 consecutive slots (= bodies in cell order).  Per tile:
-//  1. one thread issues a TMA bulk copy of the tile's 8 KB of AABB records into shared memory; meanwhile every
-//     thread fetches the 10 cell-table entries of its body (independent loads) and derives its 6 candidate ranges:
-//     the rest of its own cell + the 13 forward neighbour cells are 5 contiguous runs of slots, + the big list;
-//  2. two block scans compact the non-empty ranges and flatten the tile's tests into [0, T);
-//  3. the tests are dealt out evenly, FP_BATCH consecutive tests per thread per batch (one binary search per
-//     batch, then a walk): every lane is busy whatever the cell populations are; the candidates' records of a
-//     batch are fetched back to back before any is tested;
-//  4. hits are staged per warp in shared memory and leave in bursts with ONE global atomic per flush; the warps
-//     of a CTA do not synchronise while they test.
-// A candidate (separation < m_a + m_b) within the inner margin becomes a sweep pair
-//   (a | static<<31, b | static<<31, rank_a | snapshot<<31, rank_b), a = earlier in iteration order,
-// the others go to the watch list.  S_snapshot flag: the exact test physics.rs:159-164 on the snapshot.
-__global__ void __launch_bounds__(FP_THREADS)
+// one AABB record (lo, hi): 32 B, 32 B-aligned, read-only during K4
+__device__ __forceinline__ void ld_box(const float4* __restrict__ sbox, uint32_t q, float4& lo, float4& hi) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+             : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+             : "l"(sbox + 2 * (size_t)q));
+}
+
+__global__ void __launch_bounds__(WP_THREADS)
     k_find_pairs(const float4* __restrict__ sbox, const uint32_t* __restrict__ LB, uint4* __restrict__ pairs,
-                 uint2* __restrict__ watch, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
-    extern __shared__ __align__(128) unsigned char fp_smem_raw[];
-    FindPairsSmem& sm = *reinterpret_cast<FindPairsSmem*>(fp_smem_raw);
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n = ctl->n;
+                      uint2* __restrict__ watch, uint32_t* __restrict__ chain_cnt, uint32_t pair_cap, Ctl* ctl) {
+    __shared__ __align__(16) WarpPairSmem smem[WP_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpPairSmem& sm = smem[warp];
+    const uint32_t n = ctl->n, n_small = ctl->n_small;
     const GridParams g = ctl->grid;
     const float in_ratio = ctl->margin > 0.0f ? ctl->margin_in / ctl->margin : 1.0f;
-    const uint32_t n_small = ctl->n_small;
     const uint32_t row = (uint32_t)g.dx, slab = (uint32_t)g.dx * (uint32_t)g.dy;
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) mbar_init(&sm.bar, 1);
-    if (lane == 0) sm.stage_cnt[warp] = 0, sm.wstage_cnt[warp] = 0;
-    __syncthreads();
-    uint32_t parity = 0, nsnap = 0;
-    const uint32_t ntiles = (n + FP_THREADS - 1) / FP_THREADS;
-    uint4* const wstage = sm.stage[warp];
-    uint32_t* const wcnt = &sm.stage_cnt[warp];
-    uint2* const wwatch = sm.wstage[warp];
-    uint32_t* const wwcnt = &sm.wstage_cnt[warp];
+    if (lane == 0) sm.stage_cnt = 0, sm.wstage_cnt = 0;
+    __syncwarp();
+    uint32_t nsnap = 0;
 
     auto flush = [&]() {  // warp-synchronous
         __syncwarp();
-        const uint32_t c = *wcnt;
+        const uint32_t c = sm.stage_cnt;
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&ctl->n_pairs, c);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -125,7 +94,7 @@ __global__ void __launch_bounds__(FP_THREADS)
         for (uint32_t i = lane; i < c; i += 32) {
             const uint32_t slot = base + i;
             if (slot < pair_cap) {
-                const uint4 rec = wstage[i];
+                const uint4 rec = sm.stage[i];
                 pairs[2 * (size_t)slot] = rec;
                 pairs[2 * (size_t)slot + 1] = link_init();
                 if (!(rec.x & TOPBIT)) atomicAdd(&chain_cnt[rec.x], 1u);
@@ -134,23 +103,28 @@ __global__ void __launch_bounds__(FP_THREADS)
             }
         }
         __syncwarp();
-        if (lane == 0) *wcnt = 0;
+        if (lane == 0) sm.stage_cnt = 0;
         __syncwarp();
     };
     auto flush_watch = [&]() {  // warp-synchronous
         __syncwarp();
-        const uint32_t c = *wwcnt;
+        const uint32_t c = sm.wstage_cnt;
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&ctl->n_watch, c);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane == 0 && base + c > pair_cap) atomicOr(&ctl->step_flags, SF_PAIR_OVERFLOW);
         for (uint32_t i = lane; i < c; i += 32)
-            if (base + i < pair_cap) watch[base + i] = wwatch[i];
+            if (base + i < pair_cap) watch[base + i] = sm.wstage[i];
         __syncwarp();
-        if (lane == 0) *wwcnt = 0;
+        if (lane == 0) sm.wstage_cnt = 0;
         __syncwarp();
     };
-    // one candidate: a = tile body (record from shared memory, slot pa), b = slot q
+    auto flush_if_needed = [&]() {  // warp-synchronous, uniform
+        __syncwarp();
+        if (sm.stage_cnt > 32u) flush();
+        if (sm.wstage_cnt > 32u) flush_watch();
+    };
+    // one candidate: a = tile body (slot pa), b = slot q.  Same predicate and record as k_find_pairs.
     auto test = [&](const float4 alo, const float4 ahi, uint32_t pa, const float4 blo, const float4 bhi, uint32_t q) {
         const float sep = max_separation(alo, ahi, blo, bhi);
         const float m2 = box_margin(alo) + box_margin(blo);
@@ -161,30 +135,28 @@ __global__ void __launch_bounds__(FP_THREADS)
         const bool a_first = ra < rb;  // pair order = the reference's iteration order
         const uint32_t x = a_first ? (pa | sa) : (q | sb), y = a_first ? (q | sb) : (pa | sa);
         if (sep < m2 * in_ratio) {
-            // physics.rs:159-164 on the snapshot (strict): the S_snapshot flag
             const bool snap = alo.x < bhi.x && ahi.x > blo.x && alo.y < bhi.y && ahi.y > blo.y && alo.z < bhi.z &&
-                              ahi.z > blo.z;
-            wstage[atomicAdd(wcnt, 1u)] =
+                              ahi.z > blo.z;  // physics.rs:159-164 on the snapshot (strict): the S_snapshot flag
+            sm.stage[atomicAdd(&sm.stage_cnt, 1u)] =
                 make_uint4(x, y, (a_first ? ra : rb) | (snap ? TOPBIT : 0u), a_first ? rb : ra);
         } else {
-            wwatch[atomicAdd(wwcnt, 1u)] = make_uint2(x, y);
+            sm.wstage[atomicAdd(&sm.wstage_cnt, 1u)] = make_uint2(x, y);
         }
     };
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t p0 = tile * FP_THREADS;
-        const uint32_t valid = min((uint32_t)FP_THREADS, n - p0);
-        if (tid == 0) tma_load_1d(sm.abox, sbox + 2 * (size_t)p0, valid * 32u, &sm.bar);
-        const uint32_t p = p0 + tid;
-        const bool live = tid < valid;
-        uint32_t q0[FP_RANGES], len[FP_RANGES];
+    const uint32_t ntiles = (n + 31u) / 32u;
+    const uint32_t gw = blockIdx.x * WP_WARPS + warp, nw = gridDim.x * WP_WARPS;
+    for (uint32_t tile = gw; tile < ntiles; tile += nw) {
+        const uint32_t p0 = tile * 32u, p = p0 + lane;
+        const bool live = p < n;
+        float4 alo = make_float4(0.f, 0.f, 0.f, 0.f), ahi = alo;
+        uint32_t q0[WP_RANGES], len[WP_RANGES];
 #pragma unroll
-        for (int r = 0; r < FP_RANGES; ++r) q0[r] = 0, len[r] = 0;
+        for (int r = 0; r < WP_RANGES; ++r) q0[r] = 0, len[r] = 0;
         if (live) {
+            ld_box(sbox, p, alo, ahi);
             if (p < n_small) {
-                // the AABB is needed for the cell: read it straight from global (the TMA copy of the same lines is
-                // in flight; one L2 fill serves both).  Same expression as body_key() in K1: bit-identical cell.
-                const float4 alo = sbox[2 * (size_t)p], ahi = sbox[2 * (size_t)p + 1];
+                // same expression as body_key() in K1: bit-identical cell
                 const uint32_t k = cell_key(g, (alo.x + ahi.x) * 0.5f, (alo.y + ahi.y) * 0.5f, (alo.z + ahi.z) * 0.5f);
                 const uint32_t e0 = LB[k + 2];
                 const uint32_t b1 = LB[k + row - 1], e1 = LB[k + row + 2];
@@ -198,119 +170,80 @@ __global__ void __launch_bounds__(FP_THREADS)
                 q0[4] = b4, len[4] = e4 - b4;
             }
         }
-        // big list (a floor, walls: at most max_big bodies): every body tests the big bodies behind it, directly --
-        // one or two tests per body do not deserve the range bookkeeping below.  Warp-uniform loop.
-        {
-            float4 mlo = make_float4(0, 0, 0, 0), mhi = mlo;
-            if (live) mlo = sbox[2 * (size_t)p], mhi = sbox[2 * (size_t)p + 1];
-            for (uint32_t q = n_small; q < n; ++q) {
-                if (live && q > p) test(mlo, mhi, p, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
-                __syncwarp();
-                if (*wcnt > 32u) flush();
-                if (*wwcnt > 32u) flush_watch();
-            }
+        sm.abox[2 * lane] = alo, sm.abox[2 * lane + 1] = ahi;
+        // big list (a floor, walls): every body tests the big bodies behind it, directly.  Warp-uniform loop.
+        for (uint32_t q = n_small; q < n; ++q) {
+            if (live && q > p) test(alo, ahi, p, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
+            flush_if_needed();
         }
-        // compact the non-empty ranges (thread-major order) and scan their lengths
-        uint32_t nne = 0;
-        unsigned long long sum64 = 0;
+        uint32_t cnt = 0;
+        bool huge = false;
 #pragma unroll
-        for (int r = 0; r < FP_RANGES; ++r) nne += len[r] ? 1u : 0u, sum64 += len[r];
-        const bool dense = __syncthreads_or(sum64 > 0x400000ull);  // a degenerate tile (thousands of bodies per cell)
-        if (dense) {
-            // the flattened index would overflow: every thread walks its own ranges
-            const bool tma_ok = mbar_wait(&sm.bar, parity);
-            parity ^= 1u;
-            if (!tma_ok && tid == 0) atomicOr(&ctl->step_flags, SF_INTERNAL);
-            // warp-cooperative: the 32 lanes share the ranges of one body at a time
+        for (int r = 0; r < WP_RANGES; ++r) huge |= len[r] > WP_DENSE, cnt += len[r];
+        __syncwarp();  // abox is complete
+        if (__any_sync(0xffffffffu, huge)) {
+            // a degenerate cell (thousands of bodies): the 32 lanes share the ranges of one body at a time
 #pragma unroll
-            for (int r = 0; r < FP_RANGES; ++r)
+            for (int r = 0; r < WP_RANGES; ++r)
                 for (int L = 0; L < 32; ++L) {
                     const uint32_t bq0 = __shfl_sync(0xffffffffu, q0[r], L), bln = __shfl_sync(0xffffffffu, len[r], L);
                     if (bln == 0) continue;  // uniform across the warp
-                    const uint32_t j = warp * 32 + L;
-                    const float4 alo = sm.abox[2 * j], ahi = sm.abox[2 * j + 1];
+                    const float4 blo_a = sm.abox[2 * L], bhi_a = sm.abox[2 * L + 1];
                     for (uint32_t o = 0; o < bln; o += 32) {
                         const uint32_t q = bq0 + o + lane;
-                        if (o + lane < bln) test(alo, ahi, p0 + j, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
-                        __syncwarp();
-                        if (*wcnt > 32u) flush();
-                        if (*wwcnt > 32u) flush_watch();
+                        if (o + lane < bln) test(blo_a, bhi_a, p0 + L, sbox[2 * (size_t)q], sbox[2 * (size_t)q + 1], q);
+                        flush_if_needed();
                     }
                 }
-            __syncthreads();
+            __syncwarp();  // abox is rewritten by the next tile
             continue;
         }
-        uint32_t Rn, T;
-        const uint32_t rbase = block_exclusive_scan_256(nne, &Rn, sm.scan);
-        uint32_t run = block_exclusive_scan_256((uint32_t)sum64, &T, sm.scan);
-        {
-            uint32_t w = rbase;
+        // offsets of the lanes' tests in the tile's flattened list (cnt <= 5 * WP_DENSE per lane: no overflow)
+        uint32_t inc = cnt;
 #pragma unroll
-            for (int r = 0; r < FP_RANGES; ++r)
-                if (len[r]) {
-                    sm.rstart[w] = q0[r];
-                    sm.roff[w] = run;
-                    sm.rbody[w] = (uint8_t)tid;
-                    run += len[r];
-                    ++w;
-                }
-            if (tid == FP_THREADS - 1) sm.roff[Rn] = run;  // = T
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += t;
         }
-        const bool tma_ok = mbar_wait(&sm.bar, parity);
-        parity ^= 1u;
-        if (!tma_ok && tid == 0) atomicOr(&ctl->step_flags, SF_INTERNAL);
-        __syncthreads();
-
-        for (uint32_t tb = warp * 32 * FP_BATCH; tb < T; tb += FP_THREADS * FP_BATCH) {
-            const uint32_t t0 = tb + lane * FP_BATCH;
-            if (t0 < T) {
-                // range that holds test t0: largest id with roff[id] <= t0 (ranges are non-empty: roff is strictly
-                // increasing)
-                uint32_t lo_i = 0, hi_i = Rn;
-                while (hi_i - lo_i > 1) {
-                    const uint32_t mid = (lo_i + hi_i) >> 1;
-                    if (sm.roff[mid] <= t0) lo_i = mid; else hi_i = mid;
-                }
-                uint32_t id = lo_i;
-                uint32_t end_t = sm.roff[id + 1];
-                uint32_t q = sm.rstart[id] + (t0 - sm.roff[id]);
-                const uint32_t nt = min((uint32_t)FP_BATCH, T - t0);
-                // where the tests of this batch live, then all their loads, then the tests
-                uint32_t qs[FP_BATCH], js[FP_BATCH];
+        const uint32_t off = inc - cnt, Tw = __shfl_sync(0xffffffffu, inc, 31);
+        for (uint32_t base = 0; base < Tw; base += WP_LIST) {
+            const uint32_t wend = min(base + (uint32_t)WP_LIST, Tw);
+            {   // my entries that fall into the window [base, wend)
+                uint32_t pre = off;
 #pragma unroll
-                for (int u = 0; u < FP_BATCH; ++u) {
-                    if ((uint32_t)u < nt) {
-                        if (t0 + u >= end_t) {
-                            ++id;
-                            end_t = sm.roff[id + 1];
-                            q = sm.rstart[id];
-                        }
-                        qs[u] = q++;
-                        js[u] = sm.rbody[id];
-                    } else {
-                        qs[u] = qs[0], js[u] = js[0];
+                for (int r = 0; r < WP_RANGES; ++r) {
+                    const uint32_t lo = max(pre, base), hi = min(pre + len[r], wend);
+                    for (uint32_t t = lo; t < hi; ++t) {
+                        sm.q[t - base] = q0[r] + (t - pre);
+                        sm.j[t - base] = (uint8_t)lane;
                     }
+                    pre += len[r];
                 }
-                float4 bl[FP_BATCH], bh[FP_BATCH];
-#pragma unroll
-                for (int u = 0; u < FP_BATCH; ++u) bl[u] = sbox[2 * (size_t)qs[u]], bh[u] = sbox[2 * (size_t)qs[u] + 1];
-#pragma unroll
-                for (int u = 0; u < FP_BATCH; ++u)
-                    if ((uint32_t)u < nt)
-                        test(sm.abox[2 * js[u]], sm.abox[2 * js[u] + 1], p0 + js[u], bl[u], bh[u], qs[u]);
             }
             __syncwarp();
-            if (*wcnt > 32u) flush();  // the next batch adds at most 32 * FP_BATCH = 128 records
-            if (*wwcnt > 32u) flush_watch();
+            const uint32_t nt = wend - base;
+            for (uint32_t t0 = 0; t0 < nt; t0 += 64) {
+                const uint32_t ta = t0 + lane, tb = t0 + 32 + lane;
+                const bool va = ta < nt, vb = tb < nt;
+                // (entry 0 exists: nt > 0) all loads of the iteration first, then the tests
+                const uint32_t qa = sm.q[va ? ta : 0u], qb = sm.q[vb ? tb : 0u];
+                const uint32_t ja = sm.j[va ? ta : 0u], jb = sm.j[vb ? tb : 0u];
+                float4 bla, bha, blb, bhb;
+                ld_box(sbox, qa, bla, bha);
+                ld_box(sbox, qb, blb, bhb);
+                if (va) test(sm.abox[2 * ja], sm.abox[2 * ja + 1], p0 + ja, bla, bha, qa);
+                if (vb) test(sm.abox[2 * jb], sm.abox[2 * jb + 1], p0 + jb, blb, bhb, qb);
+                flush_if_needed();
+            }
+            __syncwarp();  // the list is rewritten by the next window
         }
-        __syncthreads();  // rstart/roff/abox are rewritten by the next tile
+        __syncwarp();  // abox is rewritten by the next tile
     }
-    if (*wcnt) flush();
-    if (*wwcnt) flush_watch();
+    if (sm.stage_cnt) flush();
+    if (sm.wstage_cnt) flush_watch();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsnap += __shfl_xor_sync(0xffffffffu, nsnap, o);
-    if ((tid & 31) == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
+    if (lane == 0 && nsnap) atomicAdd(&ctl->n_snapshot, nsnap);
 }
-
 
 }  // namespace gp

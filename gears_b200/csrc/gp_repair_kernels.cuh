@@ -8,10 +8,13 @@
 #include "gp_sweep_kernels.cuh"
 
 namespace gp {
+// Every function here is a PHASE of k_contacts (gp_contact_kernel.cuh): called by all threads of the cooperative grid,
+// separated from the next phase by a grid barrier.  Arrays that are written inside the kernel are read through plain
+// or .cg loads, never through the read-only path.
 
 // ---------------------------------------------------------------------------------------------
 // Repair loop of the speculative broad phase.
-//  k_requery : for every escapee x, find the bodies y with swept(x) ^ swept(y) != {} that are NOT
+//  requery   : for every escapee x, find the bodies y with swept(x) ^ swept(y) != {} that are NOT
 //              candidates yet, append those pairs, raise ctl->repair_needed.  One warp per escapee; the
 //              grid rows its query box covers are contiguous runs of the cell-sorted AABB array.
 //  k_tiny_*  : (gated) the usual repair: one warp per small connected component the new pairs touch re-executes
@@ -26,24 +29,28 @@ namespace gp {
 // pass with the grown reaches but not with the old ones are exactly the new ones (no duplicates).
 constexpr float REACH_SLACK = 1.0001f;  // covers the rounding of the measured displacement
 
-__global__ void __launch_bounds__(256)
-    k_requery(const float4* __restrict__ box, const float4* __restrict__ sbox,
-              const uint32_t* __restrict__ LB, const float* __restrict__ dmax, const float* __restrict__ reach,
-              const uint32_t* __restrict__ esc_bits, const uint32_t* __restrict__ escapees, uint32_t esc_cap,
-              uint4* __restrict__ pairs, uint32_t pair_cap, Ctl* ctl) {
-    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+__device__ void requery_phase(const ContactArgs& a) {
+    Ctl* ctl = a.ctl;
+    const float4* box = a.sbox;
+    const float4* sbox = a.sbox;
+    const uint32_t* LB = a.LB;
+    const float *dmax = a.dmax, *reach = a.reach;
+    const uint32_t *esc_bits = a.esc_bits, *escapees = a.escapees;
+    uint4* pairs = a.pairs;
+    const uint32_t esc_cap = a.esc_cap, pair_cap = a.pair_cap;
+    const uint32_t ne = min(__ldcg(&ctl->n_escapees), esc_cap);
     if (ne == 0) return;
     const GridParams g = ctl->grid;
     const float mu = ctl->margin;
     const float ext_max = ctl->ext_max;
-    const float partner_reach = fmaxf(mu * ext_max, __uint_as_float(ctl->max_abs_disp_bits) * REACH_SLACK);
+    const float partner_reach = fmaxf(mu * ext_max, __uint_as_float(__ldcg(&ctl->max_abs_disp_bits)) * REACH_SLACK);
     const uint32_t n_small = ctl->n_small, n = ctl->n;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t ei = warp; ei < ne; ei += nwarps) {
-        const uint32_t x = escapees[ei];
-        const float rx_prev = reach[x];
-        const float rx_now = dmax[x] * REACH_SLACK;
+        const uint32_t x = __ldcg(&escapees[ei]);
+        const float rx_prev = __ldcg(&reach[x]);
+        const float rx_now = __ldcg(&dmax[x]) * REACH_SLACK;
         if (!(rx_now > rx_prev)) continue;  // did not move further than in an earlier sweep
         const float4 alo = box[2 * (size_t)x], ahi = box[2 * (size_t)x + 1];
         const float ma = box_margin(alo);  // the very bits K4 used
@@ -70,12 +77,12 @@ __global__ void __launch_bounds__(256)
             if (y == x) return;
             if (ta & tb & TOPBIT) return;  // static-static (an escapee is dynamic; kept for symmetry)
             const float mb = box_margin(blo);
-            const float ry_prev = reach[y], ry_now = dmax[y] * REACH_SLACK;
+            const float ry_prev = __ldcg(&reach[y]), ry_now = __ldcg(&dmax[y]) * REACH_SLACK;
             const float rb_old = fmaxf(mb, ry_prev), rb_new = fmaxf(rb_old, ry_now);
             if (inflated_overlap(alo, ahi, blo, bhi, ra_old + rb_old)) return;   // found in an earlier round / by K4
             if (!inflated_overlap(alo, ahi, blo, bhi, ra_new + rb_new)) return;  // still out of reach
             // y is an escapee that grew too: its own query reports the pair (the lower slot wins)
-            if (y < x && ry_now > ry_prev && ((esc_bits[y >> 5] >> (y & 31u)) & 1u)) return;
+            if (y < x && ry_now > ry_prev && ((__ldcg(&esc_bits[y >> 5]) >> (y & 31u)) & 1u)) return;
             const uint32_t rb = __float_as_uint(bhi.w);
             uint4 rec = (ra < rb) ? make_uint4(ta, tb, ra, rb) : make_uint4(tb, ta, rb, ra);
             cg::coalesced_group cgp = cg::coalesced_threads();
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Component-local repair (ONE cooperative launch, gated on ctl->repair_needed).  The pairs that verification
+// Component-local repair (a phase of k_contacts with grid barriers of its own).  The pairs that verification
 // appended can only change the result of bodies in their connected components of the sweep-pair graph; every other
 // component keeps the result of the sweep that already ran.  Phases (a grid barrier between them):
 //   seed     dynamic endpoints of the new pairs are DIRTY
@@ -114,17 +121,6 @@ __global__ void __launch_bounds__(256)
 // The repair sweep then runs over the collected pairs only (k_sweep, list mode).  If more than a third of the live
 // bodies turn dirty (a pile: one giant component) everything is declared dirty and the same code re-does it all.
 // ---------------------------------------------------------------------------------------------
-struct RepairArrays {
-    uint32_t* dirty_bits;        // per slot
-    uint32_t* dlist;             // dirty bodies
-    uint32_t* dpairs;            // pairs of the dirty components
-    uint32_t* offs2;             // per slot: start of the body's segment in adj2
-    uint32_t* deg2;              // per slot: its length
-    unsigned long long* adj2;    // chain entries of the dirty bodies
-    uint32_t* dheavy;            // dirty bodies whose chain needs the block-wide sorter
-    uint32_t dheavy_cap;
-};
-
 __device__ __forceinline__ bool mark_dirty(uint32_t x, const RepairArrays& ra, Ctl* ctl, uint32_t* level_counter) {
     const uint32_t bit = 1u << (x & 31u);
     if (atomicOr(&ra.dirty_bits[x >> 5], bit) & bit) return false;
@@ -136,17 +132,24 @@ __device__ __forceinline__ bool is_dirty(uint32_t x, const RepairArrays& ra) {
     return (__ldcg(&ra.dirty_bits[x >> 5]) >> (x & 31u)) & 1u;
 }
 
-__global__ void __launch_bounds__(COOP_THREADS, 1)
-    k_repair_local(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
-                   const unsigned long long* __restrict__ adj, uint32_t* __restrict__ chain_cnt,
-                   const uint32_t* __restrict__ perm, const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
-                   float* __restrict__ dmax, float* __restrict__ reach, const uint32_t* __restrict__ escapees,
-                   uint32_t esc_cap, RepairArrays ra, Ctl* ctl, float dt, float d16, float d18, float d35) {
-    if (ctl->repair_needed == 0) return;  // uniform: nobody reaches a barrier
-    cg::grid_group grid = cg::this_grid();
+__device__ void repair_local_phase(const ContactArgs& a, unsigned long long (*wbuf)[WSORT_SMEM], cg::grid_group& grid) {
+    uint4* pairs = a.pairs;
+    const uint32_t pair_cap = a.pair_cap, esc_cap = a.esc_cap;
+    const uint32_t* offs = a.offs;
+    const unsigned long long* adj = a.adj;
+    uint32_t* chain_cnt = a.chain_cnt;
+    const uint32_t* perm = a.perm;
+    const Bodies B0 = a.B0, B1 = a.B1;
+    const float4* A0 = a.A0;
+    float *dmax = a.dmax, *reach = a.reach;
+    const uint32_t* escapees = a.escapees;
+    const RepairArrays ra = a.ra;
+    Ctl* ctl = a.ctl;
+    const float dt = a.dt, d16 = a.d16, d18 = a.d18, d35 = a.d35;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const uint32_t n = ctl->n;
-    const uint32_t np0 = ctl->n_pairs_k4, np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    const uint32_t np0 = __ldcg(&ctl->n_pairs_k4), np1 = __ldcg(&ctl->n_pairs_swept),
+                   np2 = min(__ldcg(&ctl->n_pairs), pair_cap);
     if (gtid == 0) {
         ctl->n_dirty = 0, ctl->n_dpairs = 0, ctl->dirty_bump = 0, ctl->n_dheavy = 0, ctl->dirty_all = 0;
         ctl->n_hits_cleared = 0;
@@ -245,9 +248,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
         pairs[2 * (size_t)i + 1] = link_init();
     }
     {  // every escapee commits the reach of the sweep that ran (clean ones keep their sweep record)
-        const uint32_t ne = min(ctl->n_escapees, esc_cap);
+        const uint32_t ne = min(__ldcg(&ctl->n_escapees), esc_cap);
         for (uint32_t i = gtid; i < ne; i += gsz) {
-            const uint32_t x = escapees[i];
+            const uint32_t x = __ldcg(&escapees[i]);
             if (!is_dirty(x, ra)) reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
         }
     }
@@ -317,7 +320,6 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
     }
     grid.sync();
     {  // heavy chains: one warp per body (same sorter as k_sort_heavy)
-        __shared__ unsigned long long wbuf[COOP_THREADS / 32][WSORT_SMEM];
         const uint32_t nh = min(__ldcg(&ctl->n_dheavy), ra.dheavy_cap);
         for (uint32_t hi = gtid >> 5; hi < nh; hi += gsz >> 5) {
             const uint32_t x = __ldcg(&ra.dheavy[hi]);
@@ -353,12 +355,15 @@ constexpr uint32_t TINY_REC = 2 + TINY_MAX_BODIES + TINY_MAX_PAIRS + 30;  // u32
 
 // per-body lists of the pairs appended since K4: xhead[body] -> entry (pid | side<<31), xnext[2*pid + side] -> next.
 // Also: every escapee commits the reach of the sweep that ran (its query was answered by k_requery).
-__global__ void __launch_bounds__(256)
-    k_tiny_link(const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ xhead,
-                uint32_t* __restrict__ xnext, const float* __restrict__ dmax, float* __restrict__ reach,
-                const uint32_t* __restrict__ escapees, uint32_t esc_cap, uint32_t rec_cap, Ctl* ctl) {
-    if (ctl->repair_needed == 0) return;
-    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+__device__ void tiny_link_phase(const ContactArgs& a) {
+    Ctl* ctl = a.ctl;
+    const uint4* pairs = a.pairs;
+    uint32_t *xhead = a.xhead, *xnext = a.xnext;
+    const float* dmax = a.dmax;
+    float* reach = a.reach;
+    const uint32_t* escapees = a.escapees;
+    const uint32_t pair_cap = a.pair_cap, esc_cap = a.esc_cap, rec_cap = a.rec_cap;
+    const uint32_t np1 = __ldcg(&ctl->n_pairs_swept), np2 = min(__ldcg(&ctl->n_pairs), pair_cap);
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     if (gtid == 0 && np2 - np1 > rec_cap) ctl->tiny_fallback = 1u;
     for (uint32_t j = np1 + gtid; j < np2; j += gsz) {
@@ -366,10 +371,10 @@ __global__ void __launch_bounds__(256)
         if (!(r.x & TOPBIT)) xnext[2 * (size_t)j] = atomicExch(&xhead[r.x], j);
         if (!(r.y & TOPBIT)) xnext[2 * (size_t)j + 1] = atomicExch(&xhead[r.y], j | TOPBIT);
     }
-    const uint32_t ne = min(ctl->n_escapees, esc_cap);
+    const uint32_t ne = min(__ldcg(&ctl->n_escapees), esc_cap);
     for (uint32_t i = gtid; i < ne; i += gsz) {
-        const uint32_t x = escapees[i];
-        reach[x] = fmaxf(reach[x], dmax[x] * REACH_SLACK);
+        const uint32_t x = __ldcg(&escapees[i]);
+        reach[x] = fmaxf(reach[x], __ldcg(&dmax[x]) * REACH_SLACK);
     }
 }
 
@@ -384,15 +389,16 @@ __device__ __forceinline__ int tiny_find(const uint32_t* bodies, uint32_t nb, ui
     return -1;
 }
 
-__global__ void __launch_bounds__(256)
-    k_tiny_walk(const uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ offs,
-                const unsigned long long* __restrict__ adj, const uint32_t* __restrict__ xhead,
-                const uint32_t* __restrict__ xnext, uint32_t* __restrict__ recs, uint32_t rec_cap, Ctl* ctl) {
-    __shared__ TinyWalk tw[8];
-    if (ctl->repair_needed == 0) return;
+__device__ void tiny_walk_phase(const ContactArgs& a, TinyWalk& t) {
+    Ctl* ctl = a.ctl;
+    const uint4* pairs = a.pairs;
+    const uint32_t* offs = a.offs;
+    const unsigned long long* adj = a.adj;
+    const uint32_t *xhead = a.xhead, *xnext = a.xnext;
+    uint32_t* recs = a.recs;
+    const uint32_t pair_cap = a.pair_cap, rec_cap = a.rec_cap;
     const uint32_t lane = threadIdx.x & 31;
-    TinyWalk& t = tw[threadIdx.x >> 5];
-    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
+    const uint32_t np1 = __ldcg(&ctl->n_pairs_swept), np2 = min(__ldcg(&ctl->n_pairs), pair_cap);
     if (np2 - np1 > rec_cap) return;  // (k_tiny_link raised tiny_fallback)
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t inew = np1 + warp0; inew < np2; inew += nwarps) {
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(256)
             const uint32_t x = t.bodies[fi];
             // two sources of pairs of x: the K5 adjacency (pairs K4 emitted), then the list of later pairs
             const uint32_t e0 = offs[x], e1 = offs[x + 1];
-            uint32_t xl = xhead[x];  // (same value in all lanes)
+            uint32_t xl = __ldcg(&xhead[x]);  // (same value in all lanes)
             for (uint32_t base = e0; !over; base += 32) {
                 uint32_t ent = NONE;
                 bool valid = false;
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(256)
                     if (base + lane < e1) ent = (uint32_t)adj[base + lane], valid = true;
                 } else if (xl != NONE) {  // one list entry at a time (lane 0 holds it)
                     if (lane == 0) ent = xl, valid = true;
-                    xl = xnext[2 * (size_t)(xl & ~TOPBIT) + (xl >> 31)];
+                    xl = __ldcg(&xnext[2 * (size_t)(xl & ~TOPBIT) + (xl >> 31)]);
                 } else {
                     break;
                 }
@@ -491,15 +497,14 @@ struct TinyExec {
     float dm[TINY_MAX_BODIES];       // displacement record of this re-execution (track_move, kept on chip)
     uint8_t bflag[TINY_MAX_BODIES];  // 1: moved, 2: left its margin
 };
-constexpr int TINY_EXEC_WARPS = 4;
+constexpr int TINY_EXEC_WARPS = 8;  // warps of each CTA that execute components (the shared-memory copy is 6 KB per warp)
 
 __device__ __forceinline__ float4 tiny_fetch(const float4* dyn, const float4* stat, const float4* glob, uint32_t l) {
     return l < 128u ? dyn[l] : l < 255u ? stat[l - 128u] : ldcg4(glob);
 }
 
 // track_move on the shared-memory copy (same comparisons, same NaN behaviour); global effects are applied afterwards
-__device__ __forceinline__ void tiny_track(TinyExec& t, uint32_t l, const BodyRW& x, float mu_verify, float& maxrel,
-                                           float& maxabs) {
+__device__ __forceinline__ void tiny_track(TinyExec& t, uint32_t l, const BodyRW& x, float& maxrel, float& maxabs) {
     const float4 lo_snap = t.Snap[l];
     const V3 lo_now = x.omin + x.pos;
     const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
@@ -508,35 +513,39 @@ __device__ __forceinline__ void tiny_track(TinyExec& t, uint32_t l, const BodyRW
     maxrel = fmaxf(maxrel, d / e);
     if (!(d <= t.dm[l])) t.dm[l] = d;
     uint8_t f = t.bflag[l] | 1;
-    if (!(d <= mu_verify * e)) {
+    if (!(d <= ESCAPE_FRAC * box_margin(lo_snap))) {
         f |= 2;
         maxabs = fmaxf(maxabs, d);
     }
     t.bflag[l] = f;
 }
 
-__global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
-    k_tiny_exec(uint4* __restrict__ pairs, uint32_t pair_cap, const uint32_t* __restrict__ recs, uint32_t rec_cap,
-                const uint32_t* __restrict__ perm, const Bodies B0, const float4* __restrict__ A0, const Bodies B1,
-                const float4* __restrict__ box, float* __restrict__ dmax, float* __restrict__ reach,
-                uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ escapees,
-                uint32_t esc_cap, Ctl* ctl, float dt, float d16, float d18, float d35) {
-    __shared__ TinyExec tw[TINY_EXEC_WARPS];
-    if (ctl->repair_needed == 0 || ctl->tiny_fallback != 0) return;
+__device__ void tiny_exec_phase(const ContactArgs& a, TinyExec* tw) {
+    if ((threadIdx.x >> 5) >= TINY_EXEC_WARPS) return;  // (no barrier inside this phase)
+    Ctl* ctl = a.ctl;
+    uint4* pairs = a.pairs;
+    const uint32_t* recs = a.recs;
+    const uint32_t* perm = a.perm;
+    const Bodies B0 = a.B0, B1 = a.B1;
+    const float4* A0 = a.A0;
+    const float4* box = a.sbox;
+    float *dmax = a.dmax, *reach = a.reach;
+    uint32_t *moved_bits = a.moved_bits, *esc_bits = a.esc_bits, *escapees = a.escapees;
+    const uint32_t pair_cap = a.pair_cap, esc_cap = a.esc_cap;
+    const float dt = a.dt, d16 = a.d16, d18 = a.d18, d35 = a.d35;
     const uint32_t lane = threadIdx.x & 31;
     TinyExec& t = tw[threadIdx.x >> 5];
-    const uint32_t np1 = ctl->n_pairs_swept, np2 = min(ctl->n_pairs, pair_cap);
-    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const float mverify = 0.98f * ctl->margin;
+    const uint32_t np1 = __ldcg(&ctl->n_pairs_swept), np2 = min(__ldcg(&ctl->n_pairs), pair_cap);
+    const uint32_t warp0 = blockIdx.x * TINY_EXEC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * TINY_EXEC_WARPS;
     for (uint32_t inew = np1 + warp0; inew < np2; inew += nwarps) {
         const uint32_t* rec = recs + (size_t)(inew - np1) * TINY_REC;
-        const uint32_t nb = rec[0];
+        const uint32_t nb = __ldcg(&rec[0]);
         if (nb == 0) continue;
-        const uint32_t npp = rec[1];
+        const uint32_t npp = __ldcg(&rec[1]);
         __syncwarp();
         // ---- restore the bodies into shared memory, commit their reach, start a fresh displacement record ----
         if (lane < nb) {
-            const uint32_t x = rec[2 + lane];
+            const uint32_t x = __ldcg(&rec[2 + lane]);
             t.bodies[lane] = x;
             const uint32_t s0 = perm[x];
             float4 p = B0.P(s0), v = B0.V(s0);
@@ -544,16 +553,16 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
             if (!(__float_as_uint(a.w) & F_INTEGRATED)) integrate_body(p, v, a, dt, d16, d18, d35);
             t.P[lane] = p, t.V[lane] = v, t.Lo[lane] = ldcg4(&B1.Lo(x)), t.Hi[lane] = ldcg4(&B1.Hi(x));
             t.Snap[lane] = box[2 * (size_t)x];
-            const float dm = dmax[x];
-            if (dm != 0.0f) reach[x] = fmaxf(reach[x], dm * REACH_SLACK);
+            const float dm = __ldcg(&dmax[x]);
+            if (dm != 0.0f) reach[x] = fmaxf(__ldcg(&reach[x]), dm * REACH_SLACK);
             t.dm[lane] = 0.0f, t.bflag[lane] = 0;
         }
         __syncwarp();
         // ---- pairs: sort keys, local body indices, hit flags off ----
         uint32_t cleared = 0;
         for (uint32_t k = lane; k < npp; k += 32) {
-            const uint32_t pid = rec[2 + TINY_MAX_BODIES + k];
-            const uint4 r = pairs[2 * (size_t)pid];
+            const uint32_t pid = __ldcg(&rec[2 + TINY_MAX_BODIES + k]);
+            const uint4 r = __ldcg(&pairs[2 * (size_t)pid]);
             t.pid[k] = pid, t.rx[k] = r.x, t.ry[k] = r.y, t.rw[k] = r.w, t.hit[k] = 0;
             t.key[k] = ((unsigned long long)(r.z & ~TOPBIT) << 32) | (r.w & ~TOPBIT);
             t.la[k] = (r.x & TOPBIT) ? (uint8_t)255 : (uint8_t)tiny_find(t.bodies, nb, r.x);
@@ -610,33 +619,33 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
                 const uint32_t k = t.order[oi];
                 const uint32_t ia = t.rx[k] & ~TOPBIT, ib = t.ry[k] & ~TOPBIT;
                 const uint32_t la = t.la[k], lb = t.lb[k];
-                BodyRW a, b;
-                a.is_static = la >= 128u, b.is_static = lb >= 128u;
+                BodyRW ba, bb;
+                ba.is_static = la >= 128u, bb.is_static = lb >= 128u;
                 const float4 pa = tiny_fetch(t.P, t.SP, &B1.P(ia), la), pb = tiny_fetch(t.P, t.SP, &B1.P(ib), lb);
                 const float4 loa = tiny_fetch(t.Lo, t.SLo, &B1.Lo(ia), la), hia = tiny_fetch(t.Hi, t.SHi, &B1.Hi(ia), la);
                 const float4 lob = tiny_fetch(t.Lo, t.SLo, &B1.Lo(ib), lb), hib = tiny_fetch(t.Hi, t.SHi, &B1.Hi(ib), lb);
-                a.pos = xyz(pa), a.mass = pa.w, a.omin = xyz(loa), a.omax = xyz(hia);
-                b.pos = xyz(pb), b.mass = pb.w, b.omin = xyz(lob), b.omax = xyz(hib);
-                const V3 amin = a.omin + a.pos, amax = a.omax + a.pos;
-                const V3 bmin = b.omin + b.pos, bmax = b.omax + b.pos;
+                ba.pos = xyz(pa), ba.mass = pa.w, ba.omin = xyz(loa), ba.omax = xyz(hia);
+                bb.pos = xyz(pb), bb.mass = pb.w, bb.omin = xyz(lob), bb.omax = xyz(hib);
+                const V3 amin = ba.omin + ba.pos, amax = ba.omax + ba.pos;
+                const V3 bmin = bb.omin + bb.pos, bmax = bb.omax + bb.pos;
                 const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y &&
                                  amin.z < bmax.z && amax.z > bmin.z;
                 if (!hit) continue;
                 ++hits;
                 t.hit[k] = 1;
                 const float4 va = tiny_fetch(t.V, t.SV, &B1.V(ia), la), vb = tiny_fetch(t.V, t.SV, &B1.V(ib), lb);
-                a.vel = xyz(va), a.rest = va.w;
-                b.vel = xyz(vb), b.rest = vb.w;
-                const bool moved = resolve_pair(a, b, amin, amax, bmin, bmax);
-                if (!a.is_static) {
-                    t.P[la] = make_float4(a.pos.x, a.pos.y, a.pos.z, a.mass);
-                    t.V[la] = make_float4(a.vel.x, a.vel.y, a.vel.z, a.rest);
-                    if (moved) tiny_track(t, la, a, mverify, maxd, maxabs);
+                ba.vel = xyz(va), ba.rest = va.w;
+                bb.vel = xyz(vb), bb.rest = vb.w;
+                const bool moved = resolve_pair(ba, bb, amin, amax, bmin, bmax);
+                if (!ba.is_static) {
+                    t.P[la] = make_float4(ba.pos.x, ba.pos.y, ba.pos.z, ba.mass);
+                    t.V[la] = make_float4(ba.vel.x, ba.vel.y, ba.vel.z, ba.rest);
+                    if (moved) tiny_track(t, la, ba, maxd, maxabs);
                 }
-                if (!b.is_static) {
-                    t.P[lb] = make_float4(b.pos.x, b.pos.y, b.pos.z, b.mass);
-                    t.V[lb] = make_float4(b.vel.x, b.vel.y, b.vel.z, b.rest);
-                    if (moved) tiny_track(t, lb, b, mverify, maxd, maxabs);
+                if (!bb.is_static) {
+                    t.P[lb] = make_float4(bb.pos.x, bb.pos.y, bb.pos.z, bb.mass);
+                    t.V[lb] = make_float4(bb.vel.x, bb.vel.y, bb.vel.z, bb.rest);
+                    if (moved) tiny_track(t, lb, bb, maxd, maxabs);
                 }
             }
             atomicAdd(&ctl->n_contacts, hits - cleared);  // (unsigned wrap-around = signed difference)
@@ -674,8 +683,7 @@ __global__ void __launch_bounds__(32 * TINY_EXEC_WARPS)
 }
 
 // all components fitted: the repair is done (the general repair kernels behind this one become no-ops)
-__global__ void k_tiny_done(Ctl* ctl, uint32_t pair_cap) {
-    if (ctl->repair_needed == 0) return;
+__device__ void tiny_done(Ctl* ctl, uint32_t pair_cap) {
     if (ctl->tiny_fallback == 0) {
         ctl->repair_needed = 0;
         ctl->n_repairs += 1;
@@ -687,27 +695,28 @@ __global__ void k_tiny_done(Ctl* ctl, uint32_t pair_cap) {
     ctl->tiny_fallback = 0;
 }
 
-// after the repair sweep: the next k_requery decides again
-__global__ void k_repair_done(Ctl* ctl) { ctl->repair_needed = 0; }
-
 // Lazy candidates: a watch pair (between the inner and the outer margin) can only intersect at its turn if one
 // of its bodies moved.  After a sweep, every watch pair whose SWEPT boxes (snapshot (+) reach) touch joins the sweep
 // set and a repair sweep runs; pairs that stay out provably never intersect (exactness argument).
-__global__ void __launch_bounds__(256)
-    k_verify_watch(uint2* __restrict__ watch, uint32_t watch_cap, const float4* __restrict__ sbox,
-                   const float* __restrict__ dmax, const float* __restrict__ reach,
-                   const uint32_t* __restrict__ moved_bits, uint4* __restrict__ pairs, uint32_t pair_cap, Ctl* ctl) {
+__device__ void verify_watch_phase(const ContactArgs& a) {
+    Ctl* ctl = a.ctl;
+    uint2* watch = a.watch;
+    const float4* sbox = a.sbox;
+    const float *dmax = a.dmax, *reach = a.reach;
+    const uint32_t* moved_bits = a.moved_bits;
+    uint4* pairs = a.pairs;
+    const uint32_t pair_cap = a.pair_cap, watch_cap = a.pair_cap;
     const uint32_t nw = min(ctl->n_watch, watch_cap);
     for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nw; wi += gridDim.x * blockDim.x) {
-        const uint2 wp = watch[wi];
+        const uint2 wp = __ldcg(&watch[wi]);
         if (wp.x == NONE) continue;  // joined the sweep in an earlier round
-        const uint32_t a = wp.x & ~TOPBIT, b = wp.y & ~TOPBIT;
-        const bool ma = (moved_bits[a >> 5] >> (a & 31u)) & 1u, mb = (moved_bits[b >> 5] >> (b & 31u)) & 1u;
+        const uint32_t xa = wp.x & ~TOPBIT, xb = wp.y & ~TOPBIT;
+        const bool ma = (__ldcg(&moved_bits[xa >> 5]) >> (xa & 31u)) & 1u, mb = (__ldcg(&moved_bits[xb >> 5]) >> (xb & 31u)) & 1u;
         if (!(ma || mb)) continue;
-        const float ra = ma ? fmaxf(reach[a], dmax[a] * REACH_SLACK) : 0.0f;
-        const float rb = mb ? fmaxf(reach[b], dmax[b] * REACH_SLACK) : 0.0f;
-        const float4 alo = sbox[2 * (size_t)a], ahi = sbox[2 * (size_t)a + 1];
-        const float4 blo = sbox[2 * (size_t)b], bhi = sbox[2 * (size_t)b + 1];
+        const float ra = ma ? fmaxf(__ldcg(&reach[xa]), __ldcg(&dmax[xa]) * REACH_SLACK) : 0.0f;
+        const float rb = mb ? fmaxf(__ldcg(&reach[xb]), __ldcg(&dmax[xb]) * REACH_SLACK) : 0.0f;
+        const float4 alo = sbox[2 * (size_t)xa], ahi = sbox[2 * (size_t)xa + 1];
+        const float4 blo = sbox[2 * (size_t)xb], bhi = sbox[2 * (size_t)xb + 1];
         if (!inflated_overlap(alo, ahi, blo, bhi, ra + rb)) continue;
         watch[wi].x = NONE;
         const uint4 rec = make_uint4(wp.x, wp.y, __float_as_uint(ahi.w), __float_as_uint(bhi.w));  // a = lower rank
@@ -729,7 +738,7 @@ __global__ void __launch_bounds__(256)
 
 // End of step: a last k_requery has run; if it still found pairs the step is inexact (async) or the host
 // runs more repair rounds (sync).  Adapt the margin, reset per-step counters, clear escapee marks.
-__global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
+__device__ void finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     Ctl c = *ctl;
     if (c.repair_needed) c.step_flags |= SF_MARGIN;
     if (latch == 1) {  // async stepping: failures are latched, the host looks later
@@ -776,6 +785,7 @@ __global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) {
     c.taint_flag[0] = 0, c.taint_flag[1] = 0, c.taint_flag[2] = 0;
     *ctl = c;
 }
-
+// stand-alone form: the host resets a step it gave up on (latch 2), or finishes a step without bodies
+__global__ void k_finish_step(Ctl* ctl, Ctl* snapshot_out, int latch) { finish_step(ctl, snapshot_out, latch); }
 
 }  // namespace gp

@@ -24,14 +24,18 @@ __device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __r
     *flag = 1u;
 }
 
-// ONE cooperative launch: clear, seed, propagate to the fixed point (a grid barrier per round), count.
+// A phase of k_contacts: clear, seed, propagate to the fixed point (a grid barrier per round), count.
 constexpr uint32_t TAINT_MAX_ROUNDS = 64;
-__global__ void __launch_bounds__(COOP_THREADS, 1)
-    k_taint_closure(const float4* __restrict__ sbox, const float* __restrict__ dmax, const float* __restrict__ reach,
-                    const uint32_t* __restrict__ moved_bits, uint32_t* __restrict__ taint_bits,
-                    const uint4* __restrict__ pairs, uint32_t pair_cap, const uint2* __restrict__ watch,
-                    const float4* __restrict__ A, Ctl* ctl) {
-    cg::grid_group grid = cg::this_grid();
+__device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
+    const float4* sbox = a.sbox;
+    const float *dmax = a.dmax, *reach = a.reach;
+    const uint32_t* moved_bits = a.moved_bits;
+    uint32_t* taint_bits = a.taint_bits;
+    const uint4* pairs = a.pairs;
+    const uint32_t pair_cap = a.pair_cap;
+    const uint2* watch = a.watch;
+    const float4* A = a.A1;
+    Ctl* ctl = a.ctl;
     const uint32_t n = ctl->n;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     for (uint32_t wd = gtid; wd < (n + 31u) / 32u; wd += gsz) taint_bits[wd] = 0u;
@@ -42,13 +46,13 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
         const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
         if (box_static(lo)) continue;  // static bodies never change: nothing to get wrong
         float r = box_margin(lo);
-        if ((moved_bits[i >> 5] >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(reach[i], dmax[i] * REACH_SLACK));
+        if ((__ldcg(&moved_bits[i >> 5]) >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(__ldcg(&reach[i]), __ldcg(&dmax[i]) * REACH_SLACK));
         const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
         const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
         if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
     }
     grid.sync();
-    const uint32_t np = min(ctl->n_pairs, pair_cap), nw = min(ctl->n_watch, pair_cap);
+    const uint32_t np = min(__ldcg(&ctl->n_pairs), pair_cap), nw = min(ctl->n_watch, pair_cap);
     uint32_t it = 0;
     bool open = true;
     while (open && it < TAINT_MAX_ROUNDS) {
@@ -58,11 +62,11 @@ __global__ void __launch_bounds__(COOP_THREADS, 1)
         uint32_t* flag = &ctl->taint_flag[it % 3u];
         if (gtid == 0) ctl->taint_flag[(it + 1u) % 3u] = 0u;
         for (uint32_t i = gtid; i < np; i += gsz) {
-            const uint4 r = pairs[2 * (size_t)i];
+            const uint4 r = __ldcg(&pairs[2 * (size_t)i]);
             taint_edge(r.x, r.y, taint_bits, flag);
         }
         for (uint32_t i = gtid; i < nw; i += gsz) {
-            const uint2 r = watch[i];
+            const uint2 r = __ldcg(&watch[i]);
             if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, flag);  // (activated entries are among the pairs)
         }
         grid.sync();

@@ -31,7 +31,6 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
-#include <unordered_map>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -386,24 +385,51 @@ static void pass2_brute(Scene& sc, AabbCache& c, PairSink& sweep) {
 // re-inserted when they drift more than `tol`; bodies larger than the cell go to a short
 // list that is always tested.
 // ---------------------------------------------------------------------------------------
-struct HashGrid {
+// Dense uniform grid with intrusive per-cell lists (head / next / prev): O(1) insert and remove, one array access
+// per cell lookup.  Cell indices are clamped to the grid, so a body that drifts outside the bounds seen at
+// construction lands in an edge cell and a query that pokes outside is clamped the same (monotone) way: the cells a
+// query visits always contain every body whose centre lies in the query box.
+struct DenseGrid {
     float cs = 1.0f, inv = 1.0f;
-    std::unordered_map<uint64_t, std::vector<uint32_t>> cells;
-    static uint64_t key(int64_t x, int64_t y, int64_t z) {
-        return (uint64_t)((x & 0x1FFFFF) | ((y & 0x1FFFFF) << 21) | ((z & 0x1FFFFF) << 42));
-    }
-    int64_t cell(float v) const { return (int64_t)floorf(v * inv); }
-    void insert(uint32_t k, V3 c) { cells[key(cell(c.x), cell(c.y), cell(c.z))].push_back(k); }
-    void remove(uint32_t k, V3 c) {
-        auto it = cells.find(key(cell(c.x), cell(c.y), cell(c.z)));
-        if (it == cells.end()) return;
-        auto& v = it->second;
-        for (size_t i = 0; i < v.size(); ++i)
-            if (v[i] == k) {
-                v[i] = v.back();
-                v.pop_back();
-                break;
+    float lo[3] = {0, 0, 0};
+    int64_t dim[3] = {1, 1, 1};
+    std::vector<int32_t> head, next, prev;
+    std::vector<uint32_t> cell_of;
+    void init(const float blo[3], const float bhi[3], float cell, size_t n) {
+        cs = cell;
+        for (;;) {
+            double cells = 1;
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = blo[k];
+                double d = std::floor(((double)bhi[k] - (double)blo[k]) / (double)cs) + 1.0;
+                if (!(d >= 1.0)) d = 1.0;
+                dim[k] = (int64_t)std::min(d, 1.0e6);
+                cells *= (double)dim[k];
             }
+            if (cells <= 2.0e8) break;
+            cs *= 1.26f;  // the table must fit: coarser cells only add candidates
+        }
+        inv = 1.0f / cs;
+        head.assign((size_t)(dim[0] * dim[1] * dim[2]), -1);
+        next.assign(n, -1), prev.assign(n, -1), cell_of.assign(n, 0);
+    }
+    int64_t cell(float v, int k) const {
+        const float f = floorf((v - lo[k]) * inv);
+        if (!(f > 0.0f)) return 0;  // (NaN lands in cell 0; a NaN box never intersects anything)
+        return std::min<int64_t>((int64_t)std::min(f, 2.0e6f), dim[k] - 1);
+    }
+    size_t index(int64_t x, int64_t y, int64_t z) const { return (size_t)(x + dim[0] * (y + dim[1] * z)); }
+    void insert(uint32_t k, V3 c) {
+        const size_t ci = index(cell(c.x, 0), cell(c.y, 1), cell(c.z, 2));
+        cell_of[k] = (uint32_t)ci;
+        prev[k] = -1, next[k] = head[ci];
+        if (head[ci] >= 0) prev[head[ci]] = (int32_t)k;
+        head[ci] = (int32_t)k;
+    }
+    void remove(uint32_t k) {
+        const size_t ci = cell_of[k];
+        if (prev[k] >= 0) next[prev[k]] = next[k]; else head[ci] = next[k];
+        if (next[k] >= 0) prev[next[k]] = prev[k];
     }
 };
 
@@ -415,7 +441,8 @@ static inline float max_extent(const Aabb& a) {
 struct SweepGrid {
     Scene& sc;
     AabbCache& c;
-    HashGrid g;
+    DenseGrid g;
+    uint32_t n_in_grid = 0;
     float med = 1.0f, thr = 1.0f, tol = 0.0f;
     std::vector<uint32_t> big;
     std::vector<V3> ins_c;      // centre at insertion
@@ -429,26 +456,34 @@ struct SweepGrid {
         std::vector<float> tmp(ext);
         std::sort(tmp.begin(), tmp.end());
         med = std::max(tmp[n / 2], 1e-6f);
-        // bodies above ~4x the median extent go to the big list; keep that list short (<= 64)
-        thr = 4.0f * med;
-        if (n > 64) thr = std::max(thr, tmp[n - 65]);
-        tol = 0.25f * med;
-        g.cs = thr + 2.0f * tol;
-        g.inv = 1.0f / g.cs;
+        // cell size = the largest extent that leaves at most 64 bodies above it (they go to the big list, which is
+        // always tested), but never below the median extent: the tightest grid that still hosts all but 64 bodies
+        // (a pile of unit boxes gets unit cells instead of 4x cells holding ~80 bodies each)
+        thr = n > 64 ? std::max(med, tmp[n - 65]) : 4.0f * med;
+        tol = 0.125f * med;
         ins_c.resize(n);
         ins_box.resize(n);
         in_grid.assign(n, 0);
+        float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (uint32_t k = 0; k < n; ++k) {
-            Aabb a = c.get(k);
-            if (!(ext[k] <= thr) || !std::isfinite(ext[k])) {
+            const Aabb a = c.get(k);
+            const V3 ce = center_of(a);
+            if (!(ext[k] <= thr) || !std::isfinite(ext[k]) || !std::isfinite(ce.x) || !std::isfinite(ce.y) ||
+                !std::isfinite(ce.z)) {
                 big.push_back(k);
             } else {
                 in_grid[k] = 1;
-                ins_c[k] = center_of(a);
+                ++n_in_grid;
+                ins_c[k] = ce;
                 ins_box[k] = a;
-                g.insert(k, ins_c[k]);
+                blo[0] = std::min(blo[0], ce.x), blo[1] = std::min(blo[1], ce.y), blo[2] = std::min(blo[2], ce.z);
+                bhi[0] = std::max(bhi[0], ce.x), bhi[1] = std::max(bhi[1], ce.y), bhi[2] = std::max(bhi[2], ce.z);
             }
         }
+        if (!n_in_grid) blo[0] = blo[1] = blo[2] = 0.0f, bhi[0] = bhi[1] = bhi[2] = 1.0f;
+        g.init(blo, bhi, thr + 2.0f * tol, n);
+        for (uint32_t k = 0; k < n; ++k)
+            if (in_grid[k]) g.insert(k, ins_c[k]);
     }
     // body k moved: refresh its cached AABB, re-insert if it drifted more than tol
     void refresh(uint32_t k) {
@@ -458,7 +493,7 @@ struct SweepGrid {
         const Aabb& o = ins_box[k];
         if (a.lo.x < o.lo.x - tol || a.lo.y < o.lo.y - tol || a.lo.z < o.lo.z - tol || a.hi.x > o.hi.x + tol ||
             a.hi.y > o.hi.y + tol || a.hi.z > o.hi.z + tol) {
-            g.remove(k, ins_c[k]);
+            g.remove(k);
             ins_c[k] = center_of(a);
             ins_box[k] = a;
             g.insert(k, ins_c[k]);
@@ -469,24 +504,20 @@ struct SweepGrid {
         cand.clear();
         // the stored centre of any small partner lies within [q.lo - reach, q.hi + reach]
         const float reach = R + tol + 0.5f * thr;
-        const int64_t x0 = g.cell(q.lo.x - reach), x1 = g.cell(q.hi.x + reach);
-        const int64_t y0 = g.cell(q.lo.y - reach), y1 = g.cell(q.hi.y + reach);
-        const int64_t z0 = g.cell(q.lo.z - reach), z1 = g.cell(q.hi.z + reach);
+        const int64_t x0 = g.cell(q.lo.x - reach, 0), x1 = g.cell(q.hi.x + reach, 0);
+        const int64_t y0 = g.cell(q.lo.y - reach, 1), y1 = g.cell(q.hi.y + reach, 1);
+        const int64_t z0 = g.cell(q.lo.z - reach, 2), z1 = g.cell(q.hi.z + reach, 2);
         const double ncell = double(x1 - x0 + 1) * double(y1 - y0 + 1) * double(z1 - z0 + 1);
-        if (ncell > 4.0 * double(g.cells.size()) + 64.0) {
-            // huge query box (e.g. a floor): walk the occupied cells instead
-            for (auto& kv : g.cells)
-                for (uint32_t k : kv.second)
-                    if (k > after) cand.push_back(k);
+        if (ncell > 4.0 * double(n_in_grid) + 64.0) {
+            // huge query box (e.g. a floor): every body in the grid is a candidate
+            for (uint32_t k = after + 1; k < sc.n; ++k)
+                if (in_grid[k]) cand.push_back(k);
         } else {
             for (int64_t z = z0; z <= z1; ++z)
                 for (int64_t y = y0; y <= y1; ++y)
-                    for (int64_t x = x0; x <= x1; ++x) {
-                        auto it = g.cells.find(HashGrid::key(x, y, z));
-                        if (it == g.cells.end()) continue;
-                        for (uint32_t k : it->second)
-                            if (k > after) cand.push_back(k);
-                    }
+                    for (int64_t x = x0; x <= x1; ++x)
+                        for (int32_t k = g.head[g.index(x, y, z)]; k >= 0; k = g.next[k])
+                            if ((uint32_t)k > after) cand.push_back((uint32_t)k);
         }
         for (uint32_t k : big)
             if (k > after) cand.push_back(k);
@@ -501,7 +532,7 @@ static void pass2_grid(Scene& sc, AabbCache& c, PairSink& sweep) {
     SweepGrid sg(sc, c);
     std::vector<uint32_t> cand;
     for (uint32_t i = 0; i < n; ++i) {
-        float R = 0.5f * sg.med;
+        float R = 0.125f * sg.med;
         uint32_t after = i;  // only slots > after are still to be visited for this i
         Aabb q = c.get(i);   // i's AABB when the candidate list was built
         sg.query(q, R, after, cand);

@@ -32,7 +32,7 @@ def assert_same_bits(a, b, what):
                              f"{a[tuple(bad[0])]:#x} vs {b[tuple(bad[0])]:#x}")
 
 
-def run_and_compare(oracle, scene, steps, mode=0, check_every=1, **wkw):
+def run_and_compare(oracle, scene, steps, mode=0, check_every=1, oracle_pair_cap=None, **wkw):
     """Step the GPU and the oracle in lock step, comparing bits every `check_every` steps."""
     with world(**wkw) as w:
         w.upload(scene)
@@ -43,7 +43,7 @@ def run_and_compare(oracle, scene, steps, mode=0, check_every=1, **wkw):
             k = min(check_every, steps - done)
             for _ in range(k):
                 stats = w.step(DT)
-            r = oracle.step(s, DT, k, mode=mode, want_snapshot=True)
+            r = oracle.step(s, DT, k, mode=mode, want_snapshot=True, pair_cap=oracle_pair_cap)
             done += k
             pos, vel = w.download()
             assert_same_bits(pos, r["pos"], f"pos after step {done}")
@@ -175,23 +175,14 @@ def test_both_repair_paths(oracle, monkeypatch, scene, tiny):
     assert retries > 0  # verification appended pairs, so a repair ran
 
 
-@pytest.mark.skipif(not os.environ.get("GP_EXPERIMENTAL"),
-                    reason="kernels that have not run on hardware yet are tested only on request (GP_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("variant", ["warp", "warp256", "wide_scatter", "sweep_skip"])
 @pytest.mark.parametrize("scene", ["uniform", "dense", "mixed", "pile", "one_cell"])
-def test_experimental_kernel_variants(oracle, monkeypatch, scene, variant):
-    """GP_PAIRFIND=warp / warp256 selects k_find_pairs_warp (gp_pairfind_warp.cuh) instead of k_find_pairs;
-    GP_WIDE_SCATTER=1 selects k_scatter_cells<true> (256-bit loads / stores of the body and AABB records);
-    GP_SWEEP_SKIP=1 lets the first sweep skip pairs that provably miss again without fetching their bodies."""
-    if variant == "wide_scatter":
-        monkeypatch.setenv("GP_WIDE_SCATTER", "1")
-    elif variant == "sweep_skip":
-        monkeypatch.setenv("GP_SWEEP_SKIP", "1")
-    else:
-        monkeypatch.setenv("GP_PAIRFIND", variant)
-    if scene == "one_cell":  # thousands of bodies in one grid cell: the body-at-a-time branch
-        s = scenes.uniform(5000, L=1.5, seed=41, rank_seed=42)  # (12.5 M pairs, every body a heavy chain)
-        run_and_compare(oracle, s, 1, mode=1, max_pairs=40_000_000)
+def test_kernel_paths(oracle, scene):
+    """Scenes chosen to reach every branch of K3/K4/K6: windows of the flattened test list (dense), multi-cell
+    big-list tests (mixed), heavy chains (pile), and thousands of bodies in ONE grid cell (the body-at-a-time walk of
+    k_find_pairs; 12.5 M pairs, every chain heavy)."""
+    if scene == "one_cell":
+        s = scenes.uniform(5000, L=1.5, seed=41, rank_seed=42)
+        run_and_compare(oracle, s, 1, mode=1, max_pairs=40_000_000, oracle_pair_cap=14_000_000)
         return
     s = {"uniform": lambda: scenes.uniform(100_000, L=126.0, seed=1001, rank_seed=2001),
          "dense": lambda: scenes.uniform(20_000, L=40.0, seed=33, rank_seed=34),
