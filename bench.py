@@ -140,6 +140,44 @@ def algorithmic_bytes(n: int, st: dict) -> dict:
     }
 
 
+def slab_parity(w, full_scene, wkw_single, dist, torch, local_rank: int, steps: int) -> dict:
+    """Multi-GPU correctness, measured: `steps` steps of the slab worlds against the SAME steps of one single-GPU world
+    of the whole scene (every rank runs its own copy of that reference, so nothing large crosses ranks).  A body may
+    differ only if the per-step exactness proof flagged it (or something it touched) at some step."""
+    from gears_b200.world import PhysicsWorld
+    n_total = int(full_scene["pos"].shape[0])
+    flagged = np.zeros(n_total, np.uint8)
+    for _ in range(steps):
+        w.step_async(DT, 1)
+        ent, pos, vel = w.download_owned()
+        flagged[ent[w.last_unverified != 0]] = 1
+    with PhysicsWorld(device=local_rank, **wkw_single) as ref:
+        ref.upload(full_scene)
+        for _ in range(steps):
+            ref.step(DT)
+        rpos, rvel = ref.download()
+    ft = torch.from_numpy(flagged).cuda()
+    dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+    flagged = ft.cpu().numpy()
+    rp, rv = rpos[ent], rvel[ent]
+    diff = (pos.view(np.uint32) != rp.view(np.uint32)).any(axis=1) | (vel.view(np.uint32) != rv.view(np.uint32)).any(axis=1)
+    err = 0.0
+    if diff.any():
+        for a, b in ((pos[diff], rp[diff]), (vel[diff], rv[diff])):
+            err = max(err, float(np.max(np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b.astype(np.float64)), 1.0))))
+    t = torch.tensor([float(len(ent)), float(diff.sum()), float((diff & (flagged[ent] == 0)).sum())], device="cuda",
+                     dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    n_cmp, n_diff, n_unfl = (int(x) for x in t.tolist())
+    return {"steps": steps, "bodies_compared": n_cmp, "every_body_owned_once": n_cmp == n_total,
+            "bit_identical": n_diff == 0, "n_differing": n_diff, "n_differing_not_flagged": n_unfl,
+            "n_flagged_cumulative": int(flagged.sum()), "max_rel_err": float(e.item()),
+            "against": "a single-GPU world of the whole scene stepped on every rank's own GPU (bit-exact vs the oracle "
+                       "in tests/)"}
+
+
 def run_ours(args) -> dict:
     import torch
     import torch.distributed as dist
@@ -172,7 +210,7 @@ def run_ours(args) -> dict:
         halo_est = args.halo if args.halo > 0 else 4.0 * float(ext[~rep].max())
         faces = slabs.bounds(scene, world_size, "balanced", replicate=rep, halo=halo_est)
         part = slabs.partition(scene, faces, rep)[rank]
-        del scene
+        full_scene, wkw_single = scene, dict(wkw)
         scene = part
         n_local = int(scene["pos"].shape[0])
         wkw = dict(wkw)
@@ -192,6 +230,13 @@ def run_ours(args) -> dict:
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- multi-GPU: slab worlds vs a single-GPU world, bit for bit, before anything is timed ----
+    parity = None
+    if world_size > 1 and args.parity_steps > 0:
+        parity = slab_parity(w, full_scene, wkw_single, dist, torch, local_rank, args.parity_steps)
+    if world_size > 1:
+        del full_scene
 
     # ---- device-resident throughput ----
     # warm-up: synchronous steps on a single world (gp_step grows the pair buffers when a scene densifies, e.g. a
@@ -242,6 +287,7 @@ def run_ours(args) -> dict:
         allr = [torch.zeros_like(mine) for _ in range(world_size)]
         dist.all_gather(allr, mine)
         slab_stats["per_rank_group_ms"] = [[round(float(x), 4) for x in t.tolist()] for t in allr]
+        slab_stats["parity"] = parity
     ms_per_step = ms_total / args.steps
     value = n_total * args.steps / (ms_total * 1e-3)
 
@@ -266,7 +312,9 @@ def run_ours(args) -> dict:
 
     # ---- end to end through the C ABI with pinned HOST buffers: H2D state + step + D2H result every step ----
     e2e = None
-    if world_size == 1:
+    if args.e2e_steps <= 0:
+        pass  # (profiling runs: device-resident numbers only)
+    elif world_size == 1:
         nb = 3 * n_local * 4
 
         def pinned():
@@ -480,6 +528,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-grid", action="store_true", help="skip the full-N grid-oracle CPU line")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--parity-steps", type=int, default=8,
+                    help="multi-GPU: steps of the slab worlds compared with a single-GPU world before the timed region")
     ap.add_argument("--halo", type=float, default=0.0,
                     help="slab coverage H beyond a face (multi-GPU); 0 = 4 x the largest grid-class extent")
     ap.add_argument("--max-exchange", type=int, default=0, help="records per slab face buffer (0 = auto)")

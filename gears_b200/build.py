@@ -34,7 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC, "-lnccl"]
+    extra = os.environ.get("GP_NVCC_EXTRA", "").split()  # e.g. -DGP_COOP_THREADS=640 (tuning experiments)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC, "-ldl"]
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)

@@ -14,6 +14,7 @@ GP_OK = 0
 GP_WARN_MARGIN_RETRIED = 1
 GP_ERR_BAD_ARG, GP_ERR_CUDA, GP_ERR_NO_DEVICE, GP_ERR_CAPACITY = -1, -2, -3, -4
 GP_ERR_PAIR_OVERFLOW, GP_ERR_MARGIN, GP_ERR_NCCL, GP_ERR_STATE = -5, -6, -7, -8
+GP_ERR_PEER_TIMEOUT = -9
 GP_FLAG_RECORD_PAIRS = 0x1
 GP_FLAG_NO_RETRY = 0x2
 GP_FLAG_PROFILE = 0x4
@@ -71,7 +72,8 @@ SYMBOLS = [
     "gp_update_shape", "gp_step", "gp_step_async", "gp_sync", "gp_download", "gp_pairs", "gp_damping_factors",
     "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_kernel_times_read", "gp_comm_unique_id", "gp_comm_init",
     "gp_comm_init_local", "gp_step_group", "gp_owned_count", "gp_download_owned", "gp_instances", "gp_raycast",
-    "gp_obstacle_grid", "gp_test_radix_sort", "gp_test_radix_sort64", "gp_test_exclusive_scan",
+    "gp_obstacle_grid", "gp_frame_submit", "gp_frame_wait", "gp_test_radix_sort", "gp_test_radix_sort64",
+    "gp_test_exclusive_scan",
 ]
 
 _lib = None
@@ -141,6 +143,10 @@ def lib():
     L.gp_raycast.restype = C.c_int32
     L.gp_obstacle_grid.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_obstacle_grid.restype = C.c_int32
+    L.gp_frame_submit.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    L.gp_frame_submit.restype = C.c_int32
+    L.gp_frame_wait.argtypes = [vp, C.c_uint32, C.POINTER(GpStepStats)]
+    L.gp_frame_wait.restype = C.c_int32
     L.gp_test_radix_sort.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     L.gp_test_radix_sort.restype = C.c_int32
     L.gp_test_radix_sort64.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]

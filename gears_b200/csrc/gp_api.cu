@@ -34,6 +34,7 @@ struct gp_world {
     uint32_t n = 0, cap = 0;
     uint64_t pair_cap = 0;
     bool uploaded = false;
+    bool dead = false;  // a slab neighbour timed out: no further steps until gp_upload (GP_ERR_PEER_TIMEOUT)
 
     // body state: two sets of five float4 arrays; every step gathers set `cur` into set `cur^1` in cell order
     float4 *B[2] = {nullptr, nullptr};  // 64 B records: P, V, Lo, Hi (see struct Bodies)
@@ -81,6 +82,16 @@ struct gp_world {
     // staging for host-layout arrays
     unsigned char* stage = nullptr;
     size_t stage_bytes = 0;
+    // pipelined frames (gp_frame_submit): copy streams, double-buffered device staging, body constants in id order
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    float4* home = nullptr;
+    bool home_valid = false;
+    float* fin[2] = {nullptr, nullptr};      // 3 x (n x 3) floats: pos, vel, acc
+    float4* fout[2] = {nullptr, nullptr};    // n x 8 floats
+    uint32_t frame_cap = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr},
+                ev_d2h[2] = {nullptr, nullptr};
+    uint64_t frames_submitted = 0;
 
     // profiling (GP_FLAG_PROFILE): events between kernel groups
     static constexpr int PROF_STEPS = 512;
@@ -96,6 +107,7 @@ struct gp_world {
     size_t fine_used = 0;
     std::vector<std::pair<std::string, std::pair<double, uint64_t>>> fine_acc;
     uint64_t fine_steps = 0;
+    bool fine_reset_done = false;
 
     gp_step_stats last{};
     uint64_t steps_total = 0;
@@ -141,6 +153,28 @@ static void fine_print(gp_world* w) {
     for (auto& a : w->fine_acc)
         fprintf(stderr, "[gp fine] %-22s %8.1f us/step  (%.2f launches/step)\n", a.first.c_str(),
                 1e3 * a.second.first / w->fine_steps, (double)a.second.second / w->fine_steps);
+    // phases inside k_contacts, as seen by thread 0 of the grid (globaltimer)
+    Ctl c;
+    if (cudaMemcpy(&c, w->ctl, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    static const char* names[12] = {"sweep: first frontier", "sweep: grid levels", "sweep: tail levels (CTA 0)",
+                                    "sweep: stats",          "verify: requery",    "verify: watch list",
+                                    "repair: link+walk",     "repair: exec",       "repair: list sweep",
+                                    "repair: component-local", "repair: re-verify", "slab proof"};
+    for (int i = 0; i < 12; ++i)
+        if (c.dbg_phase_ns[i])
+            fprintf(stderr, "[gp fine]   k_contacts / %-26s %8.1f us/step\n", names[i],
+                    1e-3 * (double)c.dbg_phase_ns[i] / w->fine_steps);
+    fprintf(stderr, "[gp fine]   k_contacts / levels run by CTA 0 alone: %.2f per step\n",
+            (double)c.dbg_tail_rounds / w->fine_steps);
+    for (int i = 0; i < 16; ++i)
+        if (c.dbg_level_ns[i])
+            fprintf(stderr, "[gp fine]   first sweep, slot %2d: %8.1f us/step, %10.1f pairs/step%s\n", i,
+                    1e-3 * (double)c.dbg_level_ns[i] / w->fine_steps, (double)c.dbg_level_n[i] / w->fine_steps,
+                    i == 0 ? "  (the scan that lists level 0)" : "");
+    fprintf(stderr, "[gp fine]   per step: %.1f escapees, %.1f requeried pairs, %.1f activated watch pairs, %.2f repair rounds; "
+            "per-component repair: %u rounds ok, %u fell back, largest component %u bodies / %u pairs\n",
+            (double)c.dbg_counts[0] / w->fine_steps, (double)c.dbg_counts[1] / w->fine_steps,
+            (double)c.dbg_counts[2] / w->fine_steps, (double)c.dbg_counts[3] / w->fine_steps, c.dbg_tiny[0], c.dbg_tiny[1], c.dbg_tiny[4], c.dbg_tiny[5]);
 }
 
 static gp_status fail(gp_world* w, gp_status s, const char* fmt, ...) {
@@ -175,7 +209,21 @@ static cudaError_t dmalloc(T** p, size_t count) {
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
+static void free_frames(gp_world* w) {
+    for (int b = 0; b < 2; ++b) {
+        if (w->fin[b]) cudaFree(w->fin[b]), w->fin[b] = nullptr;
+        if (w->fout[b]) cudaFree(w->fout[b]), w->fout[b] = nullptr;
+        for (cudaEvent_t* e : {&w->ev_h2d[b], &w->ev_in_free[b], &w->ev_unpacked[b], &w->ev_d2h[b]})
+            if (*e) cudaEventDestroy(*e), *e = nullptr;
+    }
+    if (w->home) cudaFree(w->home), w->home = nullptr;
+    if (w->st_h2d) cudaStreamDestroy(w->st_h2d), w->st_h2d = nullptr;
+    if (w->st_d2h) cudaStreamDestroy(w->st_d2h), w->st_d2h = nullptr;
+    w->frame_cap = 0, w->home_valid = false;
+}
+
 static void free_all(gp_world* w) {
+    free_frames(w);
     void* ptrs[] = {w->B[0],   w->B[1],  w->A[0],  w->A[1], w->ext,        w->slot_of, w->entity_dev, w->rawbox,
                     w->sbox,  w->key,     w->lrank,     w->perm, w->lb_tiles,   w->LB,
                     w->chain_cnt, w->offs,   w->tile_sums,  w->pairs, w->adj,
@@ -543,6 +591,8 @@ extern "C" gp_status gp_upload(gp_world* w, uint32_t n, const float* pos3, const
     s = setup_grid(w);
     if (s != GP_OK) return s;
     w->uploaded = true;
+    w->home_valid = false;
+    w->dead = false;
     w->slot_valid = false;
     w->last = gp_step_stats{};
     w->last_np = 0;
@@ -654,6 +704,7 @@ extern "C" gp_status gp_update_shape(gp_world* w, uint32_t k, const uint32_t* id
     k_classify<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, w->thr, Bodies{w->B[w->cur]}, w->A[w->cur],
                                                    w->d_small + 2 * EXT_BUCKETS);
     w->launches++;
+    w->home_valid = false;
     CK(cudaStreamSynchronize(w->st));
     return GP_OK;
 }
@@ -702,6 +753,18 @@ extern "C" gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out) {
     }
     for (int g = 0; g < GP_NUM_KERNEL_GROUPS; ++g) out->launches[g] = w->prof_launch[g], w->prof_launch[g] = 0;
     w->prof_n = 0;
+    if (w->fine && !w->fine_reset_done) {  // the fine-grained accumulators restart ONCE (bench.py drops its warm-up this way)
+        w->fine_reset_done = true;
+        fine_collect(w);
+        w->fine_acc.clear();
+        w->fine_steps = 0;
+        Ctl* dc = w->ctl;
+        CK(cudaMemsetAsync(dc->dbg_phase_ns, 0, sizeof dc->dbg_phase_ns, w->st));
+        CK(cudaMemsetAsync(dc->dbg_level_ns, 0, sizeof dc->dbg_level_ns + sizeof dc->dbg_level_n, w->st));
+        CK(cudaMemsetAsync(dc->dbg_counts, 0, sizeof dc->dbg_counts, w->st));
+        CK(cudaMemsetAsync(&dc->dbg_tail_rounds, 0, sizeof(uint32_t), w->st));
+        CK(cudaStreamSynchronize(w->st));
+    }
     return GP_OK;
 }
 
@@ -734,6 +797,7 @@ static gp_status enqueue_contacts(gp_world* w, float dt, const float* d, uint32_
     a.taint_bits = w->multi ? gp_multi_taint_bits(w->multi) : nullptr;
     a.dt = dt, a.d16 = d[0], a.d18 = d[1], a.d35 = d[2];
     a.start_phase = start_phase, a.max_rounds = max_rounds, a.tiny = w->tiny_repair ? 1u : 0u, a.latch = latch;
+    a.profile = w->fine ? 1u : 0u;
     void* args[] = {&a};
     CK(cudaLaunchCooperativeKernel((void*)k_contacts, dim3(w->sweep_grid), dim3(COOP_THREADS), args, sizeof(ContactSmem),
                                    w->st));
@@ -978,6 +1042,8 @@ extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, ui
     CK(cudaSetDevice(w->device));
     if (w->multi && gp_multi_is_local(w->multi))
         return fail(w, GP_ERR_STATE, "in-process slabs advance together: use gp_step_group");
+    if (w->dead)
+        return fail(w, GP_ERR_PEER_TIMEOUT, "a slab neighbour timed out earlier: this world is incomplete, upload again");
     CK(cudaEventRecord(w->ev0, w->st));
     for (uint32_t s = 0; s < nsteps; ++s) {
         gp_status r = enqueue_step(w, dt, damp3, 1, REPAIR_ROUNDS_ENQUEUED);
@@ -1002,6 +1068,10 @@ extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
     const Ctl& c = *w->h_ctl;
     if (w->steps_total) fill_stats(w, c, 0);
     if (stats) *stats = w->last;
+    if (c.unverified_total) {  // "since the last gp_sync": start a fresh sum
+        CK(cudaMemsetAsync(&w->ctl->unverified_total, 0, sizeof(uint32_t), w->st));
+        CK(cudaMemsetAsync(&w->ctl_snap->unverified_total, 0, sizeof(uint32_t), w->st));
+    }
     if (getenv("GP_DEBUG_TINY"))
         fprintf(stderr, "[gp] tiny repair: rounds ok %u, fell back %u, components %u, too large %u, largest %u bodies / %u pairs\n",
                 c.dbg_tiny[0], c.dbg_tiny[1], c.dbg_tiny[2], c.dbg_tiny[3], c.dbg_tiny[4], c.dbg_tiny[5]);
@@ -1010,7 +1080,15 @@ extern "C" gp_status gp_sync(gp_world* w, gp_step_stats* stats) {
         // clear the latch so the caller can continue after reacting
         Ctl* dc = w->ctl;
         CK(cudaMemsetAsync(&dc->sticky_flags, 0, sizeof(uint32_t), w->st));
+        CK(cudaMemsetAsync(&dc->steps_inexact, 0, sizeof(uint32_t), w->st));  // reported below: start a fresh count
+        CK(cudaMemsetAsync(&w->ctl_snap->sticky_flags, 0, sizeof(uint32_t), w->st));
+        CK(cudaMemsetAsync(&w->ctl_snap->steps_inexact, 0, sizeof(uint32_t), w->st));
         CK(cudaStreamSynchronize(w->st));
+        if (f & SF_PEER_TIMEOUT) {
+            w->dead = true;
+            return fail(w, GP_ERR_PEER_TIMEOUT, "a slab neighbour did not arrive at the exchange within the time-out "
+                        "(GP_PEER_TIMEOUT_MS): bodies in flight are lost, %u step(s) invalid; upload again", c.steps_inexact);
+        }
         if (f & SF_EXCHANGE_OVERFLOW)
             return fail(w, GP_ERR_CAPACITY, "%u async step(s) were inexact: a slab exchange buffer (max_exchange) or "
                         "max_bodies was too small", c.steps_inexact);
@@ -1054,6 +1132,98 @@ extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
     if (vel3) CK(cudaMemcpyAsync(vel3, dv, b3, cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
     return gp_sync(w, nullptr);
+}
+
+// ---- pipelined frames ----
+static gp_status ensure_frames(gp_world* w) {
+    if (!w->st_h2d) {
+        CK(cudaStreamCreateWithFlags(&w->st_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&w->st_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b)
+            for (cudaEvent_t* e : {&w->ev_h2d[b], &w->ev_in_free[b], &w->ev_unpacked[b], &w->ev_d2h[b]})
+                CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    if (w->frame_cap < w->n) {
+        // (buffers of frames in flight: none -- the first frame after a (re)allocation waits for everything)
+        CK(cudaStreamSynchronize(w->st));
+        CK(cudaStreamSynchronize(w->st_h2d));
+        CK(cudaStreamSynchronize(w->st_d2h));
+        for (int b = 0; b < 2; ++b) {
+            CK(dmalloc(&w->fin[b], 9 * (size_t)w->cap));
+            CK(dmalloc(&w->fout[b], 2 * (size_t)w->cap));
+        }
+        CK(dmalloc(&w->home, 3 * (size_t)w->cap));
+        w->frame_cap = w->cap;
+        w->home_valid = false;
+        w->frames_submitted = 0;
+    }
+    if (!w->home_valid) {
+        k_build_home<<<cdiv(w->n, 256), 256, 0, w->st>>>(w->n, Bodies{w->B[w->cur]}, w->A[w->cur], w->home);
+        w->launches++;
+        CK(cudaGetLastError());
+        w->home_valid = true;
+    }
+    return GP_OK;
+}
+
+extern "C" gp_status gp_frame_submit(gp_world* w, const float* pos3, const float* vel3, const float* acc3, float dt,
+                                     const float* damp3, float* state8_out) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_frame_submit before gp_upload");
+    if (w->multi) return fail(w, GP_ERR_STATE, "gp_frame_submit addresses bodies by upload index: not available on a slab world");
+    if (!pos3 || !vel3 || !acc3 || !state8_out) return fail(w, GP_ERR_BAD_ARG, "gp_frame_submit: a buffer is NULL");
+    CK(cudaSetDevice(w->device));
+    const uint32_t n = w->n;
+    if (n == 0) return GP_OK;
+    gp_status s = ensure_frames(w);
+    if (s != GP_OK) return s;
+    const int b = (int)(w->frames_submitted & 1u);
+    const bool reuse = w->frames_submitted >= 2;  // the buffers of parity b were last used by frame t-2
+    const size_t row = 3 * sizeof(float) * (size_t)n, stride = 3 * (size_t)w->frame_cap;
+    float* in = w->fin[b];
+    // copy stream: inputs of this frame (after the refresh of frame t-2 has consumed the buffer)
+    if (reuse) CK(cudaStreamWaitEvent(w->st_h2d, w->ev_in_free[b], 0));
+    CK(cudaMemcpyAsync(in, pos3, row, cudaMemcpyHostToDevice, w->st_h2d));
+    CK(cudaMemcpyAsync(in + stride, vel3, row, cudaMemcpyHostToDevice, w->st_h2d));
+    CK(cudaMemcpyAsync(in + 2 * stride, acc3, row, cudaMemcpyHostToDevice, w->st_h2d));
+    CK(cudaEventRecord(w->ev_h2d[b], w->st_h2d));
+    // step stream: refresh (bodies land in id order; K1..K3 sort them as in every step), step, read-back
+    CK(cudaStreamWaitEvent(w->st, w->ev_h2d[b], 0));
+    k_set_state_all<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->home, in, in + stride, in + 2 * stride, Bodies{w->B[w->cur]},
+                                                      w->A[w->cur]);
+    w->launches++;
+    fine_mark(w, "k_set_state_all");
+    CK(cudaEventRecord(w->ev_in_free[b], w->st));
+    s = enqueue_step(w, dt, damp3, 1, REPAIR_ROUNDS_ENQUEUED);
+    if (s != GP_OK) return s;
+    w->cur ^= 1;
+    w->steps_total++;
+    if (reuse) CK(cudaStreamWaitEvent(w->st, w->ev_d2h[b], 0));  // the download of frame t-2 has left the buffer
+    k_unpack8<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, w->fout[b]);
+    w->launches++;
+    fine_mark(w, "k_unpack8");
+    CK(cudaEventRecord(w->ev_unpacked[b], w->st));
+    // download stream
+    CK(cudaStreamWaitEvent(w->st_d2h, w->ev_unpacked[b], 0));
+    CK(cudaMemcpyAsync(state8_out, w->fout[b], 8 * sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, w->st_d2h));
+    CK(cudaEventRecord(w->ev_d2h[b], w->st_d2h));
+    w->frames_submitted++;
+    w->slot_valid = false;
+    return GP_OK;
+}
+
+extern "C" gp_status gp_frame_wait(gp_world* w, uint32_t max_in_flight, gp_step_stats* stats) {
+    if (!w) return GP_ERR_BAD_ARG;
+    CK(cudaSetDevice(w->device));
+    if (w->frames_submitted == 0 || !w->st_d2h) return max_in_flight ? GP_OK : gp_sync(w, stats);
+    if (max_in_flight == 0) {
+        CK(cudaStreamSynchronize(w->st_d2h));
+        return gp_sync(w, stats);
+    }
+    if (max_in_flight >= 2) return GP_OK;  // the events bound the queue at two frames
+    // one frame may stay in flight: wait for the download of the frame before the last one
+    if (w->frames_submitted >= 2) CK(cudaEventSynchronize(w->ev_d2h[(int)((w->frames_submitted - 2) & 1u)]));
+    return GP_OK;
 }
 
 extern "C" gp_status gp_pairs(gp_world* w, int32_t which, uint32_t* pairs2, uint64_t cap, uint64_t* n_out) {

@@ -179,15 +179,24 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until *f >= want for both flags (nullptr = no neighbour on that side)
-__global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t want, Ctl* ctl) {
+// wait until *f >= want for both flags (nullptr = no neighbour on that side).  Bounded (a library kernel never spins
+// forever), but generously: ranks are separate processes, and ordinary host skew (a download, a GC pause, late
+// enqueueing) must not expire it.  An expired wait is FATAL for the world: records that were migrating in the missed
+// message are gone, so peer_dead is latched, k_append appends nothing from then on, and gp_sync reports
+// GP_ERR_PEER_TIMEOUT until the caller uploads again.
+__global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t want, Ctl* ctl,
+                             unsigned long long timeout_ns) {
     const uint32_t* f = threadIdx.x == 0 ? f0 : f1;
     if (threadIdx.x > 1 || !f) return;
-    for (uint32_t spin = 0; spin < (1u << 23); ++spin) {
+    if (*(volatile uint32_t*)&ctl->peer_dead) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
         if (ld_acquire_sys(f) >= want) return;
-        __nanosleep(100);
+        __nanosleep(200);
+        if (globaltimer_ns() - t0 > timeout_ns) break;
     }
-    atomicOr(&ctl->step_flags, SF_INTERNAL);  // the neighbour never arrived (~1 s): the step is invalid, not hung
+    atomicOr(&ctl->step_flags, SF_PEER_TIMEOUT);
+    atomicExch(&ctl->peer_dead, 1u);
 }
 __global__ void k_post_flags(uint32_t* f0, uint32_t* f1, uint32_t v) {
     __threadfence_system();
@@ -210,6 +219,13 @@ __global__ void __launch_bounds__(256)
     k_append(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, const Bodies B0,
              float4* __restrict__ A, uint32_t* __restrict__ key, uint32_t* __restrict__ lrank,
              uint32_t* __restrict__ cell_cnt, Ctl* ctl) {
+    if (ctl->peer_dead) {  // a neighbour timed out: whatever is in the buffers is not this step's message
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ctl->n_recv = 0;
+            atomicOr(&ctl->step_flags, SF_PEER_TIMEOUT);
+        }
+        return;
+    }
     const uint32_t cl = recv_l ? min(__float_as_uint(__ldcg(recv_l).x), ctl->xcap[0]) : 0u;
     const uint32_t cr = recv_r ? min(__float_as_uint(__ldcg(recv_r).x), ctl->xcap[1]) : 0u;
     const uint32_t n_in = ctl->n_in;

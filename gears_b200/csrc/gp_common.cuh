@@ -96,7 +96,12 @@ struct Ctl {
     uint32_t dirty_level[3];     // bodies appended to the dirty list per BFS level (rotating)
     uint32_t n_resweep;          // stats: pairs re-swept by repair rounds this step
     uint32_t tiny_fallback;      // the per-component repair met a component it does not handle: the general repair runs
+    uint32_t peer_dead;          // latched: a slab neighbour timed out (k_wait_flags); nothing is appended any more
     uint32_t sweep_round;        // level the sweep continues with after CTA 0 ran the tail levels alone
+    uint32_t dbg_tail_rounds;    // since creation: levels run by CTA 0 alone
+    unsigned long long dbg_level_ns[16], dbg_level_n[16];  // first sweep: time and pairs per dependency level (GP_PROF_FINE)
+    unsigned long long dbg_counts[4];  // since creation: escapees, requeried pairs, activated watch pairs, repair rounds
+    unsigned long long dbg_phase_ns[12];  // since creation: time per phase of k_contacts as seen by thread 0 (GP_PROF_FINE)
     uint32_t n_escapees_total;   // stats: escapees of the first sweep
     uint32_t dbg_tiny[6];        // since creation: rounds done by the tiny repair, rounds that fell back, components
                                  // repaired, components too large, largest component seen (bodies, pairs)
@@ -137,7 +142,8 @@ constexpr uint32_t SF_MARGIN_MAX = 4u;   // (unused)
 constexpr uint32_t SF_HEAVY_OVERFLOW = 16u;
 constexpr uint32_t SF_ESCAPEE_OVERFLOW = 32u;
 constexpr uint32_t SF_EXCHANGE_OVERFLOW = 128u;  // a slab exchange buffer or the body arrays were too small
-constexpr uint32_t SF_INTERNAL = 64u;     // a bounded wait expired (TMA copy never landed): result invalid
+constexpr uint32_t SF_INTERNAL = 64u;     // (unused since the TMA pair find was retired)
+constexpr uint32_t SF_PEER_TIMEOUT = 256u;  // slab exchange: a neighbour never arrived; the world is dead until re-uploaded
 
 // Body record (array of structures, 64 B = one DRAM burst): P = pos|mass, V = vel|restitution, Lo = min offset|id,
 // Hi = max offset|rank.  The contact sweep touches bodies at random; with the four float4 in one 64 B line a body
@@ -205,6 +211,33 @@ struct ContactArgs {
     uint32_t max_rounds;         // repair rounds before the step is declared still-growing (SF_MARGIN)
     uint32_t tiny;               // per-component warp repair in front of the cooperative one
     int latch;                   // finish_step mode
+    uint32_t profile;            // GP_PROF_FINE: thread 0 keeps per-phase times in ctl->dbg_phase_ns
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase clock of k_contacts (thread 0 of the grid only): charge the time since the last stamp to `phase`
+struct PhaseClock {
+    unsigned long long t;
+    bool on;
+    __device__ __forceinline__ void start(bool enabled) {
+        on = enabled && blockIdx.x == 0 && threadIdx.x == 0;
+        if (on) t = globaltimer_ns();
+    }
+    __device__ __forceinline__ void stamp(Ctl* ctl, int phase, int level = -1, uint32_t level_pairs = 0) {
+        if (!on) return;
+        const unsigned long long now = globaltimer_ns();
+        ctl->dbg_phase_ns[phase] += now - t;
+        if (level >= 0) {
+            const int l = level < 15 ? level : 15;
+            ctl->dbg_level_ns[l] += now - t;
+            ctl->dbg_level_n[l] += level_pairs;
+        }
+        t = now;
+    }
 };
 
 struct V3 {

@@ -39,67 +39,76 @@ struct SweepAcc {
     float maxd = 0.0f, maxabs = 0.0f;
 };
 
-template <bool SKIP>
-__device__ __forceinline__ void sweep_pair(const ContactArgs& a, FrontierStage& fs, uint32_t pid, const uint4 rec,
-                                           const uint4 link, uint32_t* fout, uint32_t* fcount, SweepAcc& acc) {
+// test + resolve of one pair at its turn.  LEVEL0: the pair is at the head of all its chains, so no earlier pair of this
+// sweep has touched its bodies: without the S_snapshot flag it misses again, whatever moved_bits says.
+// (Loads are staged -- moved bits, then boxes, then velocities only for a hit: fetching everything a contact could need
+// in one round trip was measured slower, the extra live registers spill at 768 threads per SM.)
+template <bool SKIP, bool LEVEL0>
+__device__ __forceinline__ void pair_execute(const ContactArgs& a, FrontierStage& fs, uint32_t pid, const uint4 rec,
+                                             SweepAcc& acc) {
     const Bodies B = a.B1;
     const uint32_t ia = rec.x & ~TOPBIT, ib = rec.y & ~TOPBIT;
-    bool quick_miss = false;
     if (SKIP && !(rec.z & TOPBIT)) {
+        if (LEVEL0) return;
         const uint32_t wa = __ldcg(&a.moved_bits[ia >> 5]), wb = __ldcg(&a.moved_bits[ib >> 5]);
-        quick_miss = !(((wa >> (ia & 31u)) | (wb >> (ib & 31u))) & 1u);
+        if (!(((wa >> (ia & 31u)) | (wb >> (ib & 31u))) & 1u)) return;
     }
-    if (!quick_miss) {
-        BodyRW x, y;
-        x.is_static = (rec.x & TOPBIT) != 0;
-        y.is_static = (rec.y & TOPBIT) != 0;
-        const float4 pa = ldcg4(&B.P(ia)), pb = ldcg4(&B.P(ib));
-        const float4 loa = ldcg4(&B.Lo(ia)), hia = ldcg4(&B.Hi(ia)), lob = ldcg4(&B.Lo(ib)), hib = ldcg4(&B.Hi(ib));
-        x.pos = xyz(pa), x.mass = pa.w, x.omin = xyz(loa), x.omax = xyz(hia);
-        y.pos = xyz(pb), y.mass = pb.w, y.omin = xyz(lob), y.omax = xyz(hib);
-        const V3 amin = x.omin + x.pos, amax = x.omax + x.pos;
-        const V3 bmin = y.omin + y.pos, bmax = y.omax + y.pos;
-        // physics.rs:159-164 on the CURRENT positions
-        const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y && amin.z < bmax.z &&
-                         amax.z > bmin.z;
-        if (hit) {
-            ++acc.contacts;
-            const float4 va = ldcg4(&B.V(ia)), vb = ldcg4(&B.V(ib));
-            x.vel = xyz(va), x.rest = va.w;
-            y.vel = xyz(vb), y.rest = vb.w;
-            const bool moved = resolve_pair(x, y, amin, amax, bmin, bmax);
-            if (!x.is_static) {
-                __stcg(&B.P(ia), make_float4(x.pos.x, x.pos.y, x.pos.z, x.mass));
-                __stcg(&B.V(ia), make_float4(x.vel.x, x.vel.y, x.vel.z, x.rest));
-            }
-            if (!y.is_static) {
-                __stcg(&B.P(ib), make_float4(y.pos.x, y.pos.y, y.pos.z, y.mass));
-                __stcg(&B.V(ib), make_float4(y.vel.x, y.vel.y, y.vel.z, y.rest));
-            }
-            if (moved) {
-                if (!x.is_static)
-                    track_move(x, ia, __ldcg(&a.sbox[2 * (size_t)ia]), a.dmax, a.moved_bits, a.esc_bits, a.escapees,
-                               a.esc_cap, a.ctl, acc.maxd, acc.maxabs);
-                if (!y.is_static)
-                    track_move(y, ib, __ldcg(&a.sbox[2 * (size_t)ib]), a.dmax, a.moved_bits, a.esc_bits, a.escapees,
-                               a.esc_cap, a.ctl, acc.maxd, acc.maxabs);
-                if (SKIP) {  // every position write counts (see above)
-                    if (!x.is_static) atomicOr(&a.moved_bits[ia >> 5], 1u << (ia & 31u));
-                    if (!y.is_static) atomicOr(&a.moved_bits[ib >> 5], 1u << (ib & 31u));
-                }
-            }
-            a.pairs[2 * (size_t)pid].w = rec.w | TOPBIT;  // S_sweep flag; the repair: these bodies were written
+    BodyRW x, y;
+    x.is_static = (rec.x & TOPBIT) != 0;
+    y.is_static = (rec.y & TOPBIT) != 0;
+    const float4 pa = ldcg4(&B.P(ia)), pb = ldcg4(&B.P(ib));
+    const float4 loa = ldcg4(&B.Lo(ia)), hia = ldcg4(&B.Hi(ia)), lob = ldcg4(&B.Lo(ib)), hib = ldcg4(&B.Hi(ib));
+    x.pos = xyz(pa), x.mass = pa.w, x.omin = xyz(loa), x.omax = xyz(hia);
+    y.pos = xyz(pb), y.mass = pb.w, y.omin = xyz(lob), y.omax = xyz(hib);
+    const V3 amin = x.omin + x.pos, amax = x.omax + x.pos;
+    const V3 bmin = y.omin + y.pos, bmax = y.omax + y.pos;
+    // physics.rs:159-164 on the CURRENT positions
+    const bool hit = amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y && amin.z < bmax.z &&
+                     amax.z > bmin.z;
+    if (!hit) return;
+    ++acc.contacts;
+    const float4 va = ldcg4(&B.V(ia)), vb = ldcg4(&B.V(ib));
+    x.vel = xyz(va), x.rest = va.w;
+    y.vel = xyz(vb), y.rest = vb.w;
+    const bool moved = resolve_pair(x, y, amin, amax, bmin, bmax);
+    if (!x.is_static) {
+        __stcg(&B.P(ia), make_float4(x.pos.x, x.pos.y, x.pos.z, x.mass));
+        __stcg(&B.V(ia), make_float4(x.vel.x, x.vel.y, x.vel.z, x.rest));
+    }
+    if (!y.is_static) {
+        __stcg(&B.P(ib), make_float4(y.pos.x, y.pos.y, y.pos.z, y.mass));
+        __stcg(&B.V(ib), make_float4(y.vel.x, y.vel.y, y.vel.z, y.rest));
+    }
+    if (moved) {
+        if (!x.is_static)
+            track_move(x, ia, __ldcg(&a.sbox[2 * (size_t)ia]), __ldcg(&a.dmax[ia]), a.dmax, a.moved_bits, a.esc_bits,
+                       a.escapees, a.esc_cap, a.ctl, &fs, acc.maxd, acc.maxabs);
+        if (!y.is_static)
+            track_move(y, ib, __ldcg(&a.sbox[2 * (size_t)ib]), __ldcg(&a.dmax[ib]), a.dmax, a.moved_bits, a.esc_bits,
+                       a.escapees, a.esc_cap, a.ctl, &fs, acc.maxd, acc.maxabs);
+        if (SKIP) {  // every position write counts (see above)
+            if (!x.is_static) atomicOr(&a.moved_bits[ia >> 5], 1u << (ia & 31u));
+            if (!y.is_static) atomicOr(&a.moved_bits[ib >> 5], 1u << (ib & 31u));
         }
     }
-    // wake the successors on both chains once they are at the head everywhere (static endpoints have no chain:
-    // their link stays NONE)
+    a.pairs[2 * (size_t)pid].w = rec.w | TOPBIT;  // S_sweep flag; the repair: these bodies were written
+}
+// wake the successors on both chains once they are at the head everywhere (static endpoints have no chain: their
+// link stays NONE)
+__device__ __forceinline__ void pair_wake(const ContactArgs& a, FrontierStage& fs, const uint4 link, uint32_t* fout,
+                                          uint32_t* fcount) {
     if (link.x != NONE && atomicSub(&pair_link(a.pairs, link.x)[2], 1u) == 1u) stage_push(fs, link.x, fout, fcount);
     if (link.y != NONE && atomicSub(&pair_link(a.pairs, link.y)[2], 1u) == 1u) stage_push(fs, link.y, fout, fcount);
 }
 
-// one frontier item range [lo, hi) strided over `nthreads` threads (thread t of them), two pairs per thread in
-// flight: both pair records are fetched before either pair is processed
-template <bool SKIP>
+__device__ __forceinline__ void flush(const ContactArgs& a, FrontierStage& fs, uint32_t* fout, uint32_t* fcount) {
+    stage_flush(fs, fout, fcount, a.escapees, a.esc_cap, a.ctl);
+}
+
+// The items of one level: thread t of nthreads, two items per iteration (both records are fetched before either pair
+// is processed).  No barrier inside: the warps of a CTA drift apart and hide each other's dependent loads; a push that
+// finds the CTA's stage full goes straight to the global list.
+template <bool SKIP, bool LEVEL0>
 __device__ __forceinline__ void sweep_items(const ContactArgs& a, FrontierStage& fs, const uint32_t* fin, uint32_t nf,
                                             uint32_t t, uint32_t nthreads, uint32_t* fout, uint32_t* fcount,
                                             SweepAcc& acc) {
@@ -110,29 +119,39 @@ __device__ __forceinline__ void sweep_items(const ContactArgs& a, FrontierStage&
         const uint4 r0 = __ldcg(&a.pairs[2 * (size_t)p0]), l0 = __ldcg(&a.pairs[2 * (size_t)p0 + 1]);
         uint4 r1 = r0, l1 = l0;
         if (two) r1 = __ldcg(&a.pairs[2 * (size_t)p1]), l1 = __ldcg(&a.pairs[2 * (size_t)p1 + 1]);
-        sweep_pair<SKIP>(a, fs, p0, r0, l0, fout, fcount, acc);
-        if (two) sweep_pair<SKIP>(a, fs, p1, r1, l1, fout, fcount, acc);
+        pair_execute<SKIP, LEVEL0>(a, fs, p0, r0, acc);
+        pair_wake(a, fs, l0, fout, fcount);
+        if (two) {
+            pair_execute<SKIP, LEVEL0>(a, fs, p1, r1, acc);
+            pair_wake(a, fs, l1, fout, fcount);
+        }
     }
 }
 
 // LIST: repair sweep over the pairs the component-local repair collected (ra.dpairs); SKIP: see above
 template <bool LIST, bool SKIP>
-__device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_group& grid) {
+__device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_group& grid, PhaseClock& pc) {
     Ctl* ctl = a.ctl;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    if (threadIdx.x == 0) fs.cnt = 0;
+    if (threadIdx.x == 0) fs.cnt = 0, fs.ecnt = 0;
     __syncthreads();
     const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap);
-    // round 0 frontier: pairs at the head of all their chains
+    SweepAcc acc;
+    // Level 0 = the pairs at the head of all their chains, found by one coalesced scan of the link records.  First
+    // sweep: two thirds of them are linked to nothing and five in six carry no S_snapshot flag -- with the sweep
+    // shortcut such a pair needs neither a test nor a wake-up, so it is not even listed.
     const uint32_t nl = LIST ? __ldcg(&ctl->n_dpairs) : np;
     for (uint32_t li = gtid; li < nl; li += gsz) {
         const uint32_t pid = LIST ? __ldcg(&a.ra.dpairs[li]) : li;
-        if (__ldcg(&pair_link(a.pairs, pid)[2]) == 0) stage_push(fs, pid, a.frontier0, &ctl->frontier_n[0]);
+        const uint4 link = __ldcg(&a.pairs[2 * (size_t)pid + 1]);
+        if (link.z != 0) continue;
+        if (!LIST && SKIP && (link.x & link.y) == NONE && !(__ldcg(&a.pairs[2 * (size_t)pid].z) & TOPBIT)) continue;
+        stage_push(fs, pid, a.frontier0, &ctl->frontier_n[0]);
     }
-    stage_flush(fs, a.frontier0, &ctl->frontier_n[0]);
+    flush(a, fs, a.frontier0, &ctl->frontier_n[0]);
     grid.sync();
+    pc.stamp(ctl, LIST ? 8 : 0, LIST ? -1 : 0, 0);
     uint32_t rounds = 0;
-    SweepAcc acc;
     while (true) {
         const uint32_t ci = rounds % 3u, co = (rounds + 1u) % 3u, cz = (rounds + 2u) % 3u;
         const uint32_t nf = __ldcg(&ctl->frontier_n[ci]);
@@ -145,7 +164,10 @@ __device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_gr
                     const uint32_t* fin = (r & 1u) ? a.frontier1 : a.frontier0;
                     uint32_t* fout = (r & 1u) ? a.frontier0 : a.frontier1;
                     // the stage holds at most 2 * TAIL_MAX <= FB_CAP pushes: the overflow path is never taken
-                    sweep_items<SKIP>(a, fs, fin, n_now, threadIdx.x, blockDim.x, fout, nullptr, acc);
+                    if (!LIST && r == 0)
+                        sweep_items<SKIP, true>(a, fs, fin, n_now, threadIdx.x, blockDim.x, fout, nullptr, acc);
+                    else
+                        sweep_items<SKIP, false>(a, fs, fin, n_now, threadIdx.x, blockDim.x, fout, nullptr, acc);
                     __syncthreads();
                     const uint32_t c = fs.cnt;
                     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) __stcg(&fout[i], fs.buf[i]);
@@ -160,9 +182,11 @@ __device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_gr
                     ctl->frontier_n[(r + 1u) % 3u] = 0u;
                     ctl->frontier_n[(r + 2u) % 3u] = 0u;
                     ctl->sweep_round = r;
+                    ctl->dbg_tail_rounds += r - rounds;
                 }
             }
             grid.sync();
+            pc.stamp(ctl, LIST ? 8 : 2);
             rounds = __ldcg(&ctl->sweep_round);
             continue;
         }
@@ -171,29 +195,42 @@ __device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_gr
         if (gtid == 0) ctl->frontier_n[cz] = 0;
         const uint32_t* fin = (rounds & 1u) ? a.frontier1 : a.frontier0;
         uint32_t* fout = (rounds & 1u) ? a.frontier0 : a.frontier1;
-        sweep_items<SKIP>(a, fs, fin, nf, gtid, gsz, fout, &ctl->frontier_n[co], acc);
-        stage_flush(fs, fout, &ctl->frontier_n[co]);
+        if (!LIST && rounds == 0)
+            sweep_items<SKIP, true>(a, fs, fin, nf, gtid, gsz, fout, &ctl->frontier_n[co], acc);
+        else
+            sweep_items<SKIP, false>(a, fs, fin, nf, gtid, gsz, fout, &ctl->frontier_n[co], acc);
+        flush(a, fs, fout, &ctl->frontier_n[co]);
         ++rounds;
         grid.sync();
+        pc.stamp(ctl, LIST ? 8 : 1, LIST ? -1 : (int)rounds, nf);
     }
-    // per-thread partials -> warp -> global
+    flush(a, fs, a.frontier0, &ctl->frontier_n[0]);  // (escapees staged by the tail levels; the frontier stage is empty)
+    // per-thread partials -> warp -> CTA (the stage is idle now) -> ONE atomic per CTA and counter
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         acc.contacts += __shfl_xor_sync(0xffffffffu, acc.contacts, o);
         acc.maxd = fmaxf(acc.maxd, __shfl_xor_sync(0xffffffffu, acc.maxd, o));
         acc.maxabs = fmaxf(acc.maxabs, __shfl_xor_sync(0xffffffffu, acc.maxabs, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (acc.contacts) atomicAdd(&ctl->n_contacts, acc.contacts);
-        if (acc.maxd > 0.0f) atomicMax(&ctl->max_disp_bits, __float_as_uint(acc.maxd));
-        if (acc.maxabs > 0.0f) atomicMax(&ctl->max_abs_disp_bits, __float_as_uint(acc.maxabs));
+    __syncthreads();
+    if (threadIdx.x < 3) fs.buf[threadIdx.x] = 0u;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {  // (positive floats order like their bit patterns)
+        if (acc.contacts) atomicAdd(&fs.buf[0], acc.contacts);
+        if (acc.maxd > 0.0f) atomicMax(&fs.buf[1], __float_as_uint(acc.maxd));
+        if (acc.maxabs > 0.0f) atomicMax(&fs.buf[2], __float_as_uint(acc.maxabs));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (fs.buf[0]) atomicAdd(&ctl->n_contacts, fs.buf[0]);
+        if (fs.buf[1]) atomicMax(&ctl->max_disp_bits, fs.buf[1]);
+        if (fs.buf[2]) atomicMax(&ctl->max_abs_disp_bits, fs.buf[2]);
     }
     if (gtid == 0) {
         ctl->n_rounds = max(ctl->n_rounds, rounds);
         ctl->n_pairs_swept = np;
         if (!LIST) ctl->n_pairs_k4 = np;
         ctl->frontier_n[0] = ctl->frontier_n[1] = ctl->frontier_n[2] = 0;
-        ctl->sweep_round = 0;
     }
 }
 
@@ -206,6 +243,7 @@ union ContactSmem {
     TinyWalk walk[COOP_THREADS / 32];
     TinyExec exec[TINY_EXEC_WARPS];
     unsigned long long wbuf[COOP_THREADS / 32][WSORT_SMEM];
+    RequeryList rq[COOP_THREADS / 32];
 };
 
 __global__ void __launch_bounds__(COOP_THREADS, 1) k_contacts(const ContactArgs a) {
@@ -214,12 +252,20 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_contacts(const ContactArgs 
     cg::grid_group grid = cg::this_grid();
     Ctl* ctl = a.ctl;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    PhaseClock pc;
+    pc.start(a.profile != 0);
     if (a.start_phase == 0) {
-        sweep_phase<false, true>(a, sm.fs, grid);
+        sweep_phase<false, true>(a, sm.fs, grid, pc);
         grid.sync();
-        requery_phase(a);
+        pc.stamp(ctl, 3);
+        requery_phase(a, sm.rq[threadIdx.x >> 5]);
+        if (a.profile) {
+            grid.sync();
+            pc.stamp(ctl, 4);
+        }
         verify_watch_phase(a);
         grid.sync();
+        pc.stamp(ctl, 5);
     }
     uint32_t round = 0;
     // (uniform: every thread reads the same word behind a grid barrier)
@@ -231,30 +277,36 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_contacts(const ContactArgs 
             grid.sync();
             tiny_walk_phase(a, sm.walk[threadIdx.x >> 5]);
             grid.sync();
+            pc.stamp(ctl, 6);
             const bool fits = __ldcg(&ctl->tiny_fallback) == 0;
             if (fits) tiny_exec_phase(a, sm.exec);
             grid.sync();
             if (gtid == 0) tiny_done(ctl, a.pair_cap);
             repaired = fits;
             grid.sync();
+            pc.stamp(ctl, 7);
         }
         if (!repaired) {
-            // a component beyond 32 bodies / 96 pairs (a pile): component-local cooperative repair + list sweep
+            // a component beyond 64 bodies / 192 pairs (a pile): component-local cooperative repair + list sweep
             repair_local_phase(a, sm.wbuf, grid);
             grid.sync();
-            sweep_phase<true, false>(a, sm.fs, grid);
+            pc.stamp(ctl, 9);
+            sweep_phase<true, false>(a, sm.fs, grid, pc);
             grid.sync();
             if (gtid == 0) ctl->repair_needed = 0;
             grid.sync();
+            pc.stamp(ctl, 8);
         }
-        requery_phase(a);
+        requery_phase(a, sm.rq[threadIdx.x >> 5]);
         verify_watch_phase(a);
         grid.sync();
+        pc.stamp(ctl, 10);
         ++round;
     }
     if (a.taint_bits) {
         taint_phase(a, grid);
         grid.sync();
+        pc.stamp(ctl, 11);
     }
     if (gtid == 0) finish_step(ctl, a.ctl_snap, a.latch);
 }

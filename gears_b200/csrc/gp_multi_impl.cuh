@@ -12,9 +12,19 @@
 // The reference has no distributed runtime at all; this decomposition is new.
 #pragma once
 #include <dlfcn.h>
-#include <nccl.h>
 
-// NCCL is bound at run time so that single-GPU users of the library do not need it installed.
+// NCCL is bound at run time (dlopen) so that single-GPU users of the library need neither libnccl nor nccl.h: the few
+// types of its C API the slab transport touches are declared here (stable across NCCL 2.x).
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclChar = 0, ncclInt32 = 2 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+}
+
 struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -86,6 +96,7 @@ struct gp_multi {
     cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
     cudaEvent_t ev_copied = nullptr;   // local transport: this world has copied what it needs from its neighbours
     bool verify = true;
+    unsigned long long timeout_ns = 30ull * 1000000000ull;  // peer-to-peer waits (GP_PEER_TIMEOUT_MS)
 };
 
 static void gp_multi_destroy(gp_multi* m) {
@@ -121,7 +132,8 @@ static void gp_multi_begin_step(gp_multi* m) {
     if (!m->p2p || m->step_id <= 2) return;
     // the buffer of parity step_id&1 was last filled for step_id-2: the neighbours must have consumed that
     k_wait_flags<<<1, 2, 0, w->st>>>(m->peer_arena[0] ? arena_flag(m->arena, 4) : nullptr,
-                                     m->peer_arena[1] ? arena_flag(m->arena, 5) : nullptr, m->step_id - 2, w->ctl);
+                                     m->peer_arena[1] ? arena_flag(m->arena, 5) : nullptr, m->step_id - 2, w->ctl,
+                                     m->timeout_ns);
     w->launches++;
 }
 static void gp_multi_seal(gp_multi* m) {
@@ -141,7 +153,8 @@ static void gp_multi_before_append(gp_multi* m) {
     if (!m->p2p) return;
     const uint32_t par = m->step_id & 1u;
     k_wait_flags<<<1, 2, 0, w->st>>>(m->peer_arena[0] ? arena_flag(m->arena, 0 * 2 + par) : nullptr,
-                                     m->peer_arena[1] ? arena_flag(m->arena, 1 * 2 + par) : nullptr, m->step_id, w->ctl);
+                                     m->peer_arena[1] ? arena_flag(m->arena, 1 * 2 + par) : nullptr, m->step_id, w->ctl,
+                                     m->timeout_ns);
     w->launches++;
 }
 static void gp_multi_after_append(gp_multi* m) {
@@ -199,6 +212,7 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
     m->cfg = c;
     m->local = local;
     m->verify = !(c.flags & GP_SLAB_NO_VERIFY);
+    if (const char* e = getenv("GP_PEER_TIMEOUT_MS")) m->timeout_ns = (unsigned long long)std::max(1.0, atof(e)) * 1000000ull;
     hc.x_lo = c.x_lo, hc.x_hi = c.x_hi, hc.halo = c.halo;
     hc.has_left = c.rank > 0, hc.has_right = c.rank + 1 < c.nranks;
     hc.cap = w->cap;

@@ -75,14 +75,15 @@ __device__ __forceinline__ bool resolve_pair(BodyRW& a, BodyRW& b, V3 amin, V3 a
     return moved;
 }
 
-// Frontier appends are staged per CTA in shared memory and leave with ONE global atomic per round: the
+// Frontier appends are staged per CTA in shared memory and leave with ONE global atomic per flush: the
 // next-frontier counter is a single address, and same-address atomics serialise in L2.  A push never waits: when the
-// stage is full it goes straight to the global list.  The CTA synchronises once per ROUND (stage_flush), never per
-// batch of pairs, so the warps of a CTA drift apart and hide each other's dependent loads.
-constexpr uint32_t FB_CAP = 6144;
+// stage is full it goes straight to the global list.  Escapees (bodies that left their margin) are staged the same way.
+constexpr uint32_t FB_CAP = 12288;
+constexpr uint32_t EB_CAP = 1024;
 struct FrontierStage {
     uint32_t buf[FB_CAP];
-    uint32_t cnt, base;
+    uint32_t ebuf[EB_CAP];
+    uint32_t cnt, base, ecnt, ebase;
 };
 __device__ __forceinline__ void stage_push(FrontierStage& fs, uint32_t q, uint32_t* frontier, uint32_t* counter) {
     const uint32_t s = atomicAdd(&fs.cnt, 1u);
@@ -91,35 +92,44 @@ __device__ __forceinline__ void stage_push(FrontierStage& fs, uint32_t q, uint32
     else
         __stcg(&frontier[atomicAdd(counter, 1u)], q);
 }
+__device__ __forceinline__ void escapee_store(uint32_t* escapees, uint32_t esc_cap, Ctl* ctl, uint32_t slot, uint32_t ix) {
+    if (slot < esc_cap)
+        __stcg(&escapees[slot], ix);
+    else
+        atomicOr(&ctl->step_flags, SF_ESCAPEE_OVERFLOW);
+}
 // called by ALL threads of the CTA (contains barriers)
-__device__ __forceinline__ void stage_flush(FrontierStage& fs, uint32_t* frontier, uint32_t* counter) {
+__device__ __forceinline__ void stage_flush(FrontierStage& fs, uint32_t* frontier, uint32_t* counter, uint32_t* escapees,
+                                            uint32_t esc_cap, Ctl* ctl) {
     __syncthreads();
-    const uint32_t c = min(fs.cnt, FB_CAP);
+    const uint32_t c = min(fs.cnt, FB_CAP), ec = min(fs.ecnt, EB_CAP);
     if (threadIdx.x == 0 && c) fs.base = atomicAdd(counter, c);
+    if (threadIdx.x == 32 && ec) fs.ebase = atomicAdd(&ctl->n_escapees, ec);
     __syncthreads();
-    const uint32_t base = fs.base;
+    const uint32_t base = fs.base, ebase = fs.ebase;
     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) __stcg(&frontier[base + i], fs.buf[i]);
+    for (uint32_t i = threadIdx.x; i < ec; i += blockDim.x) escapee_store(escapees, esc_cap, ctl, ebase + i, fs.ebuf[i]);
     __syncthreads();
-    if (threadIdx.x == 0) fs.cnt = 0;
+    if (threadIdx.x == 0) fs.cnt = 0, fs.ecnt = 0;
     __syncthreads();
 }
 
 // Displacement tracking.  dmax[x] = largest per-axis displacement body x had at any time in the current sweep (its
 // swept AABB lies inside snapshot (+) dmax); reach[x] = the same over the earlier sweeps of this step (committed by
-// k_restore).  moved_bits marks bodies with dmax or reach != 0 (k_verify_watch looks there first).
-// A body whose AABB leaves its snapshot inflated by mu*extent is an ESCAPEE (esc_bits, escapees[]): the candidate
-// set built from the snapshot may miss pairs it reaches; k_requery looks for them.
-// Only one thread touches a dynamic body per round, so plain (L2) accesses suffice for dmax.
+// the repair).  moved_bits marks bodies with dmax or reach != 0 (the watch-list verification looks there first).
+// A body whose AABB leaves its snapshot inflated by its margin is an ESCAPEE (esc_bits, escapees[]): the candidate
+// set built from the snapshot may miss pairs it reaches; the requery phase looks for them.
+// Only one thread touches a dynamic body per round, so plain (L2) accesses suffice for dmax.  `old` = dmax[ix] as the
+// caller loaded it together with the body (one memory round trip for everything a contact needs).
 constexpr float ESCAPE_FRAC = 0.98f;
-__device__ __forceinline__ void track_move(const BodyRW& x, uint32_t ix, float4 lo_snap, float* dmax,
+__device__ __forceinline__ void track_move(const BodyRW& x, uint32_t ix, float4 lo_snap, float old, float* dmax,
                                            uint32_t* moved_bits, uint32_t* esc_bits, uint32_t* escapees,
-                                           uint32_t esc_cap, Ctl* ctl, float& maxrel, float& maxabs) {
+                                           uint32_t esc_cap, Ctl* ctl, FrontierStage* fs, float& maxrel, float& maxabs) {
     const V3 lo_now = x.omin + x.pos;
     const float d = fmaxf(fabsf(lo_now.x - lo_snap.x), fmaxf(fabsf(lo_now.y - lo_snap.y), fabsf(lo_now.z - lo_snap.z)));
     if (d == 0.0f) return;
     const float e = fmaxf(x.omax.x - x.omin.x, fmaxf(x.omax.y - x.omin.y, x.omax.z - x.omin.z));
     maxrel = fmaxf(maxrel, d / e);
-    const float old = __ldcg(&dmax[ix]);
     const uint32_t bit = 1u << (ix & 31u);
     if (!(d <= old)) __stcg(&dmax[ix], d);
     if (old == 0.0f) atomicOr(&moved_bits[ix >> 5], bit);
@@ -128,16 +138,19 @@ __device__ __forceinline__ void track_move(const BodyRW& x, uint32_t ix, float4 
     if (!(d <= ESCAPE_FRAC * box_margin(lo_snap))) {
         const uint32_t prev = atomicOr(&esc_bits[ix >> 5], bit);
         if (!(prev & bit)) {  // first escape of this body in this step
-            const uint32_t s = atomicAdd(&ctl->n_escapees, 1u);
-            if (s < esc_cap)
-                escapees[s] = ix;
+            const uint32_t s = fs ? atomicAdd(&fs->ecnt, 1u) : EB_CAP;
+            if (s < EB_CAP)
+                fs->ebuf[s] = ix;
             else
-                atomicOr(&ctl->step_flags, SF_ESCAPEE_OVERFLOW);
+                escapee_store(escapees, esc_cap, ctl, atomicAdd(&ctl->n_escapees, 1u), ix);
         }
         maxabs = fmaxf(maxabs, d);
     }
 }
 
-constexpr int COOP_THREADS = 768;  // the cooperative kernel: ONE large CTA per SM (a grid barrier costs per CTA)
+#ifndef GP_COOP_THREADS
+#define GP_COOP_THREADS 768
+#endif
+constexpr int COOP_THREADS = GP_COOP_THREADS;  // the cooperative kernel: ONE large CTA per SM (a grid barrier costs per CTA)
 
 }  // namespace gp

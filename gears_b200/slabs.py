@@ -22,10 +22,42 @@ from .world import GpError, PhysicsWorld
 INF = float("inf")
 
 
+def aabb_offsets_x(scene: dict) -> tuple[np.ndarray, np.ndarray]:
+    """(min, max) x offset of every body's world AABB from its position: the x component of the component-wise min / max
+    over the 8 corners rot * (corner * scale), with the operation order of the upload kernel (k_pack / corner_offsets,
+    reference physics.rs:93-119), in float32 -- so the host assigns a rotated or scaled body to the slab the device's
+    ownership test (k_keys<true>) will agree with."""
+    f = np.float32
+    bmin, bmax = scene["box_min"].astype(f), scene["box_max"].astype(f)
+    n = bmin.shape[0]
+    rot, sc = scene.get("rot"), scene.get("scale")
+    if rot is None and sc is None:
+        return bmin[:, 0].copy(), bmax[:, 0].copy()
+    q = np.tile(np.array([0, 0, 0, 1], f), (n, 1)) if rot is None else rot.astype(f)
+    sc = np.ones((n, 3), f) if sc is None else sc.astype(f)
+    qv, qs = q[:, :3], q[:, 3:4]
+
+    def cross(a, b):
+        return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                         a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], axis=1).astype(f)
+    lo = hi = None
+    for i in range(8):
+        c = np.stack([bmax[:, 0] if i & 1 else bmin[:, 0], bmax[:, 1] if i & 2 else bmin[:, 1],
+                      bmax[:, 2] if i & 4 else bmin[:, 2]], axis=1)
+        v = (c * sc).astype(f)
+        t = (cross(qv, v) + v * qs).astype(f)
+        r = (cross(qv, t) * f(2.0) + v).astype(f)
+        lo = r[:, 0] if lo is None else np.minimum(lo, r[:, 0])
+        hi = r[:, 0] if hi is None else np.maximum(hi, r[:, 0])
+    return lo.astype(f), hi.astype(f)
+
+
 def centres_x(scene: dict) -> np.ndarray:
-    """AABB centre x exactly as the kernels compute it for axis-aligned, unscaled boxes."""
-    lo = scene["box_min"][:, 0] + scene["pos"][:, 0]
-    hi = scene["box_max"][:, 0] + scene["pos"][:, 0]
+    """AABB centre x as the kernels compute it: ((off_min + pos) + (off_max + pos)) * 0.5 in float32, rotation and
+    scale included."""
+    olo, ohi = aabb_offsets_x(scene)
+    lo = (olo + scene["pos"][:, 0]).astype(np.float32)
+    hi = (ohi + scene["pos"][:, 0]).astype(np.float32)
     return ((lo + hi) * np.float32(0.5)).astype(np.float32)
 
 

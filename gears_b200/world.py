@@ -69,6 +69,9 @@ class PhysicsWorld:
         if getattr(self, "_h", None):
             self._lib.gp_destroy(self._h)
             self._h = None
+            for p in getattr(self, "_pinned", []):
+                self._lib.gp_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -146,6 +149,33 @@ class PhysicsWorld:
 
     def kernel_launches(self) -> int:
         return int(self._lib.gp_kernel_launches(self._h))
+
+    # -- pipelined frames (gp_frame_submit / gp_frame_wait) --
+    def host_alloc(self, shape, dtype=np.float32) -> np.ndarray:
+        """A numpy array over PINNED host memory (gp_host_alloc); freed when the world closes."""
+        count = int(np.prod(shape))
+        nbytes = count * np.dtype(dtype).itemsize
+        p = self._lib.gp_host_alloc(max(1, nbytes))
+        if not p:
+            raise MemoryError("gp_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_char * max(1, nbytes)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def frame_submit(self, pos, vel, acc, dt: float, state8_out, damp=None):
+        """Enqueue one frame: H2D of pos / vel / acc (n x 3 each, upload order) -> state refresh + step -> D2H of
+        (pos.xyz, vel.xyz, 0, 0) rows into state8_out (n x 8).  Returns at once; buffers should be pinned."""
+        for a in (pos, vel, acc, state8_out):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        d = None if damp is None else _f32(damp)
+        self._check(self._lib.gp_frame_submit(self._h, _ptr(pos), _ptr(vel), _ptr(acc), C.c_float(dt), _ptr(d),
+                                              _ptr(state8_out)))
+
+    def frame_wait(self, max_in_flight: int = 0) -> dict:
+        st = capi.GpStepStats()
+        self._check(self._lib.gp_frame_wait(self._h, max_in_flight, C.byref(st)))
+        return st.as_dict()
 
     # -- results --
     def download(self, pos_out=None, vel_out=None):

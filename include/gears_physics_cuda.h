@@ -48,7 +48,10 @@ typedef enum gp_status {
     GP_ERR_MARGIN = -6,      /* a body moved further than margin_max during contact resolution          */
                              /* (step result not guaranteed exact; raise margin_max)                    */
     GP_ERR_NCCL = -7,
-    GP_ERR_STATE = -8        /* call order violation (e.g. step before upload)                          */
+    GP_ERR_STATE = -8,       /* call order violation (e.g. step before upload)                          */
+    GP_ERR_PEER_TIMEOUT = -9 /* slab worlds: a neighbour rank never arrived at the exchange (GP_PEER_TIMEOUT_MS,
+                                default 30 s).  Records that were migrating are lost: the world refuses further
+                                steps until gp_upload + gp_comm_init are called again                        */
 } gp_status;
 
 /* gp_config.flags */
@@ -179,6 +182,25 @@ typedef struct gp_kernel_times {
 } gp_kernel_times;
 gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
 
+/* ---- pipelined frames (async H2D / D2H overlapped with the step) ----
+ * For hosts that own the state (every frame the ECS side hands over pos / vel / acc of ALL bodies, in upload order,
+ * and wants pos / vel back -- SURVEY.md section 3.3: external systems may have written any of them):
+ *   gp_frame_submit  enqueues  H2D of the three arrays (copy stream)  ->  whole-world state refresh + one step
+ *                    (step stream)  ->  read-back + D2H into state8_out (download stream)  and returns at once.
+ *                    Two frames may be in flight: frame t+1 uploads while frame t computes and frame t-1 downloads
+ *                    (PCIe is full duplex), so a frame costs max(H2D, kernels, D2H) instead of their sum.
+ *                    All host buffers must be pinned (gp_host_alloc) and must stay untouched until the frame has
+ *                    been waited for.  A frame REPLACES the mutable state: its result does not depend on the previous
+ *                    frame's result, only on what the host passes in (and on shapes / masses set by gp_upload /
+ *                    gp_update_shape).
+ *   state8_out       n x 8 floats, row = upload index: pos.xyz, vel.xyz, 0, 0 (one 32 B sector per body).
+ *   gp_frame_wait    blocks until at most max_in_flight submitted frames are unfinished (0 = all; then it also
+ *                    reports latched step failures like gp_sync and fills stats).
+ * Not available on a slab world. */
+gp_status gp_frame_submit(gp_world* w, const float* pos3, const float* vel3, const float* acc3, float dt,
+                          const float damp3[3], float* state8_out);
+gp_status gp_frame_wait(gp_world* w, uint32_t max_in_flight, gp_step_stats* stats);
+
 /* ---- multi-GPU: spatial slabs along x, one gp_world per GPU ----
  * The reference is a single process (no collectives of any kind); this decomposition is new.
  * A rank owns the bodies whose AABB centre x lies in [x_lo, x_hi) (use -INFINITY / +INFINITY at the two ends).
@@ -186,7 +208,9 @@ gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
  * such as a floor are uploaded on EVERY rank), then attach the worlds:
  *   - one process per GPU:   gp_comm_unique_id on rank 0, broadcast it, gp_comm_init on every rank (collective);
  *                            then gp_step_async / gp_sync as usual: every step exchanges migrating bodies and halo
- *                            copies with the two neighbours by ncclSend/ncclRecv on the step stream;
+ *                            copies with the two neighbours on the step stream -- K1 writes the records straight
+ *                            into the neighbour's buffer over NVLink (CUDA IPC peer memory, release/acquire step
+ *                            flags); ncclSend/ncclRecv when peer access is missing or GP_SLAB_TRANSPORT=nccl;
  *   - one process, n worlds: gp_comm_init_local, then gp_step_group (peer copies instead of NCCL; the worlds may
  *                            even share a device, which is how the slab logic is tested on one GPU).
  * Per-index calls (gp_set_state, gp_update_dirty, gp_update_shape, gp_download) are not available on a slab world;

@@ -20,19 +20,19 @@ fn main() {
         ])
         .arg(&so)
         .arg(csrc.join("gp_api.cu"))
-        .arg("-ldl")
+        .arg("-ldl") // NCCL is bound with dlopen at run time (gp_multi_impl.cuh): single-GPU users need no NCCL
         .status()
         .expect("nvcc not found: gears-physics-cuda has no CPU fallback");
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=gears_physics_cuda");
     println!("cargo:rustc-link-lib=dylib=cudart");
-    for f in [
-        "gp_api.cu", "gp_kernels.cuh", "gp_common.cuh", "gp_mirror_kernels.cuh", "gp_cellsort_kernels.cuh",
-        "gp_pairfind_kernels.cuh", "gp_chain_kernels.cuh", "gp_sweep_kernels.cuh", "gp_repair_kernels.cuh",
-        "gp_slab_kernels.cuh", "gp_next_kernels.cuh", "gp_multi.cuh", "gp_multi_impl.cuh", "radix_sort.cuh", "scan.cuh",
-    ] {
-        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
+    // every source under csrc/ (gp_api.cu includes all the .cuh files)
+    for entry in std::fs::read_dir(&csrc).expect("gears_b200/csrc missing") {
+        let path = entry.unwrap().path();
+        if matches!(path.extension().and_then(|e| e.to_str()), Some("cu") | Some("cuh")) {
+            println!("cargo:rerun-if-changed={}", path.display());
+        }
     }
     println!("cargo:rerun-if-changed={}", repo.join("include/gears_physics_cuda.h").display());
 }

@@ -24,6 +24,7 @@ pub const GP_ERR_PAIR_OVERFLOW: gp_status = -5;
 pub const GP_ERR_MARGIN: gp_status = -6;
 pub const GP_ERR_NCCL: gp_status = -7;
 pub const GP_ERR_STATE: gp_status = -8;
+pub const GP_ERR_PEER_TIMEOUT: gp_status = -9;
 
 pub const GP_FLAG_RECORD_PAIRS: u32 = 0x1;
 pub const GP_FLAG_NO_RETRY: u32 = 0x2;
@@ -151,6 +152,13 @@ unsafe extern "C" {
         w: *mut gp_world, k: u32, idx: *const u32, cell_size: f32, origin: *const i32, dims: *const u32,
         bitmap: *mut u32, bounds_out: *mut i32,
     ) -> gp_status;
+
+    // pipelined frames: async H2D / step / D2H, two frames in flight (pinned host buffers)
+    pub fn gp_frame_submit(
+        w: *mut gp_world, pos3: *const f32, vel3: *const f32, acc3: *const f32, dt: f32, damp3: *const f32,
+        state8_out: *mut f32,
+    ) -> gp_status;
+    pub fn gp_frame_wait(w: *mut gp_world, max_in_flight: u32, stats: *mut gp_step_stats) -> gp_status;
 
     // test hooks (not part of the drop-in surface)
     pub fn gp_test_radix_sort(device: i32, n: u32, key_bits: u32, keys_inout: *mut u32, vals_inout: *mut u32)

@@ -25,7 +25,8 @@ pub struct PhysicsCudaError(pub String);
 /// Owns one `gp_world`.  `Send` (every entry point sets the device), not re-entrant: keep it behind a `Mutex`.
 pub struct CudaPhysics {
     handle: *mut sys::gp_world,
-    /// entities of the last upload, in iteration order (= `rank`)
+    /// entities that were actually gathered at the last step, in iteration order (= `rank`); an entity without a
+    /// `Pos3` is skipped exactly like the reference skips its pairs (update_systems.rs:421-432)
     entities: Vec<Entity>,
     staging: Staging,
 }
@@ -55,6 +56,7 @@ impl CudaPhysics {
         let s = &mut self.staging;
         for v in [&mut s.pos, &mut s.scale, &mut s.vel, &mut s.acc, &mut s.bmin, &mut s.bmax] { v.clear(); v.reserve(3 * n); }
         s.rot.clear(); s.mass.clear(); s.rest.clear(); s.stat.clear(); s.ids.clear();
+        self.entities.clear();
         // gather: the same per-entity query the reference issues (update_systems.rs:381-400, :414-475)
         for &e in entities {
             let q = ComponentQuery::new()
@@ -75,6 +77,7 @@ impl CudaPhysics {
             s.bmin.extend_from_slice(&[rb.collision_box.min.x, rb.collision_box.min.y, rb.collision_box.min.z]);
             s.bmax.extend_from_slice(&[rb.collision_box.max.x, rb.collision_box.max.y, rb.collision_box.max.z]);
             s.mass.push(rb.mass); s.rest.push(rb.restitution); s.stat.push(rb.is_static as u8); s.ids.push(*e);
+            self.entities.push(e); // body i of the upload == self.entities[i]: skipped entities leave no hole
         }
         let n = s.ids.len() as u32;
         // Full mirror every frame: any user system may have written any component.  Large worlds
@@ -92,8 +95,10 @@ impl CudaPhysics {
         self.check(st)?;
         let st = unsafe { sys::gp_download(self.handle, s.pos.as_mut_ptr(), s.vel.as_mut_ptr()) };
         self.check(st)?;
-        // scatter back through the same write locks the reference takes
-        for (i, &e) in entities.iter().enumerate().take(n as usize) {
+        // scatter back through the same write locks the reference takes; iterate the GATHERED entities, not the
+        // caller's list: after a skipped entity the two no longer line up
+        debug_assert_eq!(self.entities.len(), n as usize);
+        for (i, &e) in self.entities.iter().enumerate() {
             let q = ComponentQuery::new().write::<RigidBody<AABBCollisionBox>>(vec![e]).write::<Pos3>(vec![e]);
             let Some(res) = world.acquire_query(q) else { continue };
             if let (Some(rb), Some(p3)) = (res.get::<RigidBody<AABBCollisionBox>>(e), res.get::<Pos3>(e)) {
@@ -103,8 +108,6 @@ impl CudaPhysics {
                 rb.velocity = cgmath::Vector3::new(s.vel[3 * i], s.vel[3 * i + 1], s.vel[3 * i + 2]);
             }
         }
-        self.entities.clear();
-        self.entities.extend_from_slice(entities);
         Ok(())
     }
 

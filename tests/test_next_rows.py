@@ -122,3 +122,56 @@ def test_obstacle_grid_matches_oracle(oracle):
     assert np.array_equal(grid, ref)
     assert np.array_equal(bounds, np.concatenate([blo, bhi]).astype(np.int32))
     assert grid_all.sum() >= grid.sum() and np.all(grid_all[grid])
+
+
+def world(**kw):
+    from gears_b200.world import PhysicsWorld
+    return PhysicsWorld(**kw)
+
+
+def assert_same_bits(a, b, what):
+    a = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, np.float32).view(np.uint32)
+    assert np.array_equal(a, b), f"{what}: {int((a != b).sum())} words differ"
+
+
+@pytest.mark.gpu
+def test_pipelined_frames_equal_set_state_step_download(oracle):
+    """gp_frame_submit / gp_frame_wait (N2: async H2D / D2H overlapped with the step): four frames in flight back to
+    back give the very bits of gp_set_state + gp_step + gp_download called frame by frame, and of the oracle."""
+    s = scenes.uniform(30_000, L=70.0, seed=61, rank_seed=62)
+    n = len(s["mass"])
+    rng = np.random.default_rng(5)
+    frames = []
+    with world() as w1:
+        w1.upload(s)
+        pos, vel = s["pos"].copy(), s["vel"].copy()
+        for t in range(4):
+            acc = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(4.0) * (t % 2)
+            w1.set_state(pos, vel, acc)       # what the host hands over for this frame
+            w1.step(DT)
+            p1, v1 = w1.download()
+            r = oracle.step(dict(s, pos=pos, vel=vel, acc=acc), DT, 1, mode=1, want_snapshot=False)
+            assert_same_bits(p1, r["pos"], f"frame {t} pos (per-call path vs oracle)")
+            frames.append((pos, vel, acc, p1, v1))
+            pos, vel = p1.copy(), v1.copy()
+    with world() as w2:
+        w2.upload(s)
+        w2.step(DT)  # the frame path must not depend on what state the world happens to be in
+        ins, outs = [], []
+        for (pos, vel, acc, _, _) in frames:
+            hp, hv, ha = (w2.host_alloc((n, 3)) for _ in range(3))
+            hp[:], hv[:], ha[:] = pos, vel, acc
+            o = w2.host_alloc((n, 8))
+            o[:] = np.float32(7.0)
+            w2.frame_submit(hp, hv, ha, DT, o)
+            ins.append((hp, hv, ha)), outs.append(o)
+        st = w2.frame_wait(0)
+        assert st["steps_inexact"] == 0
+        for t, (o, (_, _, _, p1, v1)) in enumerate(zip(outs, frames)):
+            assert_same_bits(o[:, 0:3], p1, f"frame {t} pos")
+            assert_same_bits(o[:, 3:6], v1, f"frame {t} vel")
+            assert not o[:, 6:8].any()
+        # and the world is left in the state of the last frame for the per-call API
+        p2, v2 = w2.download()
+        assert_same_bits(p2, frames[-1][3], "state after the last frame")

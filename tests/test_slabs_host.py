@@ -88,3 +88,23 @@ def test_world_size_2_gloo_rendezvous(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_slab_ownership_uses_the_rotated_scaled_aabb_centre():
+    """centres_x must give the very bits of the world AABB centre the device's ownership test computes
+    (k_pack corner offsets + k_keys), rotation and scale included: here checked against the oracle's world AABB
+    (physics.rs:84-135)."""
+    from oracle import pyoracle
+    s = scenes.uniform(300, L=12.0, seed=5, rank_seed=6)
+    m = len(s["mass"])
+    rng = np.random.default_rng(11)
+    q = rng.normal(size=(m, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    s["rot"] = q
+    s["scale"] = (0.5 + rng.random((m, 3))).astype(np.float32)
+    s["box_min"][:] = -(0.2 + rng.random((m, 3))).astype(np.float32)
+    cx = slabs.centres_x(s)
+    for i in range(m):
+        lo, hi = pyoracle.world_aabb(s["box_min"][i], s["box_max"][i], s["pos"][i], s["rot"][i], s["scale"][i])
+        c = np.float32((lo[0] + hi[0]) * np.float32(0.5))
+        assert c.view(np.uint32) == cx[i].view(np.uint32), i
