@@ -39,7 +39,9 @@ GROUP_MAIN_KERNEL = {"keys": "k_keys", "cell_scan": "sc_scan", "scatter": "k_sca
 def ncu_traffic(workload: str, group: str):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        k = t["workloads"][workload]["kernels"][GROUP_MAIN_KERNEL[group]]
+        ks = t["workloads"][workload]["kernels"]
+        name = GROUP_MAIN_KERNEL[group]
+        k = ks.get(name) or next(v for n, v in ks.items() if n.split("<")[0] == name)  # (k_keys<0>: template instance)
         return float(k["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -176,6 +178,10 @@ def slab_parity(w, full_scene, wkw_single, dist, torch, local_rank: int, steps: 
             "n_flagged_cumulative": int(flagged.sum()), "max_rel_err": float(e.item()),
             "against": "a single-GPU world of the whole scene stepped on every rank's own GPU (bit-exact vs the oracle "
                        "in tests/)"}
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
 
 
 def run_ours(args) -> dict:
@@ -316,29 +322,68 @@ def run_ours(args) -> dict:
         pass  # (profiling runs: device-resident numbers only)
     elif world_size == 1:
         nb = 3 * n_local * 4
-
-        def pinned():
-            p = lib.gp_host_alloc(nb)
-            return p, np.ctypeslib.as_array((C.c_float * (3 * n_local)).from_address(p)).reshape(n_local, 3)
-        (pp, hpos), (pv, hvel), (pa, hacc) = pinned(), pinned(), pinned()
+        hpos, hvel, hacc = (w.host_alloc((n_local, 3)) for _ in range(3))       # pinned
+        outs = [w.host_alloc((n_local, 6)) for _ in range(2)]                     # pinned, alternating
         w.download(hpos, hvel)
         hacc[:] = scene["acc"]
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        for _ in range(2):  # warm-up of the e2e path
-            w._check(lib.gp_set_state(w._h, pp, pv, pa)); w.step(DT); w.download(hpos, hvel)
+        e2e_steps = max(1, args.e2e_steps)
+        # (1) the pipelined frame API: every step uploads pos / vel / acc of ALL bodies from pinned host memory and
+        # downloads their pos / vel; frame t+1 uploads while frame t computes and frame t-1 downloads
+        for i in range(3):  # warm-up (allocates the staging buffers, builds the id-ordered constants)
+            w.frame_submit(hpos, hvel, hacc, DT, outs[i & 1])
+        w.frame_wait(0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            w._check(lib.gp_set_state(w._h, pp, pv, pa))   # H2D: pos, vel, acc (what external systems may have written)
-            w.step(DT)                                      # synchronous step with retry
-            w.download(hpos, hvel)                          # D2H: pos, vel (what the ECS write-back needs)
+        for i in range(e2e_steps):
+            w.frame_submit(hpos, hvel, hacc, DT, outs[i & 1])
+            w.frame_wait(1)            # at most one frame stays in flight: results of frame i-1 are on the host now
+        st_f = w.frame_wait(0)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        # (2) the dependent per-call path (each step's input is the previous step's downloaded result): no overlap
+        dep_steps = max(1, min(3, e2e_steps))
+        w._check(lib.gp_set_state(w._h, _hp(hpos), _hp(hvel), _hp(hacc))); w.step(DT); w.download(hpos, hvel)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        for _ in range(dep_steps):
+            w._check(lib.gp_set_state(w._h, _hp(hpos), _hp(hvel), _hp(hacc)))
+            w.step(DT)
+            w.download(hpos, hvel)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        # (3) a host that tracks a dirty set: per step, vel + acc of a fraction of the bodies go up through
+        # gp_update_dirty from pinned memory (asynchronous), one step follows; the state stays on the device
+        dirty = []
+        rng = np.random.default_rng(12345)
+        for frac in (0.01, 0.10):
+            k = max(1, int(n_local * frac))
+            hidx = w.host_alloc((k,), np.uint32)
+            hv, ha = w.host_alloc((k, 3)), w.host_alloc((k, 3))
+            hidx[:] = np.sort(rng.choice(n_local, size=k, replace=False)).astype(np.uint32)
+            hv[:] = hvel[hidx]
+            ha[:] = 0.0
+            w.update_dirty(hidx, vel=hv, acc=ha); w.step_async(DT, 1); w.sync()
+            torch.cuda.synchronize()
+            td0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                w.update_dirty(hidx, vel=hv, acc=ha)
+                w.step_async(DT, 1)
+            st_d = w.sync()
+            torch.cuda.synchronize()
+            td1 = time.perf_counter()
+            dirty.append({"dirty_fraction": frac, "value": n_local * e2e_steps / (td1 - td0), "unit": "body-steps/s",
+                          "ms_per_step": (td1 - td0) * 1e3 / e2e_steps, "h2d_bytes_per_step": 28 * k,
+                          "inexact_steps": st_d["steps_inexact"]})
         e2e = {"value": n_local * e2e_steps / (t1 - t0), "unit": "body-steps/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": 2 * nb,
-               "path": "gp_set_state + gp_step + gp_download on pinned host buffers"}
-        for p in (pp, pv, pa):
-            lib.gp_host_free(p)
+               "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": 6 * 4 * n_local, "dirty_set": dirty,
+               "ms_per_step": (t1 - t0) * 1e3 / e2e_steps, "inexact_steps": st_f["steps_inexact"],
+               "path": "gp_frame_submit + gp_frame_wait(1) per step on pinned host buffers: H2D (pos, vel, acc of all "
+                       "bodies) -> state refresh + step -> D2H (pos.xyz vel.xyz rows) on three streams, two "
+                       "frames in flight; a frame's inputs come from the host, not from the previous frame's result",
+               "dependent": {"value": n_local * dep_steps / (t3 - t2), "ms_per_step": (t3 - t2) * 1e3 / dep_steps,
+                             "steps": dep_steps, "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": 2 * nb,
+                             "path": "gp_set_state + gp_step + gp_download, each step fed with the previous step's "
+                                     "downloaded result (nothing can overlap)"}}
     else:
         # slab worlds keep their state on the device between steps; the host-visible result is gp_download_owned
         nown = 0
@@ -427,13 +472,13 @@ def reference_sweep(gen: dict, steps: int, warmup: int, sizes=REF_SIZES, budget_
         cur = dict(sc)
         w = min(warmup, 1 if n_s >= 16_000 else warmup)
         if w:
-            r = pyoracle.step(cur, DT, w, mode=0, threads=threads, want_snapshot=False)
+            r = pyoracle.step(cur, DT, w, mode=0, threads=threads, want_snapshot=False, pair_cap=1024, want_pairs=False)
             cur["pos"], cur["vel"] = r["pos"], r["vel"]
         # steps at this size: all K for the small sizes, fewer for the large ones so the whole sweep stays bounded
         est = 1.6e-10 * n * n + 2e-8 * n + 2e-5          # seconds per step (measured on this image's cores)
         k = int(max(1, min(steps, (budget_s / len(sizes)) / est)))
         t0 = time.perf_counter()
-        pyoracle.step(cur, DT, k, mode=0, threads=threads, want_snapshot=False)
+        pyoracle.step(cur, DT, k, mode=0, threads=threads, want_snapshot=False, pair_cap=1024, want_pairs=False)
         dt = (time.perf_counter() - t0) / k
         pts.append({"n": n, "steps": k, "ms_per_step": dt * 1e3, "body_steps_per_s": n / dt})
         if time.perf_counter() - t_begin > 2.0 * budget_s:
@@ -479,7 +524,7 @@ def cpu_baseline_grid(gen, scene=None, steps: int = 1) -> dict:
         n = int(sc["pos"].shape[0])
         threads = pyoracle.max_threads()
         t0 = time.perf_counter()
-        pyoracle.step(sc, DT, steps, mode=1, threads=threads, want_snapshot=False, pair_cap=1 << 16)
+        pyoracle.step(sc, DT, steps, mode=1, threads=threads, want_snapshot=False, pair_cap=1024, want_pairs=False)
         dt = time.perf_counter() - t0
         return {"value": n * steps / dt, "unit": "body-steps/s", "cores": 1, "kind": "port",
                 "sample": f"{steps} step(s) of the FULL workload ({n} bodies) with the oracle's uniform-grid sweep: an "
@@ -525,7 +570,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uniform_16M", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-grid", action="store_true", help="skip the full-N grid-oracle CPU line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--parity-steps", type=int, default=8,

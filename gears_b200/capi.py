@@ -72,7 +72,7 @@ SYMBOLS = [
     "gp_update_shape", "gp_step", "gp_step_async", "gp_sync", "gp_download", "gp_pairs", "gp_damping_factors",
     "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_kernel_times_read", "gp_comm_unique_id", "gp_comm_init",
     "gp_comm_init_local", "gp_step_group", "gp_owned_count", "gp_download_owned", "gp_instances", "gp_raycast",
-    "gp_obstacle_grid", "gp_frame_submit", "gp_frame_wait", "gp_test_radix_sort", "gp_test_radix_sort64",
+    "gp_obstacle_grid", "gp_cap_velocity", "gp_frame_submit", "gp_frame_wait", "gp_test_radix_sort", "gp_test_radix_sort64",
     "gp_test_exclusive_scan",
 ]
 
@@ -143,6 +143,8 @@ def lib():
     L.gp_raycast.restype = C.c_int32
     L.gp_obstacle_grid.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_obstacle_grid.restype = C.c_int32
+    L.gp_cap_velocity.argtypes = [vp, C.c_uint32, C.c_void_p]
+    L.gp_cap_velocity.restype = C.c_int32
     L.gp_frame_submit.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
     L.gp_frame_submit.restype = C.c_int32
     L.gp_frame_wait.argtypes = [vp, C.c_uint32, C.POINTER(GpStepStats)]

@@ -46,6 +46,7 @@ struct gp_world {
     uint32_t* entity_dev = nullptr;  // caller's entity ids as uploaded (become the body ids of a slab world)
     bool have_entity = false;
     bool slot_valid = false;
+    bool track_slots = false;  // K3 keeps slot_of current (set by the first per-index update: the host tracks a dirty set)
     // broad phase
     float4* sbox = nullptr;       // world AABBs of the current step in cell order (lo|tag, hi|rank)
     uint32_t *key = nullptr, *lrank = nullptr;  // per input slot: cell key, arrival rank within the cell
@@ -87,7 +88,8 @@ struct gp_world {
     float4* home = nullptr;
     bool home_valid = false;
     float* fin[2] = {nullptr, nullptr};      // 3 x (n x 3) floats: pos, vel, acc
-    float4* fout[2] = {nullptr, nullptr};    // n x 8 floats
+    float4* fout8 = nullptr;                 // n x 8 floats: whole-sector rows the scattered read-back writes
+    float* fout[2] = {nullptr, nullptr};     // n x 6 floats: what goes to the host
     uint32_t frame_cap = 0;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr},
                 ev_d2h[2] = {nullptr, nullptr};
@@ -213,6 +215,7 @@ static void free_frames(gp_world* w) {
     for (int b = 0; b < 2; ++b) {
         if (w->fin[b]) cudaFree(w->fin[b]), w->fin[b] = nullptr;
         if (w->fout[b]) cudaFree(w->fout[b]), w->fout[b] = nullptr;
+        if (b == 0 && w->fout8) cudaFree(w->fout8), w->fout8 = nullptr;
         for (cudaEvent_t* e : {&w->ev_h2d[b], &w->ev_in_free[b], &w->ev_unpacked[b], &w->ev_d2h[b]})
             if (*e) cudaEventDestroy(*e), *e = nullptr;
     }
@@ -651,7 +654,19 @@ extern "C" gp_status gp_update_dirty(gp_world* w, uint32_t k, const uint32_t* id
         if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_update_dirty: idx[%u]=%u out of range", i, idx[i]);
     gp_status s = stage_state(w, k, idx, pos3, vel3, acc3);
     if (s != GP_OK) return s;
-    CK(cudaStreamSynchronize(w->st));  // idx/pos host arrays may be pageable and short-lived
+    w->track_slots = true;  // a host that sends dirty sets does so every frame: K3 keeps the id -> slot map current
+    // Pinned buffers (gp_host_alloc) are copied asynchronously -- they must then stay untouched until the next call
+    // that synchronises (gp_step, gp_sync, gp_download); pageable ones may be short-lived: wait for the copies.
+    bool pinned = true;
+    for (const void* p : {(const void*)idx, (const void*)pos3, (const void*)vel3, (const void*)acc3}) {
+        if (!p) continue;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            pinned = false;
+        }
+    }
+    if (!pinned) CK(cudaStreamSynchronize(w->st));
     return GP_OK;
 }
 
@@ -840,7 +855,7 @@ static gp_status enqueue_phase_a(gp_world* w, float dt, const float* damp3) {
     const uint32_t nb = n_bound(w);  // grids are sized for this; kernels stop at the device-resident counts
     prof_begin_step(w);
     fine_mark(w, "begin");
-    w->slot_valid = false;
+    w->slot_valid = false;  // (the callers set it again once a step is accepted, if K3 keeps the map current)
     if (nb) {
         prof_mark(w, 0);
         // K1 + K2: one-pass radix (bucket) sort by cell key: histogram with the keys, scan, scatter
@@ -891,7 +906,8 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
         prof_mark(w, 3);
         k_scatter_cells<<<cdiv(nb, 256), 256, 0, st>>>(w->key, w->lrank, Bodies{w->B[c]}, w->A[c], Bodies{w->B[o]}, w->A[o],
                                                        w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach, w->moved_bits,
-                                                       w->esc_bits, w->xhead, w->LB, w->ctl, dt, d[0], d[1], d[2]);
+                                                       w->esc_bits, w->xhead, w->LB, w->ctl,
+                                                       (w->track_slots && !w->multi) ? w->slot_of : nullptr, dt, d[0], d[1], d[2]);
         w->launches += 1;
         fine_mark(w, "k_scatter_cells");
         prof_mark(w, 4);
@@ -1027,6 +1043,7 @@ extern "C" gp_status gp_step(gp_world* w, float dt, const float* damp3, gp_step_
         if (c.n_requeried) result = GP_WARN_MARGIN_RETRIED;
         w->cur ^= 1;
         w->steps_total++;
+        w->slot_valid = w->track_slots && !w->multi;  // K3 rewrote the id -> slot map while it scattered
         fill_stats(w, c, retries);
         break;
     }
@@ -1050,6 +1067,7 @@ extern "C" gp_status gp_step_async(gp_world* w, float dt, const float* damp3, ui
         if (r != GP_OK) return r;
         w->cur ^= 1;
         w->steps_total++;
+        w->slot_valid = w->track_slots && !w->multi;
     }
     CK(cudaEventRecord(w->ev1, w->st));
     w->timed = true;
@@ -1134,6 +1152,30 @@ extern "C" gp_status gp_download(gp_world* w, float* pos3, float* vel3) {
     return gp_sync(w, nullptr);
 }
 
+static gp_status next_rows_ready(gp_world* w, const char* what);
+
+extern "C" gp_status gp_cap_velocity(gp_world* w, uint32_t k, const uint32_t* idx) {
+    if (!w) return GP_ERR_BAD_ARG;
+    gp_status s = next_rows_ready(w, "gp_cap_velocity");
+    if (s != GP_OK) return s;
+    if (!idx) k = w->n;
+    if (k == 0) return GP_OK;
+    for (uint32_t i = 0; idx && i < k; ++i)
+        if (idx[i] >= w->n) return fail(w, GP_ERR_BAD_ARG, "gp_cap_velocity: idx[%u]=%u out of range", i, idx[i]);
+    uint32_t* d_idx = nullptr;
+    if (idx) {
+        s = ensure_stage(w, (size_t)k * 4 + 256);
+        if (s != GP_OK) return s;
+        d_idx = (uint32_t*)w->stage;
+        CK(cudaMemcpyAsync(d_idx, idx, (size_t)k * 4, cudaMemcpyHostToDevice, w->st));
+    }
+    k_cap_velocity<<<cdiv(k, 256), 256, 0, w->st>>>(k, d_idx, w->slot_of, Bodies{w->B[w->cur]});
+    w->launches++;
+    CK(cudaGetLastError());
+    if (idx) CK(cudaStreamSynchronize(w->st));  // idx may be pageable and short-lived; the staging buffer is shared
+    return GP_OK;
+}
+
 // ---- pipelined frames ----
 static gp_status ensure_frames(gp_world* w) {
     if (!w->st_h2d) {
@@ -1150,8 +1192,9 @@ static gp_status ensure_frames(gp_world* w) {
         CK(cudaStreamSynchronize(w->st_d2h));
         for (int b = 0; b < 2; ++b) {
             CK(dmalloc(&w->fin[b], 9 * (size_t)w->cap));
-            CK(dmalloc(&w->fout[b], 2 * (size_t)w->cap));
+            CK(dmalloc(&w->fout[b], 6 * (size_t)w->cap));
         }
+        CK(dmalloc(&w->fout8, 2 * (size_t)w->cap));
         CK(dmalloc(&w->home, 3 * (size_t)w->cap));
         w->frame_cap = w->cap;
         w->home_valid = false;
@@ -1167,11 +1210,11 @@ static gp_status ensure_frames(gp_world* w) {
 }
 
 extern "C" gp_status gp_frame_submit(gp_world* w, const float* pos3, const float* vel3, const float* acc3, float dt,
-                                     const float* damp3, float* state8_out) {
+                                     const float* damp3, float* state6_out) {
     if (!w) return GP_ERR_BAD_ARG;
     if (!w->uploaded) return fail(w, GP_ERR_STATE, "gp_frame_submit before gp_upload");
     if (w->multi) return fail(w, GP_ERR_STATE, "gp_frame_submit addresses bodies by upload index: not available on a slab world");
-    if (!pos3 || !vel3 || !acc3 || !state8_out) return fail(w, GP_ERR_BAD_ARG, "gp_frame_submit: a buffer is NULL");
+    if (!pos3 || !vel3 || !acc3 || !state6_out) return fail(w, GP_ERR_BAD_ARG, "gp_frame_submit: a buffer is NULL");
     CK(cudaSetDevice(w->device));
     const uint32_t n = w->n;
     if (n == 0) return GP_OK;
@@ -1199,16 +1242,17 @@ extern "C" gp_status gp_frame_submit(gp_world* w, const float* pos3, const float
     w->cur ^= 1;
     w->steps_total++;
     if (reuse) CK(cudaStreamWaitEvent(w->st, w->ev_d2h[b], 0));  // the download of frame t-2 has left the buffer
-    k_unpack8<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, w->fout[b]);
-    w->launches++;
-    fine_mark(w, "k_unpack8");
+    k_unpack8<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, w->fout8);
+    k_rows8_to_6<<<cdiv(n, 256), 256, 0, w->st>>>(n, w->fout8, w->fout[b]);
+    w->launches += 2;
+    fine_mark(w, "k_unpack8+rows6");
     CK(cudaEventRecord(w->ev_unpacked[b], w->st));
     // download stream
     CK(cudaStreamWaitEvent(w->st_d2h, w->ev_unpacked[b], 0));
-    CK(cudaMemcpyAsync(state8_out, w->fout[b], 8 * sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, w->st_d2h));
+    CK(cudaMemcpyAsync(state6_out, w->fout[b], 6 * sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, w->st_d2h));
     CK(cudaEventRecord(w->ev_d2h[b], w->st_d2h));
     w->frames_submitted++;
-    w->slot_valid = false;
+    w->slot_valid = w->track_slots;
     return GP_OK;
 }
 

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256)
                     float4* __restrict__ sbox, uint32_t* __restrict__ chain_cnt, uint32_t* __restrict__ perm,
                     float* __restrict__ dmax, float* __restrict__ reach, uint32_t* __restrict__ moved_bits,
                     uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ xhead, const uint32_t* __restrict__ LB,
-                    Ctl* ctl,
+                    Ctl* ctl, uint32_t* __restrict__ slot_of /* nullable: body id -> slot, kept for dirty-set updates */,
                     float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncells = ctl->grid.ncells;
@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(256)
                                      __uint_as_float((__float_as_uint(m) & ~TOPBIT) | ((flags & F_STATIC) ? TOPBIT : 0u)));
     st256(&sbox[2 * (size_t)s], wlo_m, whi);
     perm[s] = i;  // slot in the input set: the repair kernels re-integrate from there
+    if (slot_of) slot_of[__float_as_uint(lo.w)] = s;  // (only for worlds whose host sends per-index updates)
 }
 
 

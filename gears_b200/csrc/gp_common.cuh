@@ -33,6 +33,8 @@ constexpr float POSITION_CORRECTION_SLOP = 0.01f;
 constexpr float FRICTION_COEFFICIENT = 0.8f;
 constexpr float VELOCITY_THRESHOLD = 0.05f;
 constexpr float GRAVITY_ACCELERATION = 28.0f;
+constexpr float MAX_HORIZONTAL_VELOCITY = 20.0f;  // cap_velocity only (physics.rs:7-8)
+constexpr float MAX_VERTICAL_VELOCITY = 40.0f;
 constexpr float FALL_MULTIPLIER = 1.75f;
 constexpr float APEX_MULTIPLIER = 0.6f;
 

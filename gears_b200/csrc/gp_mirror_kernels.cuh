@@ -208,6 +208,25 @@ __global__ void k_unpack(uint32_t n, const Bodies B, float* pos3, float* vel3, u
     if (ids) ids[i] = id;
 }
 
+// RigidBody::cap_velocity (physics.rs:506-520; called by MovementController::update_pos, controllers.rs:307, after it
+// wrote the player's velocity): horizontal speed limited to 20 by cgmath's normalize() = v * (1 / |v|), vertical
+// velocity f32::clamp'ed to +-40.  Row t = body idx[t] (idx == nullptr: every body).
+__global__ void k_cap_velocity(uint32_t k, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ slot_of, Bodies B) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint32_t i = idx ? slot_of[idx[t]] : t;
+    float4 v = B.V(i);
+    const float m = len3(mk(v.x, 0.0f, v.z));
+    if (m > MAX_HORIZONTAL_VELOCITY) {
+        const float inv = 1.0f / m;
+        v.x = (v.x * inv) * MAX_HORIZONTAL_VELOCITY;
+        v.z = (v.z * inv) * MAX_HORIZONTAL_VELOCITY;
+    }
+    if (v.y < -MAX_VERTICAL_VELOCITY) v.y = -MAX_VERTICAL_VELOCITY;
+    if (v.y > MAX_VERTICAL_VELOCITY) v.y = MAX_VERTICAL_VELOCITY;
+    B.V(i) = v;
+}
+
 // ---- pipelined frames (gp_frame_submit): whole-world state refresh and read-back without random sector traffic ----
 // "Home" = the per-body constants in BODY-ID order (48 B: min offset | mass, max offset | restitution, flags | rank),
 // built once per upload / shape change.  A frame's state arrives in body-id order, so k_set_state_all streams
@@ -244,6 +263,16 @@ __global__ void __launch_bounds__(256) k_unpack8(uint32_t n, const Bodies B, flo
     ld256(&B.Lo(i), lo, hi);
     const size_t id = __float_as_uint(lo.w);
     st256(state8 + 2 * id, make_float4(p.x, p.y, p.z, v.x), make_float4(v.y, v.z, 0.f, 0.f));
+}
+
+// 32 B rows -> 24 B rows (pos.xyz, vel.xyz), streaming: the download then moves 24 B per body instead of 32
+__global__ void __launch_bounds__(256) k_rows8_to_6(uint32_t n, const float4* __restrict__ state8, float* __restrict__ state6) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    float4 a, b;
+    ld256(state8 + 2 * (size_t)id, a, b);
+    float* o = state6 + 6 * (size_t)id;
+    o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = a.w, o[4] = b.x, o[5] = b.y;
 }
 
 // RigidBody::update_pos, physics.rs:405-462 (a.w carries the flags; static bodies are untouched)

@@ -150,6 +150,11 @@ class PhysicsWorld:
     def kernel_launches(self) -> int:
         return int(self._lib.gp_kernel_launches(self._h))
 
+    def cap_velocity(self, idx=None):
+        """RigidBody::cap_velocity (physics.rs:506-520) on the device for bodies idx (None: all)."""
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32)
+        self._check(self._lib.gp_cap_velocity(self._h, 0 if ix is None else len(ix), _ptr(ix)))
+
     # -- pipelined frames (gp_frame_submit / gp_frame_wait) --
     def host_alloc(self, shape, dtype=np.float32) -> np.ndarray:
         """A numpy array over PINNED host memory (gp_host_alloc); freed when the world closes."""
@@ -163,14 +168,14 @@ class PhysicsWorld:
         buf = (C.c_char * max(1, nbytes)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
-    def frame_submit(self, pos, vel, acc, dt: float, state8_out, damp=None):
+    def frame_submit(self, pos, vel, acc, dt: float, state6_out, damp=None):
         """Enqueue one frame: H2D of pos / vel / acc (n x 3 each, upload order) -> state refresh + step -> D2H of
-        (pos.xyz, vel.xyz, 0, 0) rows into state8_out (n x 8).  Returns at once; buffers should be pinned."""
-        for a in (pos, vel, acc, state8_out):
+        (pos.xyz, vel.xyz) rows into state6_out (n x 6).  Returns at once; buffers should be pinned."""
+        for a in (pos, vel, acc, state6_out):
             assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
         d = None if damp is None else _f32(damp)
         self._check(self._lib.gp_frame_submit(self._h, _ptr(pos), _ptr(vel), _ptr(acc), C.c_float(dt), _ptr(d),
-                                              _ptr(state8_out)))
+                                              _ptr(state6_out)))
 
     def frame_wait(self, max_in_flight: int = 0) -> dict:
         st = capi.GpStepStats()

@@ -182,23 +182,28 @@ typedef struct gp_kernel_times {
 } gp_kernel_times;
 gp_status gp_kernel_times_read(gp_world* w, gp_kernel_times* out);
 
+/* RigidBody::cap_velocity (physics.rs:506-520) on the device, for the bodies idx[0..k) (upload indices; idx == NULL:
+ * every body): what MovementController::update_pos does after writing the player's velocity (controllers.rs:307).
+ * Asynchronous on the step stream (ordered before the next step); idx is copied before the call returns. */
+gp_status gp_cap_velocity(gp_world* w, uint32_t k, const uint32_t* idx);
+
 /* ---- pipelined frames (async H2D / D2H overlapped with the step) ----
  * For hosts that own the state (every frame the ECS side hands over pos / vel / acc of ALL bodies, in upload order,
  * and wants pos / vel back -- SURVEY.md section 3.3: external systems may have written any of them):
  *   gp_frame_submit  enqueues  H2D of the three arrays (copy stream)  ->  whole-world state refresh + one step
- *                    (step stream)  ->  read-back + D2H into state8_out (download stream)  and returns at once.
+ *                    (step stream)  ->  read-back + D2H into state6_out (download stream)  and returns at once.
  *                    Two frames may be in flight: frame t+1 uploads while frame t computes and frame t-1 downloads
  *                    (PCIe is full duplex), so a frame costs max(H2D, kernels, D2H) instead of their sum.
  *                    All host buffers must be pinned (gp_host_alloc) and must stay untouched until the frame has
  *                    been waited for.  A frame REPLACES the mutable state: its result does not depend on the previous
  *                    frame's result, only on what the host passes in (and on shapes / masses set by gp_upload /
  *                    gp_update_shape).
- *   state8_out       n x 8 floats, row = upload index: pos.xyz, vel.xyz, 0, 0 (one 32 B sector per body).
+ *   state6_out       n x 6 floats, row = upload index: pos.xyz, vel.xyz.
  *   gp_frame_wait    blocks until at most max_in_flight submitted frames are unfinished (0 = all; then it also
  *                    reports latched step failures like gp_sync and fills stats).
  * Not available on a slab world. */
 gp_status gp_frame_submit(gp_world* w, const float* pos3, const float* vel3, const float* acc3, float dt,
-                          const float damp3[3], float* state8_out);
+                          const float damp3[3], float* state6_out);
 gp_status gp_frame_wait(gp_world* w, uint32_t max_in_flight, gp_step_stats* stats);
 
 /* ---- multi-GPU: spatial slabs along x, one gp_world per GPU ----

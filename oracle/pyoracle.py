@@ -58,7 +58,7 @@ def _p(a, typ):
 
 
 def step(scene: dict, dt: float, steps: int = 1, mode: int = 0, threads: int = 1, want_snapshot: bool = True,
-         pair_cap: int | None = None):
+         pair_cap: int | None = None, want_pairs: bool = True):
     """Run `steps` physics steps on a copy of `scene` (dict of numpy arrays, see gears_b200.scenes).
 
     Returns dict(pos, vel, snapshot, sweep, static_static); pair arrays are (m,2) uint32 of caller
@@ -90,8 +90,10 @@ def step(scene: dict, dt: float, steps: int = 1, mode: int = 0, threads: int = 1
                        C.c_uint64(cap), _p(ss, u32p), C.c_uint64(cap), C.byref(out))
     if rc != 0:
         raise ValueError("oracle: rank is not a permutation of 0..n-1")
-    if max(out.n_snapshot, out.n_sweep, out.n_static_static) > cap:
+    if want_pairs and max(out.n_snapshot, out.n_sweep, out.n_static_static) > cap:
         raise OverflowError("oracle pair capacity too small")
+    if not want_pairs:  # (timing runs: the pair lists were counted, not stored)
+        return dict(pos=pos, vel=vel, n_sweep=int(out.n_sweep))
     return dict(pos=pos, vel=vel, snapshot=snap[: out.n_snapshot].copy(), sweep=sweep[: out.n_sweep].copy(),
                 static_static=ss[: out.n_static_static].copy())
 

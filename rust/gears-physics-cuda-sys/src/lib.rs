@@ -153,10 +153,13 @@ unsafe extern "C" {
         bitmap: *mut u32, bounds_out: *mut i32,
     ) -> gp_status;
 
+    // RigidBody::cap_velocity (physics.rs:506-520) for the bodies idx[0..k) (null: all)
+    pub fn gp_cap_velocity(w: *mut gp_world, k: u32, idx: *const u32) -> gp_status;
+
     // pipelined frames: async H2D / step / D2H, two frames in flight (pinned host buffers)
     pub fn gp_frame_submit(
         w: *mut gp_world, pos3: *const f32, vel3: *const f32, acc3: *const f32, dt: f32, damp3: *const f32,
-        state8_out: *mut f32,
+        state6_out: *mut f32,
     ) -> gp_status;
     pub fn gp_frame_wait(w: *mut gp_world, max_in_flight: u32, stats: *mut gp_step_stats) -> gp_status;
 

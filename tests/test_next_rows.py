@@ -162,7 +162,7 @@ def test_pipelined_frames_equal_set_state_step_download(oracle):
         for (pos, vel, acc, _, _) in frames:
             hp, hv, ha = (w2.host_alloc((n, 3)) for _ in range(3))
             hp[:], hv[:], ha[:] = pos, vel, acc
-            o = w2.host_alloc((n, 8))
+            o = w2.host_alloc((n, 6))
             o[:] = np.float32(7.0)
             w2.frame_submit(hp, hv, ha, DT, o)
             ins.append((hp, hv, ha)), outs.append(o)
@@ -171,7 +171,38 @@ def test_pipelined_frames_equal_set_state_step_download(oracle):
         for t, (o, (_, _, _, p1, v1)) in enumerate(zip(outs, frames)):
             assert_same_bits(o[:, 0:3], p1, f"frame {t} pos")
             assert_same_bits(o[:, 3:6], v1, f"frame {t} vel")
-            assert not o[:, 6:8].any()
         # and the world is left in the state of the last frame for the per-call API
         p2, v2 = w2.download()
         assert_same_bits(p2, frames[-1][3], "state after the last frame")
+
+
+@pytest.mark.gpu
+def test_cap_velocity_matches_oracle_bitwise(oracle):
+    """Device RigidBody::cap_velocity (physics.rs:506-520, caller controllers.rs:307) for flagged bodies: bit-equal to
+    the oracle's restatement, untouched bodies keep their bits, and the reference's own bounds hold
+    (physics.rs:664-693: horizontal <= 20, vertical within +-40)."""
+    n = 5000
+    s = scenes.uniform(n, L=40.0, seed=71, rank_seed=72, floor=False)
+    rng = np.random.default_rng(9)
+    s["vel"] = ((rng.random((n, 3)) - 0.5) * 120.0).astype(np.float32)
+    s["vel"][0] = (20.0, 40.0, 0.0)          # exactly at the caps: unchanged
+    s["vel"][1] = (12.0, -41.0, 16.0)        # |h| = 20 exactly (not above), y clamped
+    s["vel"][2] = (0.0, 0.0, 0.0)
+    idx = np.arange(0, n, 3, dtype=np.uint32)
+    with world() as w:
+        w.upload(s)
+        w.cap_velocity(idx)
+        _, v = w.download()
+        w.cap_velocity(None)
+        _, v_all = w.download()
+    flagged = np.zeros(n, bool)
+    flagged[idx] = True
+    want = np.stack([oracle.cap_velocity(x) for x in s["vel"]])
+    assert_same_bits(v[flagged], want[flagged], "capped bodies")
+    assert_same_bits(v[~flagged], s["vel"][~flagged], "bodies that were not flagged")
+    # the second call caps the flagged bodies a SECOND time (a capped horizontal speed can round to just above 20)
+    want2 = want.copy()
+    want2[flagged] = np.stack([oracle.cap_velocity(x) for x in want[flagged]])
+    assert_same_bits(v_all, want2, "all bodies")
+    h = np.sqrt(v_all[:, 0].astype(np.float64) ** 2 + v_all[:, 2].astype(np.float64) ** 2)
+    assert h.max() <= 20.0 + 1e-4 and np.abs(v_all[:, 1]).max() <= 40.0

@@ -1,24 +1,42 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-run() { # name, env..., -- bench args
-    name=$1; shift
-    envs=()
-    while [ "$1" != "--" ]; do envs+=("$1"); shift; done
-    shift
-    env "${envs[@]}" timeout -k 10 300 python bench.py --no-cpu "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err
-    grep "gp fine" gpurun_out/$name.err > gpurun_out/$name.fine
-}
-timeout -k 10 900 python -m pytest tests -m gpu -x -q --timeout=300 --deselect tests/test_gpu_large.py > gpurun_out/gpu_tests.log 2>&1 || echo "TESTS FAILED"
+timeout -k 10 900 python -m pytest tests/test_next_rows.py tests/test_rotation_known_answers.py tests/test_gpu_parity.py -m gpu -x -q --timeout=300 -k "cap_velocity or frames or rotation or instance or aabb or dirty or external" > gpurun_out/gpu_tests.log 2>&1 || echo "TESTS FAILED"
 tail -5 gpurun_out/gpu_tests.log
-run base_16M X=1 -- --workload uniform_16M --steps 20 --warmup 5
-run base_2M X=1 -- --workload uniform_2M --steps 20 --warmup 5
-run fine_16M GP_PROF_FINE=1 -- --workload uniform_16M --steps 20 --warmup 5 --e2e-steps 0
-run fine_2M GP_PROF_FINE=1 -- --workload uniform_2M --steps 20 --warmup 5 --e2e-steps 0
-for t in 512; do
-  GP_NVCC_EXTRA="-DGP_COOP_THREADS=$t" python -c "from gears_b200 import build; build.build(force=True)" > gpurun_out/build_$t.log 2>&1
-  run t${t}_16M X=1 -- --workload uniform_16M --steps 20 --warmup 5
-  run t${t}_2M X=1 -- --workload uniform_2M --steps 20 --warmup 5
-done
-python tools/show_bench.py gpurun_out/base_*.json gpurun_out/t*_*.json | grep -v n_bodies
-for f in fine_16M fine_2M; do grep "k_contacts\|per step\|slot" gpurun_out/$f.fine; done
+python tools/pcie_probe.py 576 2>&1 | tail -2
+GP_PROF_FINE=1 python - > gpurun_out/dirty_probe.log 2>&1 <<'P'
+import time, numpy as np, sys
+sys.path.insert(0, '.')
+import bench
+from gears_b200.world import PhysicsWorld
+gen, wkw = bench.WORKLOADS["uniform_16M"]
+s = bench.make_scene(gen); n = len(s["mass"])
+DT = bench.DT
+with PhysicsWorld(profile=True, **wkw) as w:
+    w.upload(s)
+    for _ in range(5): w.step(DT)
+    w.kernel_times()
+    k = n // 10
+    hidx = w.host_alloc((k,), np.uint32); hv = w.host_alloc((k, 3)); ha = w.host_alloc((k, 3))
+    hidx[:] = np.sort(np.random.default_rng(1).choice(n, size=k, replace=False)).astype(np.uint32); hv[:] = 0; ha[:] = 0
+    w.update_dirty(hidx, vel=hv, acc=ha); w.step_async(DT, 1); w.sync()
+    tu = ts = 0.0
+    t0 = time.perf_counter()
+    for _ in range(10):
+        a = time.perf_counter(); w.update_dirty(hidx, vel=hv, acc=ha); b = time.perf_counter(); w.step_async(DT, 1); c = time.perf_counter()
+        tu += b - a; ts += c - b
+    w.sync(); t1 = time.perf_counter()
+    print(f"10% dirty: {1e3*(t1-t0)/10:.2f} ms/step; host time in update_dirty {1e3*tu/10:.2f} ms, in step_async {1e3*ts/10:.2f} ms")
+P
+grep -v "k_contacts /\|slot " gpurun_out/dirty_probe.log | tail -22
+( time python bench.py ) > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+tail -2 gpurun_out/bench_default.err
+python tools/show_bench.py gpurun_out/bench_default.json | grep -v n_bodies
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
+e=d["e2e"]; print("e2e", e["value"], e["ms_per_step"], "dependent", e["dependent"]["value"], [ (x["dirty_fraction"], x["value"], x["ms_per_step"]) for x in e["dirty_set"]]); print(d["cpu_baseline_grid"]); 
+P
+CMD="python bench.py --no-cpu --steps 3 --warmup 3 --e2e-steps 2"
+$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/ncu_launches_uniform_16M.csv $CMD > gpurun_out/ncu.log 2>&1
+python tools/ncu_launches.py gpurun_out/ncu_launches_uniform_16M.csv | head -30
