@@ -241,6 +241,11 @@ def run_ours(args) -> dict:
     parity = None
     if world_size > 1 and args.parity_steps > 0:
         parity = slab_parity(w, full_scene, wkw_single, dist, torch, local_rank, args.parity_steps)
+        # back to the initial state, so that every N times the SAME steps of the scene (the cost of a step drifts as the
+        # scene evolves)
+        w.upload(scene)
+        slabs.comm_init(w, dist, rank, world_size, faces, halo=args.halo, max_exchange=args.max_exchange,
+                        device=torch.device("cuda", local_rank))
     if world_size > 1:
         del full_scene
 
@@ -385,24 +390,38 @@ def run_ours(args) -> dict:
                              "path": "gp_set_state + gp_step + gp_download, each step fed with the previous step's "
                                      "downloaded result (nothing can overlap)"}}
     else:
-        # slab worlds keep their state on the device between steps; the host-visible result is gp_download_owned
-        nown = 0
-        torch.cuda.synchronize()
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        # slab worlds: every step, each rank writes back the rows of its owned bodies (what external systems may have
+        # changed since the last read) from pinned memory, steps, and reads its owned bodies again; the ranks' PCIe
+        # links work in parallel.  (Rows are keyed by the order of the last read, which changes with every step, so
+        # frames cannot overlap here.)
+        cap_rows = int(n_local * 1.25) + 262144
+        o_ent, o_unv = w.host_alloc((cap_rows,), np.uint32), w.host_alloc((cap_rows,), np.uint8)
+        o_pos, o_vel, o_acc = (w.host_alloc((cap_rows, 3)) for _ in range(3))
+        o_acc[:] = 0.0
+        e2e_steps = max(1, args.e2e_steps)
+        ent, hp, hv = w.download_owned(out=(o_ent, o_pos, o_vel, o_unv))
+        nown = len(ent)
+        h2d = d2h = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            w.set_state_owned(pos=hp, vel=hv, acc=o_acc[:nown])        # H2D: pos, vel, acc of the owned bodies
             w.step_async(DT, 1)
-            ent, hp, hv = w.download_owned()               # D2H: ids, pos, vel of the owned bodies (sync)
+            h2d += 36 * nown
+            ent, hp, hv = w.download_owned(out=(o_ent, o_pos, o_vel, o_unv))   # D2H: ids, pos, vel (+ flags), sync
             nown = len(ent)
+            d2h += 29 * nown
         barrier()
         t1 = time.perf_counter()
         tt = torch.tensor([t1 - t0], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        bt = torch.tensor([float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(bt, op=dist.ReduceOp.SUM)
         e2e = {"value": n_total * e2e_steps / float(tt.item()), "unit": "body-steps/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 28 * nown,
-               "path": "gp_step_async + gp_download_owned per step (slab worlds have no per-index H2D path; "
-                       "inputs are device-resident)"}
+               "ms_per_step": float(tt.item()) * 1e3 / e2e_steps,
+               "h2d_bytes_per_step": int(bt[0].item() / e2e_steps), "d2h_bytes_per_step": int(bt[1].item() / e2e_steps),
+               "path": "per rank and step: gp_set_state_owned (pos, vel, acc of the owned bodies, pinned) + "
+                       "gp_step_async + gp_download_owned (ids, pos, vel, pinned); bytes summed over the ranks"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference algorithm on a bounded sample ----
     cpu = cpu_baseline(args, gen) if (rank == 0 and world_size == 1 and not args.no_cpu) else None

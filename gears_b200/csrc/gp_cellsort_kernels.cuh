@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(256)
                     float* __restrict__ dmax, float* __restrict__ reach, uint32_t* __restrict__ moved_bits,
                     uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ xhead, const uint32_t* __restrict__ LB,
                     Ctl* ctl, uint32_t* __restrict__ slot_of /* nullable: body id -> slot, kept for dirty-set updates */,
+                    uint32_t* __restrict__ seed_bits /* nullable (slab worlds): seeds of the exactness proof */,
                     float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncells = ctl->grid.ncells;
@@ -305,6 +306,14 @@ __global__ void __launch_bounds__(256)
     const float4 wlo_m = make_float4(wlo.x, wlo.y, wlo.z,
                                      __uint_as_float((__float_as_uint(m) & ~TOPBIT) | ((flags & F_STATIC) ? TOPBIT : 0u)));
     st256(&sbox[2 * (size_t)s], wlo_m, whi);
+    // Slab worlds: a body whose margin pokes beyond what the neighbour mirrors may have a partner this rank has never
+    // seen -- a seed of the per-step exactness proof (taint_phase).  Decided here, where the box is in registers, so
+    // the proof need not read 32 B per body again; bodies that out-run their margin are added from the escapee list.
+    if (seed_bits && !(flags & F_STATIC)) {
+        const bool out_r = ctl->has_right && !(whi.x + m <= ctl->x_hi + ctl->halo);
+        const bool out_l = ctl->has_left && !(wlo.x - m >= ctl->x_lo - ctl->halo);
+        if (out_l || out_r) atomicOr(&seed_bits[s >> 5], 1u << (s & 31u));
+    }
     perm[s] = i;  // slot in the input set: the repair kernels re-integrate from there
     if (slot_of) slot_of[__float_as_uint(lo.w)] = s;  // (only for worlds whose host sends per-index updates)
 }

@@ -208,6 +208,7 @@ struct ContactArgs {
     uint32_t* recs;              // component records of the per-component repair (aliases ra.adj2)
     uint32_t rec_cap;
     uint32_t* taint_bits;        // slab worlds: per-step exactness proof (nullptr otherwise)
+    uint32_t* seed_bits;         // ... and the seeds K3 marked for it
     float dt, d16, d18, d35;
     uint32_t start_phase;        // 0: sweep first; 1: continue the repair loop
     uint32_t max_rounds;         // repair rounds before the step is declared still-growing (SF_MARGIN)

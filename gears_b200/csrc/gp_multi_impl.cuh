@@ -30,6 +30,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;  // optional: tear-down without the peers (a dead slab world)
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -62,6 +63,7 @@ static bool nccl_load(std::string* why) {
     GP_SYM(GetUniqueId, "ncclGetUniqueId")
     GP_SYM(CommInitRank, "ncclCommInitRank")
     GP_SYM(CommDestroy, "ncclCommDestroy")
+    *(void**)(&a.CommAbort) = dlsym(h, "ncclCommAbort");
     GP_SYM(GroupStart, "ncclGroupStart")
     GP_SYM(GroupEnd, "ncclGroupEnd")
     GP_SYM(Send, "ncclSend")
@@ -92,11 +94,14 @@ struct gp_multi {
     size_t buf_bytes[2] = {0, 0};  // per face: 16 B header + xcap[side] records (both sides of a face agree)
     uint32_t proposal = 0;         // records per face buffer this rank asks for
     uint32_t* taint_bits = nullptr;
+    uint32_t* seed_bits = nullptr;  // marked by K3, consumed (and cleared) by the proof
     uint32_t* scratch = nullptr;   // [0] taint gate, [1..3] prepare counts, [4] compact counter
     cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
     cudaEvent_t ev_copied = nullptr;   // local transport: this world has copied what it needs from its neighbours
     bool verify = true;
     unsigned long long timeout_ns = 30ull * 1000000000ull;  // peer-to-peer waits (GP_PEER_TIMEOUT_MS)
+    uint32_t owned_count = 0xffffffffu;  // rows of the last gp_download_owned ...
+    uint64_t owned_gen = 0;              // ... and the step count it was taken at (gp_set_state_owned checks both)
 };
 
 static void gp_multi_destroy(gp_multi* m) {
@@ -104,12 +109,17 @@ static void gp_multi_destroy(gp_multi* m) {
     for (int s = 0; s < 2; ++s)
         if (m->peer_arena[s]) cudaIpcCloseMemHandle(m->peer_arena[s]);
     if (m->arena) cudaFree(m->arena);
-    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    // (ncclCommDestroy expects every rank to come along; a world whose neighbour timed out is on its own)
+    if (m->comm && m->w && m->w->dead && g_nccl.CommAbort)
+        g_nccl.CommAbort(m->comm);
+    else if (m->comm && g_nccl.CommDestroy)
+        g_nccl.CommDestroy(m->comm);
     for (int s = 0; s < 2; ++s) {
         if (m->send[s]) cudaFree(m->send[s]);
         if (m->recv[s]) cudaFree(m->recv[s]);
     }
     if (m->taint_bits) cudaFree(m->taint_bits);
+    if (m->seed_bits) cudaFree(m->seed_bits);
     if (m->scratch) cudaFree(m->scratch);
     if (m->ev_packed) cudaEventDestroy(m->ev_packed);
     if (m->ev_copied) cudaEventDestroy(m->ev_copied);
@@ -186,6 +196,7 @@ static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
 }
 
 static uint32_t* gp_multi_taint_bits(gp_multi* m) { return m->verify ? m->taint_bits : nullptr; }
+static uint32_t* gp_multi_seed_bits(gp_multi* m) { return m->verify ? m->seed_bits : nullptr; }
 
 // common part of gp_comm_init / gp_comm_init_local
 static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) {
@@ -220,6 +231,8 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
     gp_status rs = GP_OK;
     do {
         if (dmalloc(&m->scratch, 16) || dmalloc(&m->taint_bits, (size_t)w->cap / 32 + 1) ||
+            dmalloc(&m->seed_bits, (size_t)w->cap / 32 + 1) ||
+            cudaMemsetAsync(m->seed_bits, 0, sizeof(uint32_t) * ((size_t)w->cap / 32 + 1), w->st) != cudaSuccess ||
             cudaEventCreateWithFlags(&m->ev_packed, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&m->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
             rs = fail(w, GP_ERR_CUDA, "slab setup: out of device memory");
@@ -475,13 +488,14 @@ extern "C" gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt,
     return GP_OK;
 }
 
-static gp_status count_owned(gp_world* w, uint32_t* n) {
+// flags + scan of the owned bodies of a slab world (chain_cnt / offs / tile_sums are free between steps); *n = count
+static gp_status scan_owned(gp_world* w, uint32_t* n) {
     gp_multi* m = w->multi;
-    CK(cudaMemsetAsync(m->scratch + 4, 0, sizeof(uint32_t), w->st));
-    k_compact_owned<<<cdiv(w->cap, 256), 256, 0, w->st>>>(w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur], m->cfg.rank == 0,
-                                                           m->scratch + 4, nullptr, nullptr, nullptr, nullptr, nullptr);
+    const uint32_t cap = w->cap;
+    k_owned_flags<<<cdiv(cap, 256), 256, 0, w->st>>>(cap, w->ctl, w->A[w->cur], m->cfg.rank == 0, w->chain_cnt);
     w->launches++;
-    CK(cudaMemcpyAsync(n, m->scratch + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    exclusive_scan_u32(w->chain_cnt, cap, w->offs, w->tile_sums, w->st, &w->launches);
+    CK(cudaMemcpyAsync(n, w->offs + cap, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
     return GP_OK;
 }
@@ -494,17 +508,17 @@ extern "C" gp_status gp_owned_count(gp_world* w, uint32_t* n) {
         return GP_OK;
     }
     CK(cudaSetDevice(w->device));
-    return count_owned(w, n);
+    return scan_owned(w, n);
 }
 
-// entity ids + state of the bodies this rank owns now (after migration), in no particular order
+// entity ids + state of the bodies this rank owns now (after migration), in slot order
 extern "C" gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified) {
     if (!w || !entity || !pos3 || !vel3) return GP_ERR_BAD_ARG;
     if (!w->uploaded) return fail(w, GP_ERR_STATE, "no bodies uploaded");
     CK(cudaSetDevice(w->device));
     uint32_t n = 0;
     if (w->multi) {
-        gp_status s = count_owned(w, &n);
+        gp_status s = scan_owned(w, &n);
         if (s != GP_OK) return s;
     } else {
         n = w->n;
@@ -519,10 +533,11 @@ extern "C" gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos
     uint8_t* du = (uint8_t*)(w->stage + 2 * a3 + bi);
     CK(cudaMemsetAsync(du, 0, n, w->st));
     if (w->multi) {
-        CK(cudaMemsetAsync(w->multi->scratch + 4, 0, sizeof(uint32_t), w->st));
-        k_compact_owned<<<cdiv(w->cap, 256), 256, 0, w->st>>>(w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur],
-                                                               w->multi->cfg.rank == 0, w->multi->scratch + 4, di, dp, dv,
-                                                               w->multi->verify && w->steps_total ? w->multi->taint_bits : nullptr, du);
+        k_owned_gather<<<cdiv(w->cap, 256), 256, 0, w->st>>>(
+            w->cap, w->ctl, Bodies{w->B[w->cur]}, w->chain_cnt, w->offs, di, dp, dv,
+            w->multi->verify && w->steps_total ? w->multi->taint_bits : nullptr, du, w->dlist);
+        w->multi->owned_count = n;
+        w->multi->owned_gen = w->steps_total;
     } else {
         k_unpack<<<cdiv(n, 256), 256, 0, w->st>>>(n, Bodies{w->B[w->cur]}, dp, dv, di, 0);
     }
@@ -533,4 +548,33 @@ extern "C" gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos
     if (unverified) CK(cudaMemcpyAsync(unverified, du, n, cudaMemcpyDeviceToHost, w->st));
     CK(cudaStreamSynchronize(w->st));
     return gp_sync(w, nullptr);
+}
+
+// The rows gp_download_owned returned last, written back (external systems changed them): row t = the t-th owned body
+// of that download.  Valid only while no step has run since (the slots change with every step).
+extern "C" gp_status gp_set_state_owned(gp_world* w, uint32_t k, const float* pos3, const float* vel3, const float* acc3) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (!w->uploaded) return fail(w, GP_ERR_STATE, "no bodies uploaded");
+    if (!w->multi) return fail(w, GP_ERR_STATE, "gp_set_state_owned is for slab worlds; use gp_set_state");
+    gp_multi* m = w->multi;
+    if (m->owned_gen != w->steps_total || m->owned_count == 0xffffffffu)
+        return fail(w, GP_ERR_STATE, "gp_set_state_owned: call gp_download_owned first (and no step in between)");
+    if (k != m->owned_count) return fail(w, GP_ERR_BAD_ARG, "gp_set_state_owned: %u rows, the last download had %u", k, m->owned_count);
+    CK(cudaSetDevice(w->device));
+    if (k == 0) return GP_OK;
+    const size_t b3 = 3 * sizeof(float) * (size_t)k, a3 = (b3 + 255) & ~(size_t)255;
+    gp_status s = ensure_stage(w, 3 * a3 + 256);
+    if (s != GP_OK) return s;
+    unsigned char* sg = w->stage;
+    if (pos3) CK(cudaMemcpyAsync(sg, pos3, b3, cudaMemcpyHostToDevice, w->st));
+    if (vel3) CK(cudaMemcpyAsync(sg + a3, vel3, b3, cudaMemcpyHostToDevice, w->st));
+    if (acc3) CK(cudaMemcpyAsync(sg + 2 * a3, acc3, b3, cudaMemcpyHostToDevice, w->st));
+    k_set_state_slots<<<cdiv(k, 256), 256, 0, w->st>>>(k, w->dlist, pos3 ? (const float*)sg : nullptr,
+                                                        vel3 ? (const float*)(sg + a3) : nullptr,
+                                                        acc3 ? (const float*)(sg + 2 * a3) : nullptr, Bodies{w->B[w->cur]},
+                                                        w->A[w->cur]);
+    w->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w->st));  // the host arrays may be pageable and short-lived
+    return GP_OK;
 }

@@ -38,18 +38,28 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     Ctl* ctl = a.ctl;
     const uint32_t n = ctl->n;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (uint32_t wd = gtid; wd < (n + 31u) / 32u; wd += gsz) taint_bits[wd] = 0u;
+    const uint32_t words = (n + 31u) / 32u;
+    (void)moved_bits;
+    // seeds, part 1: bodies whose MARGIN pokes beyond what the neighbours mirror (K3 marked them while it had their
+    // boxes in registers; the marks are consumed here)
+    for (uint32_t wd = gtid; wd < words; wd += gsz) {
+        const uint32_t t = a.seed_bits[wd];
+        taint_bits[wd] = t;
+        if (t) a.seed_bits[wd] = 0u;
+    }
     if (gtid == 0) ctl->taint_flag[0] = 0u, ctl->taint_flag[1] = 0u, ctl->taint_flag[2] = 0u;
     grid.sync();
-    // seeds: bodies whose reach pokes beyond what the neighbours mirror
-    for (uint32_t i = gtid; i < n; i += gsz) {
-        const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
-        if (box_static(lo)) continue;  // static bodies never change: nothing to get wrong
-        float r = box_margin(lo);
-        if ((__ldcg(&moved_bits[i >> 5]) >> (i & 31u)) & 1u) r = fmaxf(r, fmaxf(__ldcg(&reach[i]), __ldcg(&dmax[i]) * REACH_SLACK));
-        const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
-        const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
-        if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
+    // seeds, part 2: bodies that moved further than their margin (all of them are on the escapee list)
+    {
+        const uint32_t ne = min(__ldcg(&ctl->n_escapees), a.esc_cap);
+        for (uint32_t e = gtid; e < ne; e += gsz) {
+            const uint32_t i = __ldcg(&a.escapees[e]);
+            const float4 lo = sbox[2 * (size_t)i], hi = sbox[2 * (size_t)i + 1];
+            const float r = fmaxf(box_margin(lo), fmaxf(__ldcg(&reach[i]), __ldcg(&dmax[i]) * REACH_SLACK));
+            const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
+            const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
+            if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
+        }
     }
     grid.sync();
     const uint32_t np = min(__ldcg(&ctl->n_pairs), pair_cap), nw = min(ctl->n_watch, pair_cap);
@@ -73,37 +83,80 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
         open = __ldcg(flag) != 0u;
         ++it;
     }
-    // owned dynamic bodies that are not provably independent of unseen bodies
+    // owned dynamic bodies that are not provably independent of unseen bodies (the tainted ones are few: walk the
+    // set bits, not the bodies)
     uint32_t c = 0;
-    for (uint32_t i = gtid; i < n; i += gsz) {
-        const uint32_t f = __float_as_uint(A[i].w);
-        if (!(f & (F_GHOST | F_STATIC)) && (open || ((__ldcg(&taint_bits[i >> 5]) >> (i & 31u)) & 1u))) ++c;
+    if (open) {  // the propagation did not reach its fixed point within the round limit: nothing is proven
+        for (uint32_t i = gtid; i < n; i += gsz) {
+            const uint32_t f = __float_as_uint(A[i].w);
+            if (!(f & (F_GHOST | F_STATIC))) ++c;
+        }
+    } else {
+        for (uint32_t wd = gtid; wd < words; wd += gsz) {
+            uint32_t t = __ldcg(&taint_bits[wd]);
+            while (t) {
+                const uint32_t i = wd * 32u + (uint32_t)__ffs(t) - 1u;
+                t &= t - 1u;
+                if (i < n && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
+            }
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->n_unverified, c);
 }
 
-// owned bodies (no halo copies; replicated big statics only on the rank that has no left neighbour) -> host layout
+// Owned bodies (no halo copies; replicated big statics only on the rank that has no left neighbour) -> host layout,
+// in SLOT ORDER (flags, exclusive scan, gather): the order is deterministic, so the host can hand the same rows back
+// with gp_set_state_owned (row k goes to owned_slot[k]) as long as no step ran in between.
 __global__ void __launch_bounds__(256)
-    k_compact_owned(const Ctl* ctl, const Bodies B, const float4* __restrict__ A, int is_first_rank, uint32_t* counter,
-                    uint32_t* __restrict__ ids, float* __restrict__ pos3, float* __restrict__ vel3,
-                    const uint32_t* __restrict__ taint_bits, uint8_t* __restrict__ unverified) {
+    k_owned_flags(uint32_t cap, const Ctl* ctl, const float4* __restrict__ A, int is_first_rank, uint32_t* __restrict__ flags) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n_in) return;  // between steps n_in = the live bodies of the last step
-    const uint32_t f = __float_as_uint(A[i].w);
-    if (f & F_GHOST) return;
-    if ((f & F_BIG) && !is_first_rank) return;
-    cg::coalesced_group g = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
-    base = g.shfl(base, 0);
-    const uint32_t s = base + g.thread_rank();
-    if (!ids) return;  // counting pass
+    if (i >= cap) return;
+    uint32_t own = 0;
+    if (i < ctl->n_in) {  // between steps n_in = the live bodies of the last step
+        const uint32_t f = __float_as_uint(A[i].w);
+        own = !(f & F_GHOST) && (!(f & F_BIG) || is_first_rank);
+    }
+    flags[i] = own;
+}
+__global__ void __launch_bounds__(256)
+    k_owned_gather(uint32_t cap, const Ctl* ctl, const Bodies B, const uint32_t* __restrict__ flags,
+                   const uint32_t* __restrict__ offs, uint32_t* __restrict__ ids, float* __restrict__ pos3,
+                   float* __restrict__ vel3, const uint32_t* __restrict__ taint_bits, uint8_t* __restrict__ unverified,
+                   uint32_t* __restrict__ owned_slot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap || !flags[i]) return;
+    const uint32_t s = offs[i];
     const float4 p = B.P(i), v = B.V(i);
     ids[s] = __float_as_uint(B.Lo(i).w);
     pos3[3 * (size_t)s] = p.x, pos3[3 * (size_t)s + 1] = p.y, pos3[3 * (size_t)s + 2] = p.z;
     vel3[3 * (size_t)s] = v.x, vel3[3 * (size_t)s + 1] = v.y, vel3[3 * (size_t)s + 2] = v.z;
-    if (taint_bits && unverified) unverified[s] = (taint_bits[i >> 5] >> (i & 31u)) & 1u;  // of the LAST step
+    if (unverified) unverified[s] = taint_bits ? (taint_bits[i >> 5] >> (i & 31u)) & 1u : 0u;  // of the LAST step
+    owned_slot[s] = i;
+}
+// rows of the last gp_download_owned back into the bodies they came from
+__global__ void __launch_bounds__(256)
+    k_set_state_slots(uint32_t k, const uint32_t* __restrict__ owned_slot, const float* __restrict__ pos3,
+                      const float* __restrict__ vel3, const float* __restrict__ acc3, Bodies B, float4* __restrict__ A) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint32_t i = owned_slot[t];
+    const size_t r = 3 * (size_t)t;
+    if (pos3) {
+        float4 p = B.P(i);
+        p.x = pos3[r], p.y = pos3[r + 1], p.z = pos3[r + 2];
+        B.P(i) = p;
+    }
+    if (vel3) {
+        float4 v = B.V(i);
+        v.x = vel3[r], v.y = vel3[r + 1], v.z = vel3[r + 2];
+        B.V(i) = v;
+    }
+    if (acc3) {
+        float4 a = A[i];
+        a.x = acc3[r], a.y = acc3[r + 1], a.z = acc3[r + 2];
+        A[i] = a;
+    }
 }
 
 // gp_comm_init: body ids become the caller's global entity ids; count what the faces would send right now

@@ -189,16 +189,27 @@ class PhysicsWorld:
         self._check(self._lib.gp_download(self._h, _ptr(pos), _ptr(vel)))
         return pos, vel
 
-    def download_owned(self):
-        """(entity, pos, vel) of the bodies this world owns now (slab worlds: after migration; no halo copies)."""
+    def download_owned(self, out=None):
+        """(entity, pos, vel) of the bodies this world owns now (slab worlds: after migration; no halo copies), in
+        device order.  out = (ent, pos, vel, unverified) buffers to fill (e.g. pinned, sized for max_bodies)."""
         n = C.c_uint32()
         self._check(self._lib.gp_owned_count(self._h, C.byref(n)))
         k = max(1, n.value)
-        ent, pos, vel = np.zeros(k, np.uint32), np.zeros((k, 3), np.float32), np.zeros((k, 3), np.float32)
-        unv = np.zeros(k, np.uint8)
+        if out is None:
+            ent, pos, vel = np.zeros(k, np.uint32), np.zeros((k, 3), np.float32), np.zeros((k, 3), np.float32)
+            unv = np.zeros(k, np.uint8)
+        else:
+            ent, pos, vel, unv = out
+            assert len(ent) >= k
         self._check(self._lib.gp_download_owned(self._h, _ptr(ent), _ptr(pos), _ptr(vel), _ptr(unv)))
         self.last_unverified = unv[: n.value]
         return ent[: n.value], pos[: n.value], vel[: n.value]
+
+    def set_state_owned(self, pos=None, vel=None, acc=None):
+        """Rows of the last download_owned written back (no step in between)."""
+        k = next(len(a) for a in (pos, vel, acc) if a is not None)
+        pos, vel, acc = _f32(pos, 3), _f32(vel, 3), _f32(acc, 3)
+        self._check(self._lib.gp_set_state_owned(self._h, k, _ptr(pos), _ptr(vel), _ptr(acc)))
 
     # -- next rows (SURVEY 8f) --
     def instances(self, rot=None, scale=None) -> np.ndarray:

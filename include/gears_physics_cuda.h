@@ -236,10 +236,13 @@ gp_status gp_comm_unique_id(uint8_t id[GP_UNIQUE_ID_BYTES]);
 gp_status gp_comm_init(gp_world* w, const uint8_t id[GP_UNIQUE_ID_BYTES], const gp_slab_config* cfg);
 gp_status gp_comm_init_local(gp_world* const* worlds, int32_t n, const gp_slab_config* cfgs);
 gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt, const float* damp3, uint32_t nsteps);
-/* bodies owned by this rank now (after migration); arrays of gp_owned_count elements, in no particular order.
- * unverified (nullable): 1 for a body the LAST step could not prove independent of unseen bodies. */
+/* bodies owned by this rank now (after migration); arrays of gp_owned_count elements, in device (slot) order.
+ * unverified (nullable): 1 for a body the LAST step could not prove independent of unseen bodies.
+ * gp_set_state_owned writes rows back (what external systems changed): row t = the t-th body of the LAST
+ * gp_download_owned, k = its count; only valid while no step has run since.  NULL arrays are left as they are. */
 gp_status gp_owned_count(gp_world* w, uint32_t* n);
 gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified);
+gp_status gp_set_state_owned(gp_world* w, uint32_t k, const float* pos3, const float* vel3, const float* acc3);
 
 /* ---- next rows: consumers of the body state right after the step ----
  * All three address bodies by upload index (single-GPU worlds only). */

@@ -77,3 +77,67 @@ def test_two_ranks_match_single_gpu(tmp_path, transport):
                         "--master-addr", "127.0.0.1", "--master-port", port, str(script)], env=env,
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+TIMEOUT_WORKER = textwrap.dedent("""
+    import os, sys, time
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from gears_b200 import scenes, slabs
+    from gears_b200.world import PhysicsWorld, GpError
+    rank, ws, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    DT = np.float32(1) / np.float32(60)
+    s = scenes.uniform(50_000, L=100.0, seed=311, rank_seed=312)
+    rep = slabs.big_static_mask(s, 4.0)
+    faces = slabs.bounds(s, ws, "balanced", replicate=rep, halo=6.0)
+    part = slabs.partition(s, faces, rep)[rank]
+    w = PhysicsWorld(device=lr, max_bodies=int(part["pos"].shape[0] * 1.5) + 65536, big_static_only=True)
+    w.upload(part)
+    slabs.comm_init(w, dist, rank, ws, faces, halo=6.0, device=torch.device("cuda", lr))
+    if rank == 0:
+        # the neighbour never steps: the bounded wait expires, the world is dead until it is uploaded again
+        w.step_async(DT, 1)
+        try:
+            w.sync()
+            raise SystemExit("the expired wait went unnoticed")
+        except GpError as e:
+            assert e.status == -9, e
+        try:
+            w.step_async(DT, 1)
+            raise SystemExit("a dead world accepted another step")
+        except GpError as e:
+            assert e.status == -9, e
+        print("TIMEOUT_OK", flush=True)
+    else:
+        time.sleep(1.5)
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)   # (no orderly tear-down of a half-dead slab pair: the point of the test is the error, not the exit)
+""")
+
+
+def test_missing_neighbour_is_a_fatal_error_not_a_hang(tmp_path):
+    """an expired peer-to-peer wait must not append a stale buffer and carry on: GP_ERR_PEER_TIMEOUT,
+    no further steps until gp_upload."""
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker_timeout.py"
+    script.write_text(TIMEOUT_WORKER.format(root=ROOT))
+    env = dict(os.environ, GP_PEER_TIMEOUT_MS="300")
+    env.pop("GP_SLAB_TRANSPORT", None)
+    # own process group + bounded wait: a worker that hangs must not survive this test and squat on a GPU
+    import signal
+    log = tmp_path / "out.log"
+    with open(log, "w") as f:
+        p = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)], env=env, stdout=f,
+                             stderr=subprocess.STDOUT, start_new_session=True)
+        try:
+            rc = p.wait(timeout=120)
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            rc = -999
+    out = log.read_text()
+    assert rc == 0 and "TIMEOUT_OK" in out, f"rc {rc}\n" + out[-4000:]

@@ -181,3 +181,54 @@ def test_slab_world_rejects_per_index_calls():
             g.worlds[0].download()
         with pytest.raises(GpError):
             g.worlds[0].step_async(DT, 1)  # in-process slabs advance together
+
+
+def test_owned_rows_can_be_written_back():
+    """gp_download_owned is in deterministic device order and gp_set_state_owned hands the same rows back (what
+    external systems changed between two steps): slab worlds fed that way equal a single world fed through
+    gp_update_dirty; a step in between invalidates the order (GP_ERR_STATE)."""
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import GpError, PhysicsWorld
+    s = scenes.uniform(40_000, L=92.0, seed=111, rank_seed=112)
+    n = s["pos"].shape[0]
+    rng = np.random.default_rng(23)
+    with PhysicsWorld() as w, LocalSlabs(s, 3, halo=6.0) as g:
+        w.upload(s)
+        for step in range(5):
+            # the same external write on both sides: new velocities / accelerations for a random tenth of the bodies
+            idx = np.sort(rng.choice(n - 1, size=n // 10, replace=False)).astype(np.uint32)
+            nv = ((rng.random((len(idx), 3)) - 0.5) * 6.0).astype(np.float32)
+            na = ((rng.random((len(idx), 3)) - 0.5) * 2.0).astype(np.float32)
+            w.update_dirty(idx, vel=nv, acc=na)
+            new_v, new_a = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+            has = np.zeros(n, bool)
+            new_v[idx], new_a[idx], has[idx] = nv, na, True
+            for sw in g.worlds:
+                ent, pos, vel = sw.download_owned()
+                ent2, _, _ = sw.download_owned()
+                assert np.array_equal(ent, ent2), "the order of gp_download_owned is deterministic"
+                vel = vel.copy()
+                acc = np.zeros_like(vel)          # (the scene's accelerations are zero until written)
+                m = has[ent]
+                vel[m] = new_v[ent[m]]
+                if step:                           # accelerations written at earlier steps persist
+                    acc = prev_acc[ent]
+                acc[m] = new_a[ent[m]]
+                sw.set_state_owned(vel=vel, acc=acc)
+            prev_acc = (prev_acc if step else np.zeros((n, 3), np.float32))
+            prev_acc[idx] = na
+            w.step(DT)
+            g.step(DT, 1)
+            g.sync()
+            ref_pos, ref_vel = w.download()
+            ent, pos, vel = g.download()
+            assert np.array_equal(ent, np.arange(n, dtype=np.uint32))
+            assert_same_bits(pos, ref_pos, f"pos after step {step + 1}")
+            assert_same_bits(vel, ref_vel, f"vel after step {step + 1}")
+        sw = g.worlds[0]
+        ent, pos, vel = sw.download_owned()
+        g.step(DT, 1)
+        g.sync()
+        with pytest.raises(GpError) as e:
+            sw.set_state_owned(vel=vel)
+        assert e.value.status == -8
