@@ -15,41 +15,55 @@ namespace gp {
 // taint spreads over components; every owned body that stays clean is bit-identical to the single-GPU result
 // (multi-GPU exactness).  n_unverified counts the owned bodies that do not stay clean.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void taint_edge(uint32_t x, uint32_t y, uint32_t* __restrict__ taint_bits, uint32_t* flag) {
-    if ((x | y) & TOPBIT) return;  // an edge through a static body carries nothing
-    const bool tx = (__ldcg(&taint_bits[x >> 5]) >> (x & 31u)) & 1u, ty = (__ldcg(&taint_bits[y >> 5]) >> (y & 31u)) & 1u;
-    if (tx == ty) return;
-    const uint32_t z = tx ? y : x;
-    atomicOr(&taint_bits[z >> 5], 1u << (z & 31u));
-    *flag = 1u;
+// Lock-free union-find over body slots (link the larger root to the smaller one, path halving), as in connected-
+// component labelling: ONE pass over the candidate edges replaces the round-by-round propagation (which cost a full
+// scan of all pairs + a grid barrier per hop of the longest tainted chain: 79 us per step at 2.3 M bodies per rank).
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+    uint32_t p = __ldcg(&parent[x]);
+    while (p != x) {
+        const uint32_t gp = __ldcg(&parent[p]);
+        if (gp != p) parent[x] = gp;  // path halving (any ancestor is a valid parent: a benign race)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_unite(uint32_t* parent, uint32_t x, uint32_t y) {
+    for (;;) {
+        x = uf_find(parent, x);
+        y = uf_find(parent, y);
+        if (x == y) return;
+        if (x < y) {
+            const uint32_t t = x;
+            x = y;
+            y = t;
+        }
+        if (atomicCAS(&parent[x], x, y) == x) return;  // x was still a root: now it hangs under the smaller root y
+    }
 }
 
-// A phase of k_contacts: clear, seed, propagate to the fixed point (a grid barrier per round), count.
-constexpr uint32_t TAINT_MAX_ROUNDS = 64;
+// A phase of k_contacts.  A body's result can only depend on its connected component of the candidate graph
+// (sweep pairs + watch pairs; an edge through a static body carries nothing), so: label the components, mark the
+// components that contain a seed, and every owned dynamic body of a marked component is unverified.
+// Scratch (free once the repair loop is over): ra.offs2 = parent, ra.dirty_bits = marked roots (left clean again).
 __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     const float4* sbox = a.sbox;
     const float *dmax = a.dmax, *reach = a.reach;
-    const uint32_t* moved_bits = a.moved_bits;
     uint32_t* taint_bits = a.taint_bits;
+    uint32_t* seed_bits = a.seed_bits;
+    uint32_t* parent = a.ra.offs2;
+    uint32_t* rootmark = a.ra.dirty_bits;
     const uint4* pairs = a.pairs;
-    const uint32_t pair_cap = a.pair_cap;
     const uint2* watch = a.watch;
     const float4* A = a.A1;
     Ctl* ctl = a.ctl;
     const uint32_t n = ctl->n;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const uint32_t words = (n + 31u) / 32u;
-    (void)moved_bits;
-    // seeds, part 1: bodies whose MARGIN pokes beyond what the neighbours mirror (K3 marked them while it had their
-    // boxes in registers; the marks are consumed here)
-    for (uint32_t wd = gtid; wd < words; wd += gsz) {
-        const uint32_t t = a.seed_bits[wd];
-        taint_bits[wd] = t;
-        if (t) a.seed_bits[wd] = 0u;
-    }
-    if (gtid == 0) ctl->taint_flag[0] = 0u, ctl->taint_flag[1] = 0u, ctl->taint_flag[2] = 0u;
-    grid.sync();
-    // seeds, part 2: bodies that moved further than their margin (all of them are on the escapee list)
+    const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap), nw = min(ctl->n_watch, a.pair_cap);
+    // ---- every body its own component; seeds, part 2: bodies that moved further than their margin (all of them are
+    //      on the escapee list) join the seeds K3 marked from the margins (part 1) ----
+    for (uint32_t i = gtid; i < n; i += gsz) parent[i] = i;
     {
         const uint32_t ne = min(__ldcg(&ctl->n_escapees), a.esc_cap);
         for (uint32_t e = gtid; e < ne; e += gsz) {
@@ -58,46 +72,84 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
             const float r = fmaxf(box_margin(lo), fmaxf(__ldcg(&reach[i]), __ldcg(&dmax[i]) * REACH_SLACK));
             const bool out_r = ctl->has_right && !(hi.x + r <= ctl->x_hi + ctl->halo);
             const bool out_l = ctl->has_left && !(lo.x - r >= ctl->x_lo - ctl->halo);
-            if (out_l || out_r) atomicOr(&taint_bits[i >> 5], 1u << (i & 31u));
+            if (out_l || out_r) atomicOr(&seed_bits[i >> 5], 1u << (i & 31u));
         }
     }
     grid.sync();
-    const uint32_t np = min(__ldcg(&ctl->n_pairs), pair_cap), nw = min(ctl->n_watch, pair_cap);
-    uint32_t it = 0;
-    bool open = true;
-    while (open && it < TAINT_MAX_ROUNDS) {
-        // three rotating flags: round `it` raises flag it%3 and clears flag (it+1)%3, which was last READ at the end
-        // of round it-2, i.e. behind the barrier of round it-1 (with two flags a fast thread would clear the flag a
-        // slow thread is still about to read, and the grid would disagree about leaving the loop)
-        uint32_t* flag = &ctl->taint_flag[it % 3u];
-        if (gtid == 0) ctl->taint_flag[(it + 1u) % 3u] = 0u;
-        for (uint32_t i = gtid; i < np; i += gsz) {
-            const uint4 r = __ldcg(&pairs[2 * (size_t)i]);
-            taint_edge(r.x, r.y, taint_bits, flag);
+    // ---- components.  Four edges per thread in flight: the first parent look-ups of all eight endpoints are issued
+    //      together, and an edge between two roots (the usual case: components are a handful of bodies) is one
+    //      compare-and-swap; the rest takes the general path.  (One edge at a time was latency-bound: three dependent
+    //      DRAM round trips per edge, 30 edges per thread.) ----
+    {
+        const uint32_t ne_total = np + nw;
+        for (uint32_t e0 = gtid; e0 < ne_total; e0 += 4u * gsz) {
+            uint32_t ex[4], ey[4], px[4], py[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + (uint32_t)u * gsz;
+                ex[u] = ey[u] = NONE;
+                if (e < np) {
+                    const uint2 r = __ldcg(reinterpret_cast<const uint2*>(&pairs[2 * (size_t)e]));
+                    ex[u] = r.x, ey[u] = r.y;
+                } else if (e < ne_total) {
+                    const uint2 r = __ldcg(&watch[e - np]);  // (activated entries are among the pairs: x == NONE)
+                    ex[u] = r.x, ey[u] = r.y;
+                }
+                if (ex[u] == NONE || ((ex[u] | ey[u]) & TOPBIT)) ex[u] = ey[u] = NONE;  // nothing to unite
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ex[u] != NONE) px[u] = __ldcg(&parent[ex[u]]), py[u] = __ldcg(&parent[ey[u]]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ex[u] == NONE) continue;
+                if (px[u] == ex[u] && py[u] == ey[u]) {  // both are roots
+                    const uint32_t hi_r = max(ex[u], ey[u]), lo_r = min(ex[u], ey[u]);
+                    if (atomicCAS(&parent[hi_r], hi_r, lo_r) == hi_r) continue;
+                }
+                uf_unite(parent, ex[u], ey[u]);
+            }
         }
-        for (uint32_t i = gtid; i < nw; i += gsz) {
-            const uint2 r = __ldcg(&watch[i]);
-            if (r.x != NONE) taint_edge(r.x, r.y, taint_bits, flag);  // (activated entries are among the pairs)
-        }
-        grid.sync();
-        open = __ldcg(flag) != 0u;
-        ++it;
     }
-    // owned dynamic bodies that are not provably independent of unseen bodies (the tainted ones are few: walk the
-    // set bits, not the bodies)
-    uint32_t c = 0;
-    if (open) {  // the propagation did not reach its fixed point within the round limit: nothing is proven
-        for (uint32_t i = gtid; i < n; i += gsz) {
-            const uint32_t f = __float_as_uint(A[i].w);
-            if (!(f & (F_GHOST | F_STATIC))) ++c;
+    grid.sync();
+    // ---- mark the components of the seeds ----
+    for (uint32_t wd = gtid; wd < words; wd += gsz) {
+        uint32_t t = __ldcg(&seed_bits[wd]);
+        while (t) {
+            const uint32_t i = wd * 32u + (uint32_t)__ffs(t) - 1u;
+            t &= t - 1u;
+            if (i < n) {
+                const uint32_t r = uf_find(parent, i);
+                atomicOr(&rootmark[r >> 5], 1u << (r & 31u));
+            }
         }
-    } else {
-        for (uint32_t wd = gtid; wd < words; wd += gsz) {
-            uint32_t t = __ldcg(&taint_bits[wd]);
-            while (t) {
-                const uint32_t i = wd * 32u + (uint32_t)__ffs(t) - 1u;
-                t &= t - 1u;
-                if (i < n && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
+    }
+    grid.sync();
+    // ---- a body is tainted iff its component is marked; count the owned dynamic ones ----
+    uint32_t c = 0;
+    for (uint32_t i0 = (gtid & ~31u); i0 < words * 32u; i0 += gsz) {  // (a warp writes one word of taint bits)
+        const uint32_t i = i0 + (threadIdx.x & 31u);
+        bool t = false;
+        if (i < n) {
+            const uint32_t r = uf_find(parent, i);
+            t = (__ldcg(&rootmark[r >> 5]) >> (r & 31u)) & 1u;
+            if (t && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, t);
+        if ((threadIdx.x & 31u) == 0u) taint_bits[i0 >> 5] = word;
+    }
+    grid.sync();
+    // ---- leave the scratch clean: the marks (only seeds' roots carry one) and the seeds themselves ----
+    for (uint32_t wd = gtid; wd < words; wd += gsz) {
+        uint32_t t = __ldcg(&seed_bits[wd]);
+        if (!t) continue;
+        seed_bits[wd] = 0u;
+        while (t) {
+            const uint32_t i = wd * 32u + (uint32_t)__ffs(t) - 1u;
+            t &= t - 1u;
+            if (i < n) {
+                const uint32_t r = uf_find(parent, i);
+                atomicAnd(&rootmark[r >> 5], ~(1u << (r & 31u)));
             }
         }
     }
