@@ -356,28 +356,30 @@ def run_ours(args) -> dict:
             w.download(hpos, hvel)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
-        # (3) a host that tracks a dirty set: per step, vel + acc of a fraction of the bodies go up through
-        # gp_update_dirty from pinned memory (asynchronous), one step follows; the state stays on the device
+        # (3) a host that tracks a dirty set: per step, the accelerations of a fraction of the bodies go
+        # up through gp_update_dirty from pinned memory (asynchronous), one step follows; the state stays on the
+        # device.  (The rows carry the values the bodies already have, so the physics -- and with it the cost of the
+        # step -- is that of the timed region above; stale velocities written every step would drive bodies into each
+        # other and measure a different scene.)
         dirty = []
         rng = np.random.default_rng(12345)
         for frac in (0.01, 0.10):
             k = max(1, int(n_local * frac))
             hidx = w.host_alloc((k,), np.uint32)
-            hv, ha = w.host_alloc((k, 3)), w.host_alloc((k, 3))
+            ha = w.host_alloc((k, 3))
             hidx[:] = np.sort(rng.choice(n_local, size=k, replace=False)).astype(np.uint32)
-            hv[:] = hvel[hidx]
-            ha[:] = 0.0
-            w.update_dirty(hidx, vel=hv, acc=ha); w.step_async(DT, 1); w.sync()
+            ha[:] = scene["acc"][hidx]
+            w.update_dirty(hidx, acc=ha); w.step_async(DT, 1); w.sync()
             torch.cuda.synchronize()
             td0 = time.perf_counter()
             for _ in range(e2e_steps):
-                w.update_dirty(hidx, vel=hv, acc=ha)
+                w.update_dirty(hidx, acc=ha)
                 w.step_async(DT, 1)
             st_d = w.sync()
             torch.cuda.synchronize()
             td1 = time.perf_counter()
             dirty.append({"dirty_fraction": frac, "value": n_local * e2e_steps / (td1 - td0), "unit": "body-steps/s",
-                          "ms_per_step": (td1 - td0) * 1e3 / e2e_steps, "h2d_bytes_per_step": 28 * k,
+                          "ms_per_step": (td1 - td0) * 1e3 / e2e_steps, "h2d_bytes_per_step": 16 * k,
                           "inexact_steps": st_d["steps_inexact"]})
         e2e = {"value": n_local * e2e_steps / (t1 - t0), "unit": "body-steps/s", "steps": e2e_steps,
                "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": 6 * 4 * n_local, "dirty_set": dirty,

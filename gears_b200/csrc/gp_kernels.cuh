@@ -6,16 +6,19 @@
 //   K2  (scan.cuh)        (new) in-place scan of the histogram = cell start table (one-pass bucket sort by cell)
 //   K3  k_scatter_cells   update_pos again on the fly + world AABB (get_rotated_aabb, physics.rs:84-135, via per-body
 //                         min/max offsets); bodies are physically re-sorted into cell order
-//   K4  k_find_pairs      CollisionBox::intersects                physics.rs:148-165  (margin-inflated superset, TMA-staged
-//                         tiles, flattened tests, per-warp staged bursts; exact snapshot test for S_snapshot)
+//   K4  k_find_pairs      CollisionBox::intersects                physics.rs:148-165  (margin-inflated superset; a warp
+//                         per tile of 32 slots, 256-bit record loads, flattened tests, per-warp staged bursts; exact
+//                         snapshot test for S_snapshot)
 //   K5  k_fill_chains / k_sort_chains / k_sort_heavy   (new) per-body contact chains in the reference's pair order
-//   K6  k_sweep           check_and_resolve_collision             physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
+//   K6  k_contacts        ONE cooperative launch (gp_contact_kernel.cuh), phases separated by grid barriers:
+//       sweep_phase       check_and_resolve_collision             physics.rs:474-499 -> intersects + resolve (physics.rs:176-299)
 //                         in the order of update_systems.rs:408-487
-//       k_requery / k_verify_watch                                (new) verification of the speculative pair set
-//       k_tiny_link / k_tiny_walk / k_tiny_exec                   (new) repair, small components: one warp re-executes a
+//       requery_phase / verify_watch_phase                        (new) verification of the speculative pair set
+//       tiny_link / tiny_walk / tiny_exec phases                  (new) repair, small components: one warp re-executes a
 //                                                                  component's pairs in (rank_a, rank_b) order on chip
-//       k_repair_local + k_sweep (list mode)                      (new) repair, large components (cooperative)
-//       k_taint_closure   (new) multi-GPU: which owned bodies are provably independent of unseen bodies
+//       repair_local_phase + sweep_phase (list mode)              (new) repair, large components
+//       taint_phase       (new) multi-GPU: which owned bodies are provably independent of unseen bodies (union-find)
+//       finish_step       (new) margin adaptation, counters, stats snapshot
 //
 // Ordering argument: the reference visits pairs (i,j), i<j in iteration order,
 // lexicographically.  Only pairs that share a DYNAMIC body interact (static bodies are never written,
