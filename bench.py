@@ -361,9 +361,15 @@ def run_ours(args) -> dict:
         # device.  (The rows carry the values the bodies already have, so the physics -- and with it the cost of the
         # step -- is that of the timed region above; stale velocities written every step would drive bodies into each
         # other and measure a different scene.)
+        # The scene is uploaded again first and warmed up like the timed region: under gravity everything in
+        # `uniform_*` is falling, steps get heavier with time (step 40 costs 2-3x step 10), and the dirty-set lines
+        # should cover the same steps as `value`.
         dirty = []
         rng = np.random.default_rng(12345)
         for frac in (0.01, 0.10):
+            w.upload(scene)
+            for _ in range(args.warmup):
+                w.step(DT)
             k = max(1, int(n_local * frac))
             hidx = w.host_alloc((k,), np.uint32)
             ha = w.host_alloc((k, 3))
@@ -371,6 +377,7 @@ def run_ours(args) -> dict:
             ha[:] = scene["acc"][hidx]
             w.update_dirty(hidx, acc=ha); w.step_async(DT, 1); w.sync()
             torch.cuda.synchronize()
+            w.kernel_times()
             td0 = time.perf_counter()
             for _ in range(e2e_steps):
                 w.update_dirty(hidx, acc=ha)
@@ -378,9 +385,11 @@ def run_ours(args) -> dict:
             st_d = w.sync()
             torch.cuda.synchronize()
             td1 = time.perf_counter()
+            ktd = w.kernel_times()
             dirty.append({"dirty_fraction": frac, "value": n_local * e2e_steps / (td1 - td0), "unit": "body-steps/s",
                           "ms_per_step": (td1 - td0) * 1e3 / e2e_steps, "h2d_bytes_per_step": 16 * k,
-                          "inexact_steps": st_d["steps_inexact"]})
+                          "inexact_steps": st_d["steps_inexact"], "steps": f"{args.warmup + 1}..{args.warmup + e2e_steps}",
+                          "step_groups_ms": {g: round(ms / max(1, ktd["steps"]), 4) for g, ms in ktd["ms"].items()}})
         e2e = {"value": n_local * e2e_steps / (t1 - t0), "unit": "body-steps/s", "steps": e2e_steps,
                "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": 6 * 4 * n_local, "dirty_set": dirty,
                "ms_per_step": (t1 - t0) * 1e3 / e2e_steps, "inexact_steps": st_f["steps_inexact"],

@@ -51,7 +51,11 @@ constexpr int WP_RANGES = 5;     // candidate slot ranges per body: 5 cell-row r
 constexpr int WP_THREADS = 128;
 constexpr int WP_WARPS = WP_THREADS / 32;
 constexpr int WP_LIST = 384;    // flattened tests per window
-constexpr int WP_STAGE = 96;    // staged records per warp: flushed above 32, one iteration adds at most 64
+#ifndef GP_WP_PER_LANE
+#define GP_WP_PER_LANE 2
+#endif
+constexpr int WP_PER_LANE = GP_WP_PER_LANE;  // tests per lane and iteration (their candidate records are in flight together)
+constexpr int WP_STAGE = 32 + 32 * WP_PER_LANE;  // staged records per warp: flushed above 32, one iteration adds 32 per test
 constexpr uint32_t WP_DENSE = 4096;  // a lane with more candidates than this: body-at-a-time walk
 
 struct WarpPairSmem {
@@ -222,17 +226,22 @@ __global__ void __launch_bounds__(WP_THREADS)
             }
             __syncwarp();
             const uint32_t nt = wend - base;
-            for (uint32_t t0 = 0; t0 < nt; t0 += 64) {
-                const uint32_t ta = t0 + lane, tb = t0 + 32 + lane;
-                const bool va = ta < nt, vb = tb < nt;
+            for (uint32_t t0 = 0; t0 < nt; t0 += 32 * WP_PER_LANE) {
                 // (entry 0 exists: nt > 0) all loads of the iteration first, then the tests
-                const uint32_t qa = sm.q[va ? ta : 0u], qb = sm.q[vb ? tb : 0u];
-                const uint32_t ja = sm.j[va ? ta : 0u], jb = sm.j[vb ? tb : 0u];
-                float4 bla, bha, blb, bhb;
-                ld_box(sbox, qa, bla, bha);
-                ld_box(sbox, qb, blb, bhb);
-                if (va) test(sm.abox[2 * ja], sm.abox[2 * ja + 1], p0 + ja, bla, bha, qa);
-                if (vb) test(sm.abox[2 * jb], sm.abox[2 * jb + 1], p0 + jb, blb, bhb, qb);
+                uint32_t qs[WP_PER_LANE], js[WP_PER_LANE];
+                bool vs[WP_PER_LANE];
+                float4 bl[WP_PER_LANE], bh[WP_PER_LANE];
+#pragma unroll
+                for (int u = 0; u < WP_PER_LANE; ++u) {
+                    const uint32_t t = t0 + 32 * u + lane;
+                    vs[u] = t < nt;
+                    qs[u] = sm.q[vs[u] ? t : 0u], js[u] = sm.j[vs[u] ? t : 0u];
+                }
+#pragma unroll
+                for (int u = 0; u < WP_PER_LANE; ++u) ld_box(sbox, qs[u], bl[u], bh[u]);
+#pragma unroll
+                for (int u = 0; u < WP_PER_LANE; ++u)
+                    if (vs[u]) test(sm.abox[2 * js[u]], sm.abox[2 * js[u] + 1], p0 + js[u], bl[u], bh[u], qs[u]);
                 flush_if_needed();
             }
             __syncwarp();  // the list is rewritten by the next window
