@@ -264,7 +264,17 @@ def run_ours(args) -> dict:
     barrier()
     sampler.start()
     t_wall0 = time.perf_counter()
-    w.step_async(DT, args.steps)
+    if world_size > 1 and args.rebalance > 0:
+        from gears_b200 import slabs as _slabs
+        done = 0
+        while done < args.steps:     # (the re-balancing calls are part of the timed region)
+            k = min(args.rebalance, args.steps - done)
+            w.step_async(DT, k)
+            done += k
+            if done < args.steps:
+                _slabs.rebalance(w)
+    else:
+        w.step_async(DT, args.steps)
     async_error = None
     try:
         st = w.sync()
@@ -275,6 +285,8 @@ def run_ours(args) -> dict:
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     ms_total = w.last_step_ms()  # CUDA events on the step stream around the K steps
+    if world_size > 1 and args.rebalance > 0:
+        ms_total = t_wall * 1e3  # (several enqueue calls with host-side collectives in between: wall clock)
     launches = w.kernel_launches() - l0
     kt = w.kernel_times()
     slab_stats = None
@@ -603,6 +615,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-grid", action="store_true", help="skip the full-N grid-oracle CPU line")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rebalance", type=int, default=0, help="multi-GPU: re-balance the slab faces every K steps (0 = never)")
     ap.add_argument("--parity-steps", type=int, default=8,
                     help="multi-GPU: steps of the slab worlds compared with a single-GPU world before the timed region")
     ap.add_argument("--halo", type=float, default=0.0,

@@ -71,7 +71,8 @@ SYMBOLS = [
     "gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_upload", "gp_set_state", "gp_update_dirty",
     "gp_update_shape", "gp_step", "gp_step_async", "gp_sync", "gp_download", "gp_pairs", "gp_damping_factors",
     "gp_host_alloc", "gp_host_free", "gp_last_step_ms", "gp_kernel_launches", "gp_kernel_times_read", "gp_comm_unique_id", "gp_comm_init",
-    "gp_comm_init_local", "gp_step_group", "gp_owned_count", "gp_download_owned", "gp_set_state_owned", "gp_instances", "gp_raycast",
+    "gp_comm_init_local", "gp_step_group", "gp_owned_count", "gp_download_owned", "gp_set_state_owned", "gp_slab_rebalance",
+    "gp_slab_rebalance_local", "gp_instances", "gp_raycast",
     "gp_obstacle_grid", "gp_cap_velocity", "gp_frame_submit", "gp_frame_wait", "gp_test_radix_sort", "gp_test_radix_sort64",
     "gp_test_exclusive_scan",
 ]
@@ -139,6 +140,10 @@ def lib():
     L.gp_download_owned.restype = C.c_int32
     L.gp_set_state_owned.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_set_state_owned.restype = C.c_int32
+    L.gp_slab_rebalance.argtypes = [vp, C.c_float, u32p]
+    L.gp_slab_rebalance.restype = C.c_int32
+    L.gp_slab_rebalance_local.argtypes = [C.POINTER(vp), C.c_int32, C.c_float, u32p]
+    L.gp_slab_rebalance_local.restype = C.c_int32
     L.gp_instances.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_instances.restype = C.c_int32
     L.gp_raycast.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]

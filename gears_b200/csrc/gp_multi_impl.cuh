@@ -21,7 +21,7 @@ typedef struct {
     char internal[128];
 } ncclUniqueId;
 typedef enum { ncclSuccess = 0 } ncclResult_t;
-typedef enum { ncclChar = 0, ncclInt32 = 2 } ncclDataType_t;
+typedef enum { ncclChar = 0, ncclInt32 = 2, ncclUint32 = 3 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
 }
 
@@ -100,6 +100,7 @@ struct gp_multi {
     cudaEvent_t ev_copied = nullptr;   // local transport: this world has copied what it needs from its neighbours
     bool verify = true;
     unsigned long long timeout_ns = 30ull * 1000000000ull;  // peer-to-peer waits (GP_PEER_TIMEOUT_MS)
+    uint32_t* rb_buf = nullptr;          // re-balancing scratch: [0..1] min/max, [2..2+64) faces, [128..128+RB_BINS) histogram
     uint32_t owned_count = 0xffffffffu;  // rows of the last gp_download_owned ...
     uint64_t owned_gen = 0;              // ... and the step count it was taken at (gp_set_state_owned checks both)
 };
@@ -120,6 +121,7 @@ static void gp_multi_destroy(gp_multi* m) {
     }
     if (m->taint_bits) cudaFree(m->taint_bits);
     if (m->seed_bits) cudaFree(m->seed_bits);
+    if (m->rb_buf) cudaFree(m->rb_buf);
     if (m->scratch) cudaFree(m->scratch);
     if (m->ev_packed) cudaEventDestroy(m->ev_packed);
     if (m->ev_copied) cudaEventDestroy(m->ev_copied);
@@ -576,5 +578,159 @@ extern "C" gp_status gp_set_state_owned(gp_world* w, uint32_t k, const float* po
     w->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(w->st));  // the host arrays may be pageable and short-lived
+    return GP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Re-balancing of the slab faces ("re-balanced every K steps").  Between two steps: histogram of
+// the owned bodies' centre x over the global x range, summed over the ranks; new faces = equal-count quantiles; a
+// face moves by at most max_shift per call, so that what changes owner in the next step is no more than a halo's
+// worth of bodies (they travel through the ordinary migration path of K1, which hands a body to the ADJACENT rank).
+// Every rank computes every face from the same summed histogram, so both sides of a face get the same bits.
+// ---------------------------------------------------------------------------------------------
+static const int RB_MAX_RANKS = 64;
+
+static gp_status rb_alloc(gp_world* w) {
+    gp_multi* m = w->multi;
+    if (!m->rb_buf) CK(dmalloc(&m->rb_buf, 128 + RB_BINS));
+    return GP_OK;
+}
+static void rb_enqueue_minmax(gp_world* w) {
+    gp_multi* m = w->multi;
+    const uint32_t init[2] = {0xffffffffu, 0u};
+    cudaMemcpyAsync(m->rb_buf, init, sizeof init, cudaMemcpyHostToDevice, w->st);
+    k_owned_minmax<<<cdiv(w->cap, 256), 256, 0, w->st>>>(w->cap, w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur], m->rb_buf);
+    w->launches++;
+}
+static void rb_enqueue_hist(gp_world* w, float x0, float inv_bin) {
+    gp_multi* m = w->multi;
+    cudaMemsetAsync(m->rb_buf + 128, 0, RB_BINS * sizeof(uint32_t), w->st);
+    k_owned_xhist<<<w->sm_count * 2, 256, 0, w->st>>>(w->cap, w->ctl, Bodies{w->B[w->cur]}, w->A[w->cur], x0, inv_bin,
+                                                       m->rb_buf + 128);
+    w->launches++;
+}
+// faces[0..nr]: faces[0] = -inf, faces[nr] = +inf.  Returns false (faces untouched) when a slab would get too narrow.
+static bool rb_new_faces(const uint32_t* hist, float x0, float binw, int nr, float* faces, float max_shift, float min_width) {
+    unsigned long long total = 0;
+    for (uint32_t b = 0; b < RB_BINS; ++b) total += hist[b];
+    if (total == 0) return false;
+    std::vector<float> out(faces, faces + nr + 1);
+    unsigned long long cum = 0;
+    uint32_t b = 0;
+    for (int r = 1; r < nr; ++r) {
+        const double target = (double)total * r / nr;
+        while (b < RB_BINS && (double)(cum + hist[b]) < target) cum += hist[b++];
+        const double frac = (b < RB_BINS && hist[b]) ? (target - (double)cum) / (double)hist[b] : 0.0;
+        float f = x0 + (float)(((double)b + frac) * (double)binw);
+        f = std::min(std::max(f, faces[r] - max_shift), faces[r] + max_shift);
+        out[r] = f;
+    }
+    for (int r = 1; r < nr; ++r) {
+        const float left = r == 1 ? -INFINITY : out[r - 1];
+        if (!(out[r] - left >= min_width)) return false;
+    }
+    for (int r = 1; r < nr; ++r) faces[r] = out[r];
+    return true;
+}
+static gp_status rb_apply(gp_world* w, float x_lo, float x_hi) {
+    gp_multi* m = w->multi;
+    m->cfg.x_lo = x_lo, m->cfg.x_hi = x_hi;
+    const float v[2] = {x_lo, x_hi};
+    CK(cudaMemcpyAsync(&w->ctl->x_lo, v, sizeof v, cudaMemcpyHostToDevice, w->st));  // (x_lo, x_hi are adjacent in Ctl)
+    CK(cudaStreamSynchronize(w->st));
+    return GP_OK;
+}
+
+extern "C" gp_status gp_slab_rebalance(gp_world* w, float max_shift, uint32_t* moved_out) {
+    if (!w) return GP_ERR_BAD_ARG;
+    if (moved_out) *moved_out = 0;
+    if (!w->multi || w->multi->local) return fail(w, GP_ERR_STATE, "gp_slab_rebalance needs a world attached with gp_comm_init");
+    gp_multi* m = w->multi;
+    const int nr = m->cfg.nranks, rank = m->cfg.rank;
+    if (nr < 2) return GP_OK;
+    if (nr > RB_MAX_RANKS) return fail(w, GP_ERR_BAD_ARG, "gp_slab_rebalance: more than %d ranks", RB_MAX_RANKS);
+    CK(cudaSetDevice(w->device));
+    gp_status s = rb_alloc(w);
+    if (s != GP_OK) return s;
+    if (!(max_shift > 0)) max_shift = 0.5f * m->cfg.halo;
+    uint32_t* d = m->rb_buf;
+    // global range of the owned centres + everybody's left face (each rank fills its own slot, the sum is exact)
+    rb_enqueue_minmax(w);
+    uint32_t slots[RB_MAX_RANKS] = {};
+    memcpy(&slots[rank], &m->cfg.x_lo, 4);
+    CK(cudaMemcpyAsync(d + 2, slots, sizeof slots, cudaMemcpyHostToDevice, w->st));
+    CKN(g_nccl.AllReduce(d, d, 1, ncclUint32, ncclMin, m->comm, w->st));
+    CKN(g_nccl.AllReduce(d + 1, d + 1, 1, ncclUint32, ncclMax, m->comm, w->st));
+    CKN(g_nccl.AllReduce(d + 2, d + 2, RB_MAX_RANKS, ncclUint32, ncclSum, m->comm, w->st));
+    uint32_t h[2 + RB_MAX_RANKS];
+    CK(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    if (h[0] == 0xffffffffu || h[1] == 0u) return GP_OK;  // nobody owns anything
+    const float gx0 = ord2f(h[0]), gx1 = ord2f(h[1]);
+    if (!(gx1 > gx0)) return GP_OK;
+    const float binw = (gx1 - gx0) / (float)RB_BINS * 1.0001f;
+    rb_enqueue_hist(w, gx0, 1.0f / binw);
+    CKN(g_nccl.AllReduce(d + 128, d + 128, RB_BINS, ncclUint32, ncclSum, m->comm, w->st));
+    std::vector<uint32_t> hist(RB_BINS);
+    CK(cudaMemcpyAsync(hist.data(), d + 128, RB_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CK(cudaStreamSynchronize(w->st));
+    float faces[RB_MAX_RANKS + 1];
+    for (int r = 0; r < nr; ++r) memcpy(&faces[r], &h[2 + r], 4);
+    faces[0] = -INFINITY, faces[nr] = INFINITY;
+    const float old_lo = faces[rank], old_hi = faces[rank + 1];
+    if (!rb_new_faces(hist.data(), gx0, binw, nr, faces, max_shift, 2.0f * m->cfg.halo)) return GP_OK;
+    if (moved_out) *moved_out = (faces[rank] != old_lo) || (faces[rank + 1] != old_hi);
+    return rb_apply(w, faces[rank], faces[rank + 1]);
+}
+
+extern "C" gp_status gp_slab_rebalance_local(gp_world* const* worlds, int32_t n, float max_shift, uint32_t* moved_out) {
+    if (!worlds || n < 1) return GP_ERR_BAD_ARG;
+    if (moved_out) *moved_out = 0;
+    if (n > RB_MAX_RANKS) return GP_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i)
+        if (!worlds[i] || !worlds[i]->multi || !worlds[i]->multi->local)
+            return worlds[i] ? fail(worlds[i], GP_ERR_STATE, "gp_slab_rebalance_local needs worlds set up by gp_comm_init_local") : GP_ERR_BAD_ARG;
+    if (n < 2) return GP_OK;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int i = 0; i < n; ++i) {
+        gp_world* w = worlds[i];
+        CK(cudaSetDevice(w->device));
+        gp_status s = rb_alloc(w);
+        if (s != GP_OK) return s;
+        rb_enqueue_minmax(w);
+        uint32_t mm[2];
+        CK(cudaMemcpyAsync(mm, w->multi->rb_buf, sizeof mm, cudaMemcpyDeviceToHost, w->st));
+        CK(cudaStreamSynchronize(w->st));
+        lo = std::min(lo, mm[0]), hi = std::max(hi, mm[1]);
+    }
+    if (lo == 0xffffffffu || hi == 0u) return GP_OK;
+    const float gx0 = ord2f(lo), gx1 = ord2f(hi);
+    if (!(gx1 > gx0)) return GP_OK;
+    const float binw = (gx1 - gx0) / (float)RB_BINS * 1.0001f;
+    std::vector<uint32_t> hist(RB_BINS, 0u), part(RB_BINS);
+    for (int i = 0; i < n; ++i) {
+        gp_world* w = worlds[i];
+        CK(cudaSetDevice(w->device));
+        rb_enqueue_hist(w, gx0, 1.0f / binw);
+        CK(cudaMemcpyAsync(part.data(), w->multi->rb_buf + 128, RB_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+        CK(cudaStreamSynchronize(w->st));
+        for (uint32_t b = 0; b < RB_BINS; ++b) hist[b] += part[b];
+    }
+    float faces[RB_MAX_RANKS + 1];
+    for (int r = 0; r < n; ++r) faces[r] = worlds[r]->multi->cfg.x_lo;
+    faces[0] = -INFINITY, faces[n] = INFINITY;
+    float max_halo = 0.f;
+    for (int i = 0; i < n; ++i) max_halo = std::max(max_halo, worlds[i]->multi->cfg.halo);
+    if (!(max_shift > 0)) max_shift = 0.5f * max_halo;
+    std::vector<float> old(faces, faces + n + 1);
+    if (!rb_new_faces(hist.data(), gx0, binw, n, faces, max_shift, 2.0f * max_halo)) return GP_OK;
+    for (int i = 0; i < n; ++i) {
+        gp_world* w = worlds[i];
+        if (faces[i] == old[i] && faces[i + 1] == old[i + 1]) continue;
+        if (moved_out) *moved_out = 1;
+        CK(cudaSetDevice(w->device));
+        gp_status s = rb_apply(w, faces[i], faces[i + 1]);
+        if (s != GP_OK) return s;
+    }
     return GP_OK;
 }

@@ -211,6 +211,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- re-balancing of the slab faces (gp_slab_rebalance): where are the bodies this rank owns? ----
+constexpr uint32_t RB_BINS = 4096;
+__device__ __forceinline__ bool rb_owned_centre(const Ctl* ctl, const Bodies B, const float4* A, uint32_t i, float& cx) {
+    if (i >= ctl->n_in) return false;  // between steps n_in = the live bodies of the last step
+    const uint32_t f = __float_as_uint(A[i].w);
+    if (f & (F_GHOST | F_BIG)) return false;  // halo copies belong to the neighbour; big statics are replicated
+    const float4 p = B.P(i), lo = B.Lo(i), hi = B.Hi(i);
+    cx = ((lo.x + p.x) + (hi.x + p.x)) * 0.5f;  // the very expression of the ownership test in k_keys<true>
+    return isfinite(cx);
+}
+// minmax[0] = min, [1] = max of the owned centres, as order-preserving uints (init: 0xffffffff, 0)
+__global__ void __launch_bounds__(256)
+    k_owned_minmax(uint32_t cap, const Ctl* ctl, const Bodies B, const float4* __restrict__ A, uint32_t* minmax) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cx = 0.f;
+    const bool own = i < cap && rb_owned_centre(ctl, B, A, i, cx);
+    float lo = own ? cx : 3.0e38f, hi = own ? cx : -3.0e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo < 3.0e38f) atomicMin(&minmax[0], f2ord(lo));
+        if (hi > -3.0e38f) atomicMax(&minmax[1], f2ord(hi));
+    }
+}
+// histogram of the owned centres over RB_BINS equal bins of [x0, x0 + RB_BINS / inv_bin)
+__global__ void __launch_bounds__(256)
+    k_owned_xhist(uint32_t cap, const Ctl* ctl, const Bodies B, const float4* __restrict__ A, float x0, float inv_bin,
+                  uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RB_BINS];
+    for (uint32_t b = threadIdx.x; b < RB_BINS; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        float cx;
+        if (!rb_owned_centre(ctl, B, A, i, cx)) continue;
+        const int b = min(max(__float2int_rd((cx - x0) * inv_bin), 0), (int)RB_BINS - 1);
+        atomicAdd(&sh[b], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < RB_BINS; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
 // gp_comm_init: body ids become the caller's global entity ids; count what the faces would send right now
 __global__ void k_slab_prepare(uint32_t n, const Bodies B, const float4* __restrict__ A,
                                const uint32_t* __restrict__ entity, uint32_t* __restrict__ counts /*[3]: L, R, dyn big*/,

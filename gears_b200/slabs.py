@@ -180,6 +180,22 @@ class LocalSlabs:
     def sync(self) -> list[dict]:
         return [w.sync() for w in self.worlds]
 
+    def rebalance(self, max_shift: float = 0.0) -> bool:
+        """Move the faces towards equal owned counts (between two steps); True if a face moved."""
+        moved = C.c_uint32()
+        st = self.lib.gp_slab_rebalance_local(self._hs, self.n, C.c_float(max_shift), C.byref(moved))
+        if st < 0:
+            raise GpError(st, "; ".join(self.lib.gp_last_error(w._h).decode() for w in self.worlds))
+        return bool(moved.value)
+
+    def owned_counts(self) -> list[int]:
+        out = []
+        for w in self.worlds:
+            n = C.c_uint32()
+            w._check(self.lib.gp_owned_count(w._h, C.byref(n)))
+            out.append(int(n.value))
+        return out
+
     def download(self):
         """(entity, pos, vel) of all owned bodies, sorted by entity id."""
         es, ps, vs, us = [], [], [], []
@@ -200,6 +216,15 @@ class LocalSlabs:
 
     def __exit__(self, *a):
         self.close()
+
+
+def rebalance(world: PhysicsWorld, max_shift: float = 0.0) -> bool:
+    """One process per GPU: COLLECTIVE re-balancing of the slab faces (every rank calls it at the same step)."""
+    moved = C.c_uint32()
+    st = capi.lib().gp_slab_rebalance(world._h, C.c_float(max_shift), C.byref(moved))
+    if st < 0:
+        raise GpError(st, capi.lib().gp_last_error(world._h).decode())
+    return bool(moved.value)
 
 
 def comm_init(world: PhysicsWorld, dist, rank: int, nranks: int, faces: np.ndarray, halo: float = 0.0,

@@ -243,6 +243,13 @@ gp_status gp_step_group(gp_world* const* worlds, int32_t n, float dt, const floa
 gp_status gp_owned_count(gp_world* w, uint32_t* n);
 gp_status gp_download_owned(gp_world* w, uint32_t* entity, float* pos3, float* vel3, uint8_t* unverified);
 gp_status gp_set_state_owned(gp_world* w, uint32_t k, const float* pos3, const float* vel3, const float* acc3);
+/* Re-balance the slab faces between two steps: equal-count quantiles of the owned bodies'
+ * centre x over all ranks; a face moves by at most max_shift per call (<= 0: half the halo), so that the bodies that
+ * change owner in the next step fit the ordinary migration path; a call that would make a slab narrower than twice
+ * the halo changes nothing.  gp_slab_rebalance is COLLECTIVE (every rank of the communicator calls it at the same
+ * step); *moved_out (nullable) = 1 if one of this rank's faces moved. */
+gp_status gp_slab_rebalance(gp_world* w, float max_shift, uint32_t* moved_out);
+gp_status gp_slab_rebalance_local(gp_world* const* worlds, int32_t n, float max_shift, uint32_t* moved_out);
 
 /* ---- next rows: consumers of the body state right after the step ----
  * All three address bodies by upload index (single-GPU worlds only). */

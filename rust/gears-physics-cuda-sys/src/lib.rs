@@ -153,6 +153,8 @@ unsafe extern "C" {
         bitmap: *mut u32, bounds_out: *mut i32,
     ) -> gp_status;
 
+    pub fn gp_slab_rebalance(w: *mut gp_world, max_shift: f32, moved_out: *mut u32) -> gp_status;
+    pub fn gp_slab_rebalance_local(worlds: *const *mut gp_world, n: i32, max_shift: f32, moved_out: *mut u32) -> gp_status;
     pub fn gp_set_state_owned(w: *mut gp_world, k: u32, pos3: *const f32, vel3: *const f32, acc3: *const f32) -> gp_status;
 
     // RigidBody::cap_velocity (physics.rs:506-520) for the bodies idx[0..k) (null: all)

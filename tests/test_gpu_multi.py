@@ -79,6 +79,65 @@ def test_two_ranks_match_single_gpu(tmp_path, transport):
     assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+REBALANCE_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from gears_b200 import scenes, slabs
+    from gears_b200.world import PhysicsWorld
+    rank, ws, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    DT = np.float32(1) / np.float32(60)
+    n = 60_000
+    s = scenes.uniform(n, L=106.0, seed=321, rank_seed=322, floor=False)
+    s["acc"][:] = (30.0, 0.0, 0.0)     # everything drifts along +x: fixed faces would empty rank 0
+    faces = slabs.bounds(s, ws, "count", halo=6.0)
+    part = slabs.partition(s, faces, np.zeros(n, bool))[rank]
+    w = PhysicsWorld(device=lr, max_bodies=n + 65536, big_static_only=True)
+    w.upload(part)
+    slabs.comm_init(w, dist, rank, ws, faces, halo=6.0, device=torch.device("cuda", lr))
+    moved = False
+    for k in range(12):
+        w.step_async(DT, 5)
+        st = w.sync()
+        moved |= slabs.rebalance(w)        # collective: NCCL all-reduces of the range, the faces and the histogram
+    ent, pos, vel = w.download_owned()
+    out = [None] * ws if rank == 0 else None
+    dist.gather_object((ent, pos, vel, st["steps_inexact"], moved), out, dst=0)
+    if rank == 0:
+        e = np.concatenate([o[0] for o in out]); p = np.concatenate([o[1] for o in out]); v = np.concatenate([o[2] for o in out])
+        order = np.argsort(e, kind="stable")
+        assert np.array_equal(e[order], np.arange(n, dtype=np.uint32)), "every body owned exactly once"
+        assert sum(o[3] for o in out) == 0 and any(o[4] for o in out)
+        counts = np.array([len(o[0]) for o in out], np.float64)
+        assert (counts.max() - counts.min()) / counts.mean() < 0.10, counts
+        with PhysicsWorld(device=lr) as ref:
+            ref.upload(s)
+            ref.step_async(DT, 60)
+            assert ref.sync()["steps_inexact"] == 0
+            rp, rv = ref.download()
+        assert np.array_equal(p[order].view(np.uint32), rp.view(np.uint32)), "positions differ from the single-GPU run"
+        assert np.array_equal(v[order].view(np.uint32), rv.view(np.uint32)), "velocities differ from the single-GPU run"
+        print("REBALANCE_OK", counts)
+    w.close()
+    dist.destroy_process_group()
+""")
+
+
+def test_two_ranks_rebalance_a_drifting_scene(tmp_path):
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker_rebalance.py"
+    script.write_text(REBALANCE_WORKER.format(root=ROOT))
+    env = dict(os.environ)
+    env.pop("GP_SLAB_TRANSPORT", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29734", str(script)], env=env,
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "REBALANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 TIMEOUT_WORKER = textwrap.dedent("""
     import os, sys, time
     sys.path.insert(0, {root!r})

@@ -232,3 +232,47 @@ def test_owned_rows_can_be_written_back():
         with pytest.raises(GpError) as e:
             sw.set_state_owned(vel=vel)
         assert e.value.status == -8
+
+
+def test_rebalancing_keeps_a_drifting_scene_even_and_exact():
+    """SURVEY 8e "re-balanced every K steps": every body is pushed along +x, so with fixed faces the left slab
+    empties; gp_slab_rebalance_local every 5 steps keeps the owned counts within 10 % of each other while the result
+    stays bit-identical to the single world (bodies change owner through the ordinary migration path).  No floor: a
+    layer of bodies resting on it is one connected component, which the exactness proof flags wholesale."""
+    from gears_b200.slabs import LocalSlabs
+    from gears_b200.world import PhysicsWorld
+    n = 30_000
+    s = scenes.uniform(n, L=84.0, seed=121, rank_seed=122, floor=False)
+    s["acc"][:] = (30.0, 0.0, 0.0)            # steady drift of ~19 units/s (physics.rs:405-462: damped, then + a*dt)
+    nranks, steps, every = 3, 60, 5
+
+    def spread(counts):
+        c = np.asarray(counts, np.float64)
+        return (c.max() - c.min()) / c.mean()
+
+    with LocalSlabs(s, nranks, halo=6.0) as fixed:
+        fixed.step(DT, steps)
+        fixed.sync()
+        drift_spread = spread(fixed.owned_counts())
+    with PhysicsWorld() as w, LocalSlabs(s, nranks, halo=6.0) as g:
+        w.upload(s)
+        moved_any, unverified = False, 0
+        for k in range(steps // every):
+            w.step_async(DT, every)
+            g.step(DT, every)
+            for st in g.sync():
+                assert st["steps_inexact"] == 0
+                unverified += st["unverified_total"]
+            if k % 4 == 3:
+                ref_pos, ref_vel = w.download()
+                ent, pos, vel = g.download()
+                assert np.array_equal(ent, np.arange(n, dtype=np.uint32)), "every body owned exactly once"
+                assert_same_bits(pos, ref_pos, f"pos after step {every * (k + 1)}")
+                assert_same_bits(vel, ref_vel, f"vel after step {every * (k + 1)}")
+            moved_any |= g.rebalance()
+        assert w.sync()["steps_inexact"] == 0
+        balanced_spread = spread(g.owned_counts())
+    assert moved_any
+    assert unverified == 0
+    assert drift_spread > 0.3, f"the scene must drift enough to unbalance fixed faces (spread {drift_spread:.2f})"
+    assert balanced_spread < 0.10, f"owned counts differ by {balanced_spread:.2%} of the mean after re-balancing"
