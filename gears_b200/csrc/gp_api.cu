@@ -789,6 +789,7 @@ static inline uint32_t n_bound(const gp_world* w) { return w->multi ? w->cap : w
 // Slab worlds: where the per-step exactness proof keeps its marks (gp_multi_impl.cuh)
 static uint32_t* gp_multi_taint_bits(gp_multi* m);
 static uint32_t* gp_multi_seed_bits(gp_multi* m);
+static uint32_t* gp_multi_uf_parent(gp_multi* m);
 
 // K6: the whole contact phase -- ordered sweep, verification of the speculative pair set, repair rounds while they
 // are needed, the slab exactness proof, end of step -- is ONE cooperative launch (gp_contact_kernel.cuh).
@@ -812,6 +813,7 @@ static gp_status enqueue_contacts(gp_world* w, float dt, const float* d, uint32_
     a.rec_cap = (uint32_t)std::min<size_t>(w->pair_cap * 4 / TINY_REC, 1u << 20);
     a.taint_bits = w->multi ? gp_multi_taint_bits(w->multi) : nullptr;
     a.seed_bits = w->multi ? gp_multi_seed_bits(w->multi) : nullptr;
+    a.uf_parent = w->multi ? gp_multi_uf_parent(w->multi) : nullptr;
     a.dt = dt, a.d16 = d[0], a.d18 = d[1], a.d35 = d[2];
     a.start_phase = start_phase, a.max_rounds = max_rounds, a.tiny = w->tiny_repair ? 1u : 0u, a.latch = latch;
     a.profile = w->fine ? 1u : 0u;
@@ -910,7 +912,8 @@ static gp_status enqueue_phase_b(gp_world* w, float dt, const float* damp3, int 
                                                        w->sbox, w->chain_cnt, w->perm, w->dmax, w->reach, w->moved_bits,
                                                        w->esc_bits, w->xhead, w->LB, w->ctl,
                                                        (w->track_slots && !w->multi) ? w->slot_of : nullptr,
-                                                       w->multi ? gp_multi_seed_bits(w->multi) : nullptr, dt, d[0], d[1], d[2]);
+                                                       w->multi ? gp_multi_seed_bits(w->multi) : nullptr,
+                                                       w->multi ? gp_multi_uf_parent(w->multi) : nullptr, dt, d[0], d[1], d[2]);
         w->launches += 1;
         fine_mark(w, "k_scatter_cells");
         prof_mark(w, 4);

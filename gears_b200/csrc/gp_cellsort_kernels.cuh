@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(256)
                     uint32_t* __restrict__ esc_bits, uint32_t* __restrict__ xhead, const uint32_t* __restrict__ LB,
                     Ctl* ctl, uint32_t* __restrict__ slot_of /* nullable: body id -> slot, kept for dirty-set updates */,
                     uint32_t* __restrict__ seed_bits /* nullable (slab worlds): seeds of the exactness proof */,
+                    uint32_t* __restrict__ uf_parent /* nullable (slab worlds): the proof's union-find, reset here */,
                     float dt, float d16, float d18, float d35) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncells = ctl->grid.ncells;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256)
     // slots [0, n) are a prefix of the indices handled here, and a coalesced store costs a fraction of a scattered
     // 4-byte one (partial sectors).  xhead: no pair appended after K4 touches this body yet (k_tiny_link).
     chain_cnt[i] = 0, dmax[i] = 0.0f, reach[i] = 0.0f, xhead[i] = NONE;
+    if (uf_parent) uf_parent[i] = i;  // every body its own component (saves the proof a pass and a grid barrier)
     if ((i & 31u) == 0u) moved_bits[i >> 5] = 0u, esc_bits[i >> 5] = 0u;
     const uint32_t k = key[i];
     if (k > ncells) return;  // dead (a ghost of the last step, a body that migrated away): dropped here

@@ -209,6 +209,7 @@ struct ContactArgs {
     uint32_t rec_cap;
     uint32_t* taint_bits;        // slab worlds: per-step exactness proof (nullptr otherwise)
     uint32_t* seed_bits;         // ... and the seeds K3 marked for it
+    uint32_t* uf_parent;         // ... and its union-find forest, reset by K3 (parent[i] = i)
     float dt, d16, d18, d35;
     uint32_t start_phase;        // 0: sweep first; 1: continue the repair loop
     uint32_t max_rounds;         // repair rounds before the step is declared still-growing (SF_MARGIN)

@@ -95,6 +95,7 @@ struct gp_multi {
     uint32_t proposal = 0;         // records per face buffer this rank asks for
     uint32_t* taint_bits = nullptr;
     uint32_t* seed_bits = nullptr;  // marked by K3, consumed (and cleared) by the proof
+    uint32_t* uf_parent = nullptr;  // the proof's union-find forest (reset by K3)
     uint32_t* scratch = nullptr;   // [0] taint gate, [1..3] prepare counts, [4] compact counter
     cudaEvent_t ev_packed = nullptr;   // local transport: this world's send buffers are ready
     cudaEvent_t ev_copied = nullptr;   // local transport: this world has copied what it needs from its neighbours
@@ -121,6 +122,7 @@ static void gp_multi_destroy(gp_multi* m) {
     }
     if (m->taint_bits) cudaFree(m->taint_bits);
     if (m->seed_bits) cudaFree(m->seed_bits);
+    if (m->uf_parent) cudaFree(m->uf_parent);
     if (m->rb_buf) cudaFree(m->rb_buf);
     if (m->scratch) cudaFree(m->scratch);
     if (m->ev_packed) cudaEventDestroy(m->ev_packed);
@@ -199,6 +201,7 @@ static gp_status gp_multi_enqueue_exchange(gp_multi* m) {
 
 static uint32_t* gp_multi_taint_bits(gp_multi* m) { return m->verify ? m->taint_bits : nullptr; }
 static uint32_t* gp_multi_seed_bits(gp_multi* m) { return m->verify ? m->seed_bits : nullptr; }
+static uint32_t* gp_multi_uf_parent(gp_multi* m) { return m->verify ? m->uf_parent : nullptr; }
 
 // common part of gp_comm_init / gp_comm_init_local
 static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) {
@@ -233,7 +236,7 @@ static gp_status slab_setup(gp_world* w, const gp_slab_config* cfg, bool local) 
     gp_status rs = GP_OK;
     do {
         if (dmalloc(&m->scratch, 16) || dmalloc(&m->taint_bits, (size_t)w->cap / 32 + 1) ||
-            dmalloc(&m->seed_bits, (size_t)w->cap / 32 + 1) ||
+            dmalloc(&m->seed_bits, (size_t)w->cap / 32 + 1) || dmalloc(&m->uf_parent, (size_t)w->cap) ||
             cudaMemsetAsync(m->seed_bits, 0, sizeof(uint32_t) * ((size_t)w->cap / 32 + 1), w->st) != cudaSuccess ||
             cudaEventCreateWithFlags(&m->ev_packed, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&m->ev_copied, cudaEventDisableTiming) != cudaSuccess) {

@@ -51,7 +51,7 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     const float *dmax = a.dmax, *reach = a.reach;
     uint32_t* taint_bits = a.taint_bits;
     uint32_t* seed_bits = a.seed_bits;
-    uint32_t* parent = a.ra.offs2;
+    uint32_t* parent = a.uf_parent;  // K3 left every body its own component
     uint32_t* rootmark = a.ra.dirty_bits;
     const uint4* pairs = a.pairs;
     const uint2* watch = a.watch;
@@ -61,9 +61,8 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const uint32_t words = (n + 31u) / 32u;
     const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap), nw = min(ctl->n_watch, a.pair_cap);
-    // ---- every body its own component; seeds, part 2: bodies that moved further than their margin (all of them are
-    //      on the escapee list) join the seeds K3 marked from the margins (part 1) ----
-    for (uint32_t i = gtid; i < n; i += gsz) parent[i] = i;
+    // ---- seeds, part 2: bodies that moved further than their margin (all of them are on the escapee list) join the
+    //      seeds K3 marked from the margins (part 1); nothing reads the seeds before the barrier after the unions ----
     {
         const uint32_t ne = min(__ldcg(&ctl->n_escapees), a.esc_cap);
         for (uint32_t e = gtid; e < ne; e += gsz) {
@@ -75,7 +74,6 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
             if (out_l || out_r) atomicOr(&seed_bits[i >> 5], 1u << (i & 31u));
         }
     }
-    grid.sync();
     // ---- components (one edge at a time per thread: a variant with four edges in flight and a compare-and-swap fast
     //      path for root-root edges was measured SLOWER, 0.31 against 0.20 ms at 8.4 M bodies per rank) ----
     for (uint32_t i = gtid; i < np; i += gsz) {
@@ -103,16 +101,30 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     grid.sync();
     // ---- a body is tainted iff its component is marked; count the owned dynamic ones ----
     uint32_t c = 0;
-    for (uint32_t i0 = (gtid & ~31u); i0 < words * 32u; i0 += gsz) {  // (a warp writes one word of taint bits)
-        const uint32_t i = i0 + (threadIdx.x & 31u);
-        bool t = false;
-        if (i < n) {
-            const uint32_t r = uf_find(parent, i);
-            t = (__ldcg(&rootmark[r >> 5]) >> (r & 31u)) & 1u;
-            if (t && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
+    // (a warp writes four words of taint bits per iteration: the four parent look-ups of a lane are in flight together,
+    // then the four mark look-ups -- one body at a time per lane left the pass latency-bound)
+    for (uint32_t i0 = (gtid & ~31u) * 4u; i0 < words * 32u; i0 += gsz * 4u) {
+        uint32_t par[4], root[4], mark[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
+            par[u] = i < n ? __ldcg(&parent[i]) : NONE;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, t);
-        if ((threadIdx.x & 31u) == 0u) taint_bits[i0 >> 5] = word;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
+            root[u] = par[u] == NONE ? NONE : (par[u] == i ? i : uf_find(parent, par[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mark[u] = root[u] == NONE ? 0u : __ldcg(&rootmark[root[u] >> 5]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
+            const bool t = root[u] != NONE && ((mark[u] >> (root[u] & 31u)) & 1u);
+            if (t && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
+            const uint32_t word = __ballot_sync(0xffffffffu, t);
+            if ((threadIdx.x & 31u) == 0u && i0 + 32u * u < words * 32u) taint_bits[(i0 >> 5) + u] = word;
+        }
     }
     grid.sync();
     // ---- leave the scratch clean: the marks (only seeds' roots carry one) and the seeds themselves ----
