@@ -129,14 +129,17 @@ __device__ __forceinline__ void sweep_items(const ContactArgs& a, FrontierStage&
 }
 
 // LIST: repair sweep over the pairs the component-local repair collected (ra.dpairs); SKIP: see above
+// Returns the number of pairs whose edges (with the whole watch list) the idle CTAs united for the slab proof while
+// CTA 0 ran tail levels (first sweep of a slab world only; 0: none).
 template <bool LIST, bool SKIP>
-__device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_group& grid, PhaseClock& pc) {
+__device__ uint32_t sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_group& grid, PhaseClock& pc) {
     Ctl* ctl = a.ctl;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     if (threadIdx.x == 0) fs.cnt = 0, fs.ecnt = 0;
     __syncthreads();
     const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap);
     SweepAcc acc;
+    uint32_t united = 0;
     // Level 0 = the pairs at the head of all their chains, found by one coalesced scan of the link records.  First
     // sweep: two thirds of them are linked to nothing and five in six carry no S_snapshot flag -- with the sweep
     // shortcut such a pair needs neither a test nor a wake-up, so it is not even listed.
@@ -184,7 +187,11 @@ __device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_gr
                     ctl->sweep_round = r;
                     ctl->dbg_tail_rounds += r - rounds;
                 }
+            } else if (!LIST && a.taint_bits && united == 0u) {
+                proof_unions(a, 0u, np, true, (blockIdx.x - 1u) * blockDim.x + threadIdx.x,
+                             (gridDim.x - 1u) * blockDim.x);
             }
+            if (!LIST && a.taint_bits && gridDim.x > 1u) united = np;  // (uniform: every CTA takes this path)
             grid.sync();
             pc.stamp(ctl, LIST ? 8 : 2);
             rounds = __ldcg(&ctl->sweep_round);
@@ -232,6 +239,7 @@ __device__ void sweep_phase(const ContactArgs& a, FrontierStage& fs, cg::grid_gr
         if (!LIST) ctl->n_pairs_k4 = np;
         ctl->frontier_n[0] = ctl->frontier_n[1] = ctl->frontier_n[2] = 0;
     }
+    return united;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,8 +262,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_contacts(const ContactArgs 
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     PhaseClock pc;
     pc.start(a.profile != 0);
+    uint32_t united = 0;
     if (a.start_phase == 0) {
-        sweep_phase<false, true>(a, sm.fs, grid, pc);
+        united = sweep_phase<false, true>(a, sm.fs, grid, pc);
         grid.sync();
         pc.stamp(ctl, 3);
         requery_phase(a, sm.rq[threadIdx.x >> 5]);
@@ -304,9 +313,10 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_contacts(const ContactArgs 
         ++round;
     }
     if (a.taint_bits) {
-        taint_phase(a, grid);
+        taint_phase(a, grid, united);
         grid.sync();
         pc.stamp(ctl, 11);
+        taint_cleanup(a);
     }
     if (gtid == 0) finish_step(ctl, a.ctl_snap, a.latch);
 }

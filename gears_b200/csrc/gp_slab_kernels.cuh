@@ -42,25 +42,46 @@ __device__ __forceinline__ void uf_unite(uint32_t* parent, uint32_t x, uint32_t 
     }
 }
 
+// The components of the candidate graph: sweep pairs [p0, p1) and (optionally) the watch list, spread over `nthr`
+// threads.  The edges do not depend on the sweep, so the CTAs that idle while CTA 0 runs the tail levels of the first
+// sweep do this part of the proof there (pairs appended later by the verification are added by taint_phase).
+// One edge at a time per thread: a variant with four edges in flight and a compare-and-swap fast path for root-root
+// edges was measured SLOWER, 0.31 against 0.20 ms at 8.4 M bodies per rank.
+__device__ void proof_unions(const ContactArgs& a, uint32_t p0, uint32_t p1, bool with_watch, uint32_t tid,
+                             uint32_t nthr) {
+    uint32_t* parent = a.uf_parent;
+    for (uint32_t i = p0 + tid; i < p1; i += nthr) {
+        const uint2 r = __ldcg(reinterpret_cast<const uint2*>(&a.pairs[2 * (size_t)i]));  // (x, y): never rewritten
+        if (!((r.x | r.y) & TOPBIT)) uf_unite(parent, r.x, r.y);
+    }
+    if (!with_watch) return;
+    const uint32_t nw = min(a.ctl->n_watch, a.pair_cap);
+    for (uint32_t i = tid; i < nw; i += nthr) {
+        const uint2 r = __ldcg(&a.watch[i]);
+        // (an entry the verification activates later is then among the pairs as well: the same edge twice)
+        if (r.x != NONE && !((r.x | r.y) & TOPBIT)) uf_unite(parent, r.x, r.y);
+    }
+}
+
 // A phase of k_contacts.  A body's result can only depend on its connected component of the candidate graph
 // (sweep pairs + watch pairs; an edge through a static body carries nothing), so: label the components, mark the
 // components that contain a seed, and every owned dynamic body of a marked component is unverified.
-// Scratch (free once the repair loop is over): ra.offs2 = parent, ra.dirty_bits = marked roots (left clean again).
-__device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
+// uf_parent = the forest (K3 left every body its own component); scratch, free once the repair loop is over:
+// ra.dirty_bits = marked roots (left clean again).  pairs_done: the pairs [0, pairs_done) and the watch list were
+// united during the first sweep's tail (0: nothing was).
+__device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid, uint32_t pairs_done) {
     const float4* sbox = a.sbox;
     const float *dmax = a.dmax, *reach = a.reach;
     uint32_t* taint_bits = a.taint_bits;
     uint32_t* seed_bits = a.seed_bits;
     uint32_t* parent = a.uf_parent;  // K3 left every body its own component
     uint32_t* rootmark = a.ra.dirty_bits;
-    const uint4* pairs = a.pairs;
-    const uint2* watch = a.watch;
     const float4* A = a.A1;
     Ctl* ctl = a.ctl;
     const uint32_t n = ctl->n;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const uint32_t words = (n + 31u) / 32u;
-    const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap), nw = min(ctl->n_watch, a.pair_cap);
+    const uint32_t np = min(__ldcg(&ctl->n_pairs), a.pair_cap);
     // ---- seeds, part 2: bodies that moved further than their margin (all of them are on the escapee list) join the
     //      seeds K3 marked from the margins (part 1); nothing reads the seeds before the barrier after the unions ----
     {
@@ -74,17 +95,8 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
             if (out_l || out_r) atomicOr(&seed_bits[i >> 5], 1u << (i & 31u));
         }
     }
-    // ---- components (one edge at a time per thread: a variant with four edges in flight and a compare-and-swap fast
-    //      path for root-root edges was measured SLOWER, 0.31 against 0.20 ms at 8.4 M bodies per rank) ----
-    for (uint32_t i = gtid; i < np; i += gsz) {
-        const uint4 r = __ldcg(&pairs[2 * (size_t)i]);
-        if (!((r.x | r.y) & TOPBIT)) uf_unite(parent, r.x, r.y);
-    }
-    for (uint32_t i = gtid; i < nw; i += gsz) {
-        const uint2 r = __ldcg(&watch[i]);
-        // (activated entries are among the pairs)
-        if (r.x != NONE && !((r.x | r.y) & TOPBIT)) uf_unite(parent, r.x, r.y);
-    }
+    // ---- components: the edges the tail of the first sweep has not seen ----
+    proof_unions(a, min(pairs_done, np), np, pairs_done == 0u, gtid, gsz);
     grid.sync();
     // ---- mark the components of the seeds ----
     for (uint32_t wd = gtid; wd < words; wd += gsz) {
@@ -101,24 +113,25 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
     grid.sync();
     // ---- a body is tainted iff its component is marked; count the owned dynamic ones ----
     uint32_t c = 0;
-    // (a warp writes four words of taint bits per iteration: the four parent look-ups of a lane are in flight together,
-    // then the four mark look-ups -- one body at a time per lane left the pass latency-bound)
-    for (uint32_t i0 = (gtid & ~31u) * 4u; i0 < words * 32u; i0 += gsz * 4u) {
-        uint32_t par[4], root[4], mark[4];
+    // (a warp writes TW words of taint bits per iteration: the TW parent look-ups of a lane are in flight together,
+    // then the TW mark look-ups -- one body at a time per lane left the pass latency-bound)
+    constexpr int TW = 8;
+    for (uint32_t i0 = (gtid & ~31u) * TW; i0 < words * 32u; i0 += gsz * TW) {
+        uint32_t par[TW], root[TW], mark[TW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < TW; ++u) {
             const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
             par[u] = i < n ? __ldcg(&parent[i]) : NONE;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < TW; ++u) {
             const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
             root[u] = par[u] == NONE ? NONE : (par[u] == i ? i : uf_find(parent, par[u]));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mark[u] = root[u] == NONE ? 0u : __ldcg(&rootmark[root[u] >> 5]);
+        for (int u = 0; u < TW; ++u) mark[u] = root[u] == NONE ? 0u : __ldcg(&rootmark[root[u] >> 5]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < TW; ++u) {
             const uint32_t i = i0 + 32u * u + (threadIdx.x & 31u);
             const bool t = root[u] != NONE && ((mark[u] >> (root[u] & 31u)) & 1u);
             if (t && !(__float_as_uint(A[i].w) & (F_GHOST | F_STATIC))) ++c;
@@ -126,23 +139,19 @@ __device__ void taint_phase(const ContactArgs& a, cg::grid_group& grid) {
             if ((threadIdx.x & 31u) == 0u && i0 + 32u * u < words * 32u) taint_bits[(i0 >> 5) + u] = word;
         }
     }
-    grid.sync();
-    // ---- leave the scratch clean: the marks (only seeds' roots carry one) and the seeds themselves ----
-    for (uint32_t wd = gtid; wd < words; wd += gsz) {
-        uint32_t t = __ldcg(&seed_bits[wd]);
-        if (!t) continue;
-        seed_bits[wd] = 0u;
-        while (t) {
-            const uint32_t i = wd * 32u + (uint32_t)__ffs(t) - 1u;
-            t &= t - 1u;
-            if (i < n) {
-                const uint32_t r = uf_find(parent, i);
-                atomicAnd(&rootmark[r >> 5], ~(1u << (r & 31u)));
-            }
-        }
-    }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->n_unverified, c);
+}
+
+// Behind the grid barrier that follows taint_phase (nothing reads the marks any more): leave the scratch clean --
+// the marked roots and the seeds.  The last thing the kernel does, so no barrier follows.
+__device__ void taint_cleanup(const ContactArgs& a) {
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const uint32_t words = (a.ctl->n + 31u) / 32u;
+    for (uint32_t wd = gtid; wd < words; wd += gsz) {
+        if (__ldcg(&a.seed_bits[wd])) a.seed_bits[wd] = 0u;
+        if (__ldcg(&a.ra.dirty_bits[wd])) a.ra.dirty_bits[wd] = 0u;
+    }
 }
 
 // Owned bodies (no halo copies; replicated big statics only on the rank that has no left neighbour) -> host layout,
